@@ -1,0 +1,11 @@
+"""Import shim: exposes the package directory ``human-interaction-generation_b200/`` as module ``hig_b200``."""
+import importlib.util
+import os
+import sys
+
+_pkg_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "human-interaction-generation_b200")
+_spec = importlib.util.spec_from_file_location(
+    "hig_b200", os.path.join(_pkg_dir, "__init__.py"), submodule_search_locations=[_pkg_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["hig_b200"] = _mod
+_spec.loader.exec_module(_mod)

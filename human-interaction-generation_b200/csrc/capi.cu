@@ -1,0 +1,81 @@
+// extern "C" boundary of libhig_b200.so — see include/hig_b200.h for the contract of every entry point.
+#include <atomic>
+#include <mutex>
+#include <string>
+#include "hig_internal.h"
+
+namespace hig {
+static std::mutex g_err_mu;
+static std::string g_err;
+static std::atomic<unsigned long long> g_launches{0};
+
+int set_error(int code, const std::string& msg) {
+  std::lock_guard<std::mutex> g(g_err_mu);
+  g_err = msg;
+  return code;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace hig
+
+extern "C" {
+
+int hig_version(void) { return 100; }
+
+const char* hig_last_error(void) {
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> g(hig::g_err_mu);
+  copy = hig::g_err;
+  return copy.c_str();
+}
+
+unsigned long long hig_launch_count(void) { return hig::g_launches.load(std::memory_order_relaxed); }
+
+int hig_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                  const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, void* out_bf16,
+                  int ldo_bf16, int act, void* stream) {
+  return hig::gemm_bf16(A, lda, W, ldw, M, N, K, bias, residual, ldr, res_row_mod, out_f32, ldo_f32, out_bf16,
+                        ldo_bf16, act, static_cast<cudaStream_t>(stream));
+}
+
+int hig_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const float* bias,
+                 const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, int act, void* stream) {
+  return hig::gemm_f32(A, lda, W, ldw, M, N, K, bias, residual, ldr, res_row_mod, out_f32, ldo_f32, act,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int hig_ln_film_silu(const void* x, int x_dtype, int rows, int width, int rows_per_seq, const float* gamma,
+                     const float* beta, const float* scale_shift, int ss_stride, int apply_silu, void* out,
+                     int out_dtype, void* stream) {
+  return hig::ln_film_silu(x, x_dtype, rows, width, rows_per_seq, gamma, beta, scale_shift, ss_stride, apply_silu, out,
+                           out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int hig_eff_attn(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
+                 void* a_out, void* y, int ldy, const int* length, int S, int T, int H, int pair_shift, int mask_v,
+                 int dtype, void* stream) {
+  return hig::eff_attn(mode, q, ldq, k, v, ldkv, a_in, a_out, y, ldy, length, S, T, H, pair_shift, mask_v, dtype,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int hig_timestep_embed(const long long* t, const float* freqs, int S, int half, void* out, int out_dtype,
+                       void* stream) {
+  return hig::timestep_embed(t, freqs, S, half, out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int hig_pack_motion(const float* x, int S, int T, int C, int ld_out, void* out, int out_dtype, void* stream) {
+  return hig::pack_motion(x, S, T, C, ld_out, out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int hig_ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
+                  int n_steps, int S, int T, int C, unsigned long long seed, void* packed, int ld_packed,
+                  int packed_dtype, long long* t_next, void* stream) {
+  return hig::ddpm_step(x, eps, ld_eps, noise, t, coef, n_steps, S, T, C, seed, packed, ld_packed, packed_dtype,
+                        t_next, static_cast<cudaStream_t>(stream));
+}
+
+int hig_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
+                 const float* sqrt_1mac, int S, int TC, float* out, void* stream) {
+  return hig::q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, S, TC, out, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+// Small HBM-bound kernels around the denoiser: timestep embedding, motion packing, the fused DDPM
+// posterior update (one kernel per sampling step) and q_sample for training.
+//
+// Reference: timestep_embedding                  codes/models/interaction_transformer.py:26-43
+//            embed_motion (two_embed layout)     :593-602
+//            p_sample / p_mean_variance / _predict_xstart_from_eps / q_posterior_mean_variance
+//                                                codes/models/gaussian_diffusion.py:606-666, 443-537, 539-544, 419-441
+//            q_sample                            :399-417
+#include "hig_common.cuh"
+#include "hig_internal.h"
+
+namespace hig {
+
+// ------------------------------------------------------------------------------------------------
+// timestep embedding: out[s, :] = [cos(t_s * f_i) | sin(t_s * f_i)],  f = host-computed fp32 table
+// ------------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void timestep_embed_kernel(const long long* __restrict__ t, const float* __restrict__ freqs, int S, int half,
+                                      TOut* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * half) return;
+  const int s = idx / half, i = idx - s * half;
+  const float arg = __fmul_rn(static_cast<float>(t[s]), freqs[i]);
+  out[(size_t)s * 2 * half + i] = static_cast<TOut>(cosf(arg));
+  out[(size_t)s * 2 * half + half + i] = static_cast<TOut>(sinf(arg));
+}
+
+int timestep_embed(const long long* t, const float* freqs, int S, int half, void* out, int out_dtype,
+                   cudaStream_t stream) {
+  if (!t || !freqs || !out || S <= 0 || half <= 0) return set_error(HIG_ERR_INVALID, "timestep_embed: bad arguments");
+  const int n = S * half, blocks = (n + 255) / 256;
+  if (out_dtype == HIG_BF16)
+    timestep_embed_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(t, freqs, S, half, (__nv_bfloat16*)out);
+  else
+    timestep_embed_kernel<float><<<blocks, 256, 0, stream>>>(t, freqs, S, half, (float*)out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("timestep_embed launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack_motion: x fp32 [S,T,C] -> GEMM operand [S*T, ld] such that ONE projection with the augmented weight
+// [joint_embed.weight | joint_embed2.weight | 0] reproduces embed_motion:
+//   row t>=1 : cols [0,C) = x[s,t,:],     cols [C,ld) = 0
+//   row t==0 : cols [0,C) = 0,            cols [C,C+4) = x[s,0,:4], rest 0
+// ------------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void pack_motion_kernel(const float* __restrict__ x, int rows, int T, int C, int ld, TOut* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * ld) return;
+  const int row = (int)(idx / ld), c = (int)(idx - (long long)row * ld);
+  const int t = row % T;
+  float v = 0.f;
+  if (t > 0) {
+    if (c < C) v = x[(size_t)row * C + c];
+  } else {
+    if (c >= C && c < C + 4) v = x[(size_t)row * C + (c - C)];
+  }
+  out[idx] = static_cast<TOut>(v);
+}
+
+int pack_motion(const float* x, int S, int T, int C, int ld_out, void* out, int out_dtype, cudaStream_t stream) {
+  if (!x || !out || S <= 0 || T <= 0 || C <= 0 || ld_out < C + 4)
+    return set_error(HIG_ERR_INVALID, "pack_motion: bad arguments");
+  const long long n = (long long)S * T * ld_out;
+  const int blocks = (int)((n + 255) / 256);
+  if (out_dtype == HIG_BF16)
+    pack_motion_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(x, S * T, T, C, ld_out, (__nv_bfloat16*)out);
+  else
+    pack_motion_kernel<float><<<blocks, 256, 0, stream>>>(x, S * T, T, C, ld_out, (float*)out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("pack_motion launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller (production noise; parity runs inject a noise tensor instead)
+// ------------------------------------------------------------------------------------------------
+HIG_DEVICE uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+HIG_DEVICE float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = (static_cast<float>(a) + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+  const float u2 = static_cast<float>(b) * 2.3283064365386963e-10f;           // [0,1)
+  const float r = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ddpm_step: x <- c1_t (r_t x - m_t eps) + c2_t x + 1[t>0] sigma_t z          (fp32, reference op order, no FMA
+// contraction) and, in the same pass, the packed GEMM operand of the next denoiser call.
+// coef = [5][n_steps] fp32: r = sqrt(1/abar), m = sqrt(1/abar - 1), c1, c2, sigma = exp(0.5*logvar_clipped)
+// ------------------------------------------------------------------------------------------------
+template <typename TPack>
+__global__ void __launch_bounds__(256)
+ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, int ld_eps, const float* __restrict__ noise,
+                 const long long* __restrict__ t, const float* __restrict__ coef, int n_steps, int S, int T, int C,
+                 unsigned long long seed, TPack* __restrict__ packed, int ld_packed) {
+  const long long per_seq = (long long)T * C;
+  const long long total = (long long)S * per_seq;
+  const long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (base >= total) return;
+  float z[4] = {0.f, 0.f, 0.f, 0.f};
+  if (noise) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (base + j < total) z[j] = noise[base + j];
+  } else {
+    // counter = (element-group index, timestep of the first element's sequence), key = seed
+    const int s0 = (int)(base / per_seq);
+    const long long ts = t[s0];
+    const uint4 ctr = make_uint4((uint32_t)(base >> 2), (uint32_t)((base >> 2) >> 32), (uint32_t)ts, 0x48494742u);
+    const uint4 rnd = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float2 n0 = box_muller(rnd.x, rnd.y), n1 = box_muller(rnd.z, rnd.w);
+    z[0] = n0.x; z[1] = n0.y; z[2] = n1.x; z[3] = n1.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long idx = base + j;
+    if (idx >= total) break;
+    const int s = (int)(idx / per_seq);
+    const int rem = (int)(idx - (long long)s * per_seq);
+    const int tt = rem / C, c = rem - tt * C;
+    long long ts = t[s];
+    ts = ts < 0 ? 0 : (ts >= n_steps ? n_steps - 1 : ts);
+    const float r = coef[ts], m = coef[n_steps + ts], c1 = coef[2 * n_steps + ts], c2 = coef[3 * n_steps + ts];
+    const float sigma = ts > 0 ? coef[4 * n_steps + ts] : 0.f;
+    const float xv = x[idx];
+    const float ev = eps[((size_t)s * T + tt) * ld_eps + c];
+    const float x0 = __fsub_rn(__fmul_rn(r, xv), __fmul_rn(m, ev));
+    const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv));
+    const float xn = __fadd_rn(mean, __fmul_rn(sigma, z[j]));
+    x[idx] = xn;
+    if (packed) {
+      TPack* prow = packed + ((size_t)s * T + tt) * ld_packed;
+      if (tt > 0) prow[c] = static_cast<TPack>(xn);
+      else if (c < 4) prow[C + c] = static_cast<TPack>(xn);
+    }
+  }
+}
+
+__global__ void advance_t_kernel(const long long* __restrict__ t, long long* __restrict__ t_next, int S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S) t_next[i] = t[i] - 1;
+}
+
+int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
+              int n_steps, int S, int T, int C, unsigned long long seed, void* packed, int ld_packed, int packed_dtype,
+              long long* t_next, cudaStream_t stream) {
+  if (!x || !eps || !t || !coef || S <= 0 || T <= 0 || C <= 0 || n_steps <= 0)
+    return set_error(HIG_ERR_INVALID, "ddpm_step: bad arguments");
+  if (packed && ld_packed < C + 4) return set_error(HIG_ERR_INVALID, "ddpm_step: ld_packed < C+4");
+  const long long total = (long long)S * T * C;
+  const int blocks = (int)(((total + 3) / 4 + 255) / 256);
+  if (packed && packed_dtype == HIG_BF16)
+    ddpm_step_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(x, eps, ld_eps, noise, t, coef, n_steps, S, T, C, seed,
+                                                               (__nv_bfloat16*)packed, ld_packed);
+  else
+    ddpm_step_kernel<float><<<blocks, 256, 0, stream>>>(x, eps, ld_eps, noise, t, coef, n_steps, S, T, C, seed,
+                                                        (float*)packed, ld_packed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("ddpm_step launch: ") + cudaGetErrorString(e));
+  count_launch();
+  if (t_next) {
+    advance_t_kernel<<<(S + 255) / 256, 256, 0, stream>>>(t, t_next, S);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("advance_t launch: ") + cudaGetErrorString(e));
+    count_launch();
+  }
+  return HIG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// q_sample: x_t = sqrt(abar_t) x0 + sqrt(1-abar_t) noise    (per-sequence t)
+// ------------------------------------------------------------------------------------------------
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                const long long* __restrict__ t, const float* __restrict__ sqrt_ac,
+                                const float* __restrict__ sqrt_1mac, long long total, int TC, float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long ts = t[idx / TC];
+  out[idx] = __fadd_rn(__fmul_rn(sqrt_ac[ts], x0[idx]), __fmul_rn(sqrt_1mac[ts], noise[idx]));
+}
+
+int q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac, const float* sqrt_1mac,
+             int S, int TC, float* out, cudaStream_t stream) {
+  if (!x0 || !noise || !t || !sqrt_ac || !sqrt_1mac || !out || S <= 0 || TC <= 0)
+    return set_error(HIG_ERR_INVALID, "q_sample: bad arguments");
+  const long long total = (long long)S * TC;
+  q_sample_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(x0, noise, t, sqrt_ac, sqrt_1mac, total, TC, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("q_sample launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+}  // namespace hig

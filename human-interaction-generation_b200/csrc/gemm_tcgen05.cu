@@ -1,0 +1,377 @@
+// hig_gemm_bf16: C[M,N] = act( A[M,K] · W[N,K]^T + bias + residual )       (bf16 in, fp32 accumulate)
+//
+// Every dense projection of the denoiser runs through this kernel: QKV / Q / out-proj / FFN / stylization
+// emb linears / joint embed / output heads  (reference: nn.Linear call sites in
+// codes/models/interaction_transformer.py:74-97,105-128,137-163,172-205,254-263,471-478,508-509).
+//
+// Design (B200, sm_100a):
+//   * persistent grid, one CTA per SM, static round-robin tile scheduler (n fastest so the CTAs that share an
+//     A row-panel run together and hit L2);
+//   * warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx),
+//     warp 1 = tcgen05.mma issuer (single elected thread) + TMEM allocator,
+//     warps 2..5 = epilogue (tcgen05.ld 32x32b -> registers -> bias/residual/activation -> global);
+//   * 128 x BN x 64 tiles, STAGES-deep smem ring, accumulator double-buffered in TMEM (2 x BN columns) so the
+//     epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include "hig_common.cuh"
+#include "hig_internal.h"
+
+namespace hig {
+
+struct GemmEpilogue {
+  const float* bias;      // [N] or nullptr
+  const float* residual;  // fp32 [rows, ldr] or nullptr
+  int ldr;
+  int res_row_mod;        // >0: residual row = m % res_row_mod (positional tables)
+  float* out_f32;         // nullable
+  int ldo_f32;
+  __nv_bfloat16* out_bf16;  // nullable
+  int ldo_bf16;
+  int act;                // 0 none, 1 GELU(erf), 2 SiLU
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int TOTAL = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;  // +1024 for manual alignment
+};
+
+template <bool kVec>
+HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const GemmEpilogue& ep, int row, bool row_ok, int col0, int N) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+
+  if (kVec) {
+    if (ep.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = __ldg(b4 + j);
+        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+    }
+    if (!row_ok) return;
+    if (ep.residual) {
+      const int rr = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
+      const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (size_t)rr * ep.ldr + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = __ldg(r4 + j);
+        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+    }
+    if (ep.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+    } else if (ep.act == 2) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+    }
+    if (ep.out_f32) {
+      float4* o4 = reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ldo_f32 + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    if (ep.out_bf16) {
+      uint4* o4 = reinterpret_cast<uint4*>(ep.out_bf16 + (size_t)row * ep.ldo_bf16 + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 p;
+        p.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        p.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        p.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        p.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        o4[j] = p;
+      }
+    }
+  } else {
+    if (!row_ok) return;
+    const int rr = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      if (col < N) {
+        float x = v[j];
+        if (ep.bias) x += __ldg(ep.bias + col);
+        if (ep.residual) x += __ldg(ep.residual + (size_t)rr * ep.ldr + col);
+        if (ep.act == 1) x = gelu_erf_f(x);
+        else if (ep.act == 2) x = silu_f(x);
+        if (ep.out_f32) ep.out_f32[(size_t)row * ep.ldo_f32 + col] = x;
+        if (ep.out_bf16) ep.out_bf16[(size_t)row * ep.ldo_bf16 + col] = __float2bfloat16(x);
+      }
+    }
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         int M, int N, int K, GemmEpilogue ep, int vec_ok) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * L::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * L::B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + s, 1);
+      mbar_init(tempty_bar + s, 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<2 * BN>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % n_tiles;
+        const int m_blk = tile / n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t stage = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1u;
+          mbar_wait(empty_bar + stage, phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar + stage, L::A_BYTES + L::B_BYTES);
+          tma_load_2d(sA + stage * L::A_BYTES, &tmA, full_bar + stage, kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(sB + stage * L::B_BYTES, &tmB, full_bar + stage, kb * GEMM_BK, n_blk * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      uint32_t it = 0;
+      uint32_t lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t as = lt & 1u;
+        const uint32_t aphase = (lt >> 1) & 1u;
+        mbar_wait(tempty_bar + as, aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t stage = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1u;
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * L::A_BYTES));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * L::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in 16-byte units
+            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
+        }
+        umma_commit(tfull_bar + as);  // accumulator ready for the epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue warps (2..5) =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int n_blk = tile % n_tiles;
+      const int m_blk = tile / n_tiles;
+      const uint32_t as = lt & 1u;
+      const uint32_t aphase = (lt >> 1) & 1u;
+      mbar_wait(tfull_bar + as, aphase);
+      tc_fence_after();
+      const int row = m_blk * GEMM_BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        const int col0 = n_blk * BN + c;
+        if (col0 >= N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+        if (vec_ok && col0 + 32 <= N) epilogue_chunk<true>(r, ep, row, row_ok, col0, N);
+        else epilogue_chunk<false>(r, ep, row, row_ok, col0, N);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + as);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side: tensor-map cache + launcher
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr; int rows, cols, ld, box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (h << 6);
+    h ^= (size_t)k.cols * 0xC2B2AE3D27D4EB4Full + (h >> 3);
+    h ^= (size_t)k.ld * 0x165667B19E3779F9ull + (h << 9);
+    h ^= (size_t)k.box_rows * 0x27D4EB2F165667C5ull;
+    return h;
+  }
+};
+
+// bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle
+static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  TmapKey key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto itr = cache.find(key);
+    if (itr != cache.end()) { *out = itr->second; return HIG_OK; }
+  }
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return set_error(HIG_ERR_NO_DRIVER, "cuTensorMapEncodeTiled not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap tm;
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(HIG_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = tm;
+  }
+  *out = tm;
+  return HIG_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
+                       int vec_ok, cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  static bool attr_set = false;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  int grid = m_tiles * n_tiles;
+  if (grid > num_sms()) grid = num_sms();
+  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, M, N, K, ep, vec_ok);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+              const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, void* out_bf16,
+              int ldo_bf16, int act, cudaStream_t stream) {
+  if (!A || !W || M <= 0 || N <= 0 || K <= 0) return set_error(HIG_ERR_INVALID, "gemm: null operand or empty shape");
+  if (!out_f32 && !out_bf16) return set_error(HIG_ERR_INVALID, "gemm: no output");
+  if ((lda % 8) || (ldw % 8) || (K % 8)) return set_error(HIG_ERR_INVALID, "gemm: lda/ldw/K must be multiples of 8 (TMA 16B rule)");
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return set_error(HIG_ERR_INVALID, "gemm: operands must be 16-byte aligned");
+  if (act < 0 || act > 2) return set_error(HIG_ERR_INVALID, "gemm: bad activation");
+
+  GemmEpilogue ep;
+  ep.bias = bias; ep.residual = residual; ep.ldr = ldr; ep.res_row_mod = res_row_mod;
+  ep.out_f32 = out_f32; ep.ldo_f32 = ldo_f32;
+  ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); ep.ldo_bf16 = ldo_bf16;
+  ep.act = act;
+
+  int vec_ok = 1;
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) vec_ok = 0;
+  if (residual && ((reinterpret_cast<uintptr_t>(residual) & 15) || (ldr % 4))) vec_ok = 0;
+  if (out_f32 && ((reinterpret_cast<uintptr_t>(out_f32) & 15) || (ldo_f32 % 4))) vec_ok = 0;
+  if (out_bf16 && ((reinterpret_cast<uintptr_t>(out_bf16) & 15) || (ldo_bf16 % 8))) vec_ok = 0;
+
+  const bool big_n = N > 128;
+  CUtensorMap tmA, tmB;
+  int rc = get_tmap(A, M, K, lda, GEMM_BM, &tmA);
+  if (rc) return rc;
+  rc = get_tmap(W, N, K, ldw, big_n ? 256 : 128, &tmB);
+  if (rc) return rc;
+  if (big_n) return launch_gemm<256, 4>(tmA, tmB, M, N, K, ep, vec_ok, stream);
+  return launch_gemm<128, 6>(tmA, tmB, M, N, K, ep, vec_ok, stream);
+}
+
+}  // namespace hig

@@ -1,0 +1,42 @@
+// Internal (C++) interfaces between the kernel translation units and the C ABI in capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include "../../include/hig_b200.h"  // HIG_OK / HIG_ERR_* / HIG_BF16 / HIG_F32
+
+namespace hig {
+
+// records a message retrievable through hig_last_error() and returns `code`
+int set_error(int code, const std::string& msg);
+// every kernel launch made by this library bumps a process-wide counter (hig_launch_count)
+void count_launch();
+
+int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+              const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, void* out_bf16,
+              int ldo_bf16, int act, cudaStream_t stream);
+
+int gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const float* bias,
+             const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, int act,
+             cudaStream_t stream);
+
+int ln_film_silu(const void* x, int x_dtype, int rows, int width, int rows_per_seq, const float* gamma,
+                 const float* beta, const float* scale_shift, int ss_stride, int apply_silu, void* out, int out_dtype,
+                 cudaStream_t stream);
+
+int eff_attn(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in, void* a_out,
+             void* y, int ldy, const int* length, int S, int T, int H, int pair_shift, int mask_v, int dtype,
+             cudaStream_t stream);
+
+int timestep_embed(const long long* t, const float* freqs, int S, int half, void* out, int out_dtype,
+                   cudaStream_t stream);
+
+int pack_motion(const float* x, int S, int T, int C, int ld_out, void* out, int out_dtype, cudaStream_t stream);
+
+int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
+              int n_steps, int S, int T, int C, unsigned long long seed, void* packed, int ld_packed, int packed_dtype,
+              long long* t_next, cudaStream_t stream);
+
+int q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac, const float* sqrt_1mac,
+             int S, int TC, float* out, cudaStream_t stream);
+
+}  // namespace hig

@@ -1,0 +1,138 @@
+// hig_ln_film_silu: fused LayerNorm (+ FiLM scale/shift from the timestep/text embedding) (+ SiLU).
+//
+// Replaces, in one coalesced pass, the chain  nn.LayerNorm -> h*(1+scale)+shift -> nn.SiLU  of
+// StylizationBlock.forward (codes/models/interaction_transformer.py:86-97) and the plain pre-attention
+// LayerNorms (:119,153,155,190,194).  The reference computes self.norm(x) three times per attention block;
+// here it is computed once and written in the GEMM operand type.
+//
+// One warp per row (row width 512 = latent_dim, or 256 = text_latent_dim); every lane owns 8 contiguous
+// elements per 256-wide chunk, so loads are 2x float4 (fp32 in) or 1x uint4 (bf16 in) and stores are 16 B.
+// Statistics are two-pass in registers (mean, then centred variance) in fp32, eps = 1e-5, biased variance —
+// the same arithmetic as ATen's native_layer_norm.
+#include "hig_common.cuh"
+#include "hig_internal.h"
+
+namespace hig {
+
+template <typename T> struct Io;
+template <> struct Io<float> {
+  static HIG_DEVICE void load8(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static HIG_DEVICE void store8(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Io<__nv_bfloat16> {
+  static HIG_DEVICE void load8(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    float2 f;
+    f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+    f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+    f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+    f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+  }
+  static HIG_DEVICE void store8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
+template <int WIDTH, typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+ln_film_silu_kernel(const TIn* __restrict__ x, int rows, int rows_per_seq, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ scale_shift, int ss_stride,
+                    int apply_silu, TOut* __restrict__ out) {
+  constexpr int CHUNKS = WIDTH / 256;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const TIn* xr = x + (size_t)row * WIDTH;
+  float v[CHUNKS][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    Io<TIn>::load8(xr + c * 256 + lane * 8, v[c]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[c][j];
+  }
+  const float mean = warp_sum(s) * (1.0f / WIDTH);
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[c][j] - mean;
+      ss = fmaf(d, d, ss);
+    }
+  const float var = warp_sum(ss) * (1.0f / WIDTH);
+  const float rstd = 1.0f / sqrtf(var + 1e-5f);
+
+  const float* ssp = scale_shift ? scale_shift + (size_t)(row / rows_per_seq) * ss_stride : nullptr;
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col = c * 256 + lane * 8;
+    float g[8], b[8];
+    Io<float>::load8(gamma + col, g);
+    Io<float>::load8(beta + col, b);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[j] + b[j];
+    if (ssp) {
+      float sc[8], sh[8];
+      Io<float>::load8(ssp + col, sc);
+      Io<float>::load8(ssp + WIDTH + col, sh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = o[j] * (1.0f + sc[j]) + sh[j];
+    }
+    if (apply_silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = o[j] / (1.0f + expf(-o[j]));
+    }
+    Io<TOut>::store8(out + (size_t)row * WIDTH + col, o);
+  }
+}
+
+template <int WIDTH, typename TIn, typename TOut>
+static void launch_ln(const void* x, int rows, int rows_per_seq, const float* gamma, const float* beta,
+                      const float* scale_shift, int ss_stride, int apply_silu, void* out, cudaStream_t stream) {
+  const int blocks = (rows + 7) / 8;
+  ln_film_silu_kernel<WIDTH, TIn, TOut><<<blocks, 256, 0, stream>>>(
+      reinterpret_cast<const TIn*>(x), rows, rows_per_seq, gamma, beta, scale_shift, ss_stride, apply_silu,
+      reinterpret_cast<TOut*>(out));
+}
+
+int ln_film_silu(const void* x, int x_dtype, int rows, int width, int rows_per_seq, const float* gamma,
+                 const float* beta, const float* scale_shift, int ss_stride, int apply_silu, void* out, int out_dtype,
+                 cudaStream_t stream) {
+  if (!x || !out || !gamma || !beta || rows <= 0) return set_error(HIG_ERR_INVALID, "ln_film_silu: bad arguments");
+  if (width != 512 && width != 256) return set_error(HIG_ERR_UNSUPPORTED, "ln_film_silu: width must be 256 or 512");
+  if (rows_per_seq <= 0) rows_per_seq = 1;
+  if (scale_shift && (ss_stride % 4)) return set_error(HIG_ERR_INVALID, "ln_film_silu: ss_stride % 4 != 0");
+  using bf = __nv_bfloat16;
+#define HIG_LN_CASE(W, TI, TO) \
+  launch_ln<W, TI, TO>(x, rows, rows_per_seq, gamma, beta, scale_shift, ss_stride, apply_silu, out, stream)
+  if (width == 512) {
+    if (x_dtype == HIG_F32 && out_dtype == HIG_BF16) HIG_LN_CASE(512, float, bf);
+    else if (x_dtype == HIG_BF16 && out_dtype == HIG_BF16) HIG_LN_CASE(512, bf, bf);
+    else if (x_dtype == HIG_F32 && out_dtype == HIG_F32) HIG_LN_CASE(512, float, float);
+    else return set_error(HIG_ERR_UNSUPPORTED, "ln_film_silu: dtype combination");
+  } else {
+    if (x_dtype == HIG_F32 && out_dtype == HIG_BF16) HIG_LN_CASE(256, float, bf);
+    else if (x_dtype == HIG_BF16 && out_dtype == HIG_BF16) HIG_LN_CASE(256, bf, bf);
+    else if (x_dtype == HIG_F32 && out_dtype == HIG_F32) HIG_LN_CASE(256, float, float);
+    else return set_error(HIG_ERR_UNSUPPORTED, "ln_film_silu: dtype combination");
+  }
+#undef HIG_LN_CASE
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("ln_film_silu launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+}  // namespace hig

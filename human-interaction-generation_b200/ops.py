@@ -1,0 +1,157 @@
+"""Tensor-level wrappers over the C ABI (include/hig_b200.h).  PyTorch supplies device memory and the current
+stream only; all arithmetic happens in the sm_100a kernels of csrc/.  CPU tensors are rejected — there is no
+fallback path.
+"""
+import torch
+
+from . import _lib
+
+BF16, F32 = 0, 1
+ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
+ATTN_SELF, ATTN_INTER, ATTN_KV_ONLY, ATTN_Q_ONLY = 0, 1, 2, 3
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError(f"hig_b200: unsupported dtype {t.dtype}")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("hig_b200: CUDA tensor required (no CPU fallback)")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rowmajor(t, what):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"hig_b200: {what} must be 2-D with unit inner stride, got {tuple(t.shape)} {t.stride()}")
+    return t.stride(0)
+
+
+def gemm(a, w, bias=None, residual=None, res_row_mod=0, out_f32=None, out_bf16=None, act=ACT_NONE):
+    """act(a @ w.T + bias + residual).  a [M,K], w [N,K] (both bf16 -> tcgen05 kernel; both fp32 -> fp32 mode)."""
+    lib = _lib.load()
+    M, K = a.shape
+    N = w.shape[0]
+    lda, ldw = _rowmajor(a, "A"), _rowmajor(w, "W")
+    if w.shape[1] != K:
+        raise ValueError("hig_b200.gemm: K mismatch")
+    ldr = _rowmajor(residual, "residual") if residual is not None else 0
+    if residual is not None and residual.dtype != torch.float32:
+        raise TypeError("hig_b200.gemm: residual must be fp32")
+    if bias is not None and bias.dtype != torch.float32:
+        raise TypeError("hig_b200.gemm: bias must be fp32")
+    if a.dtype == torch.bfloat16:
+        if w.dtype != torch.bfloat16:
+            raise TypeError("hig_b200.gemm: A/W dtype mismatch")
+        if out_f32 is None and out_bf16 is None:
+            out_bf16 = torch.empty((M, N), device=a.device, dtype=torch.bfloat16)
+        rc = lib.hig_gemm_bf16(_ptr(a), lda, _ptr(w), ldw, M, N, K, _ptr(bias), _ptr(residual), ldr, res_row_mod,
+                               _ptr(out_f32), _rowmajor(out_f32, "out_f32") if out_f32 is not None else 0,
+                               _ptr(out_bf16), _rowmajor(out_bf16, "out_bf16") if out_bf16 is not None else 0,
+                               act, _stream())
+        _lib.check(rc, "hig_gemm_bf16")
+        return out_f32 if out_bf16 is None else (out_bf16 if out_f32 is None else (out_f32, out_bf16))
+    if a.dtype == torch.float32:
+        if w.dtype != torch.float32 or out_bf16 is not None:
+            raise TypeError("hig_b200.gemm: fp32 mode takes fp32 W and fp32 output")
+        if out_f32 is None:
+            out_f32 = torch.empty((M, N), device=a.device, dtype=torch.float32)
+        rc = lib.hig_gemm_f32(_ptr(a), lda, _ptr(w), ldw, M, N, K, _ptr(bias), _ptr(residual), ldr, res_row_mod,
+                              _ptr(out_f32), _rowmajor(out_f32, "out_f32"), act, _stream())
+        _lib.check(rc, "hig_gemm_f32")
+        return out_f32
+    raise TypeError(f"hig_b200.gemm: unsupported dtype {a.dtype}")
+
+
+def ln_film_silu(x, gamma, beta, out, rows_per_seq=1, scale_shift=None, silu=False):
+    """out = [SiLU](LN(x) * (1 + scale) + shift); x [rows, W] (W in {256, 512}); scale_shift fp32 view [S, >=2W]."""
+    lib = _lib.load()
+    rows, width = x.shape
+    if not x.is_contiguous() or not out.is_contiguous():
+        raise ValueError("hig_b200.ln_film_silu: contiguous tensors required")
+    ss_stride = 0
+    if scale_shift is not None:
+        if scale_shift.dtype != torch.float32 or scale_shift.stride(1) != 1:
+            raise ValueError("hig_b200.ln_film_silu: scale_shift must be fp32 with unit inner stride")
+        ss_stride = scale_shift.stride(0)
+    rc = lib.hig_ln_film_silu(_ptr(x), _dt(x), rows, width, rows_per_seq, _ptr(gamma), _ptr(beta),
+                              _ptr(scale_shift), ss_stride, 1 if silu else 0, _ptr(out), _dt(out), _stream())
+    _lib.check(rc, "hig_ln_film_silu")
+    return out
+
+
+def eff_attn(mode, S, T, H, q=None, k=None, v=None, a_in=None, a_out=None, y=None, length=None, pair_shift=0,
+             mask_v=True):
+    """Fused efficient attention; q/k/v/y are 2-D views [S*T, ld] positioned at head 0."""
+    lib = _lib.load()
+    ref = q if q is not None else k
+    dt = _dt(ref)
+    ldq = q.stride(0) if q is not None else 0
+    ldkv = k.stride(0) if k is not None else 0
+    if k is not None and v.stride(0) != ldkv:
+        raise ValueError("hig_b200.eff_attn: K and V must share a leading dimension")
+    ldy = y.stride(0) if y is not None else 0
+    if length is not None and length.dtype != torch.int32:
+        raise TypeError("hig_b200.eff_attn: length must be int32")
+    rc = lib.hig_eff_attn(mode, _ptr(q), ldq, _ptr(k), _ptr(v), ldkv, _ptr(a_in), _ptr(a_out), _ptr(y), ldy,
+                          _ptr(length), S, T, H, pair_shift, 1 if mask_v else 0, dt, _stream())
+    _lib.check(rc, "hig_eff_attn")
+    return y if y is not None else a_out
+
+
+def timestep_embed(t, freqs, out):
+    lib = _lib.load()
+    if t.dtype != torch.int64:
+        raise TypeError("hig_b200.timestep_embed: t must be int64")
+    S, half = t.shape[0], freqs.shape[0]
+    rc = lib.hig_timestep_embed(_ptr(t), _ptr(freqs), S, half, _ptr(out), _dt(out), _stream())
+    _lib.check(rc, "hig_timestep_embed")
+    return out
+
+
+def pack_motion(x, out):
+    lib = _lib.load()
+    S, T, C = x.shape
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("hig_b200.pack_motion: x must be contiguous fp32")
+    rc = lib.hig_pack_motion(_ptr(x), S, T, C, out.stride(0), _ptr(out), _dt(out), _stream())
+    _lib.check(rc, "hig_pack_motion")
+    return out
+
+
+def ddpm_step(x, eps, t, coef, noise=None, seed=0, packed=None, t_next=None):
+    """In-place x <- posterior sample; eps [S*T, ld_eps] fp32 view, coef fp32 [5, n_steps]."""
+    lib = _lib.load()
+    S, T, C = x.shape
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("hig_b200.ddpm_step: x must be contiguous fp32")
+    if noise is not None and (noise.dtype != torch.float32 or not noise.is_contiguous()):
+        raise ValueError("hig_b200.ddpm_step: noise must be contiguous fp32")
+    eps2 = eps.reshape(S * T, -1) if eps.dim() == 3 else eps
+    rc = lib.hig_ddpm_step(_ptr(x), _ptr(eps2), eps2.stride(0), _ptr(noise), _ptr(t), _ptr(coef), coef.shape[1],
+                           S, T, C, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(packed),
+                           packed.stride(0) if packed is not None else 0,
+                           _dt(packed) if packed is not None else F32, _ptr(t_next), _stream())
+    _lib.check(rc, "hig_ddpm_step")
+    return x
+
+
+def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, out=None):
+    lib = _lib.load()
+    S = x0.shape[0]
+    TC = x0.numel() // S
+    if out is None:
+        out = torch.empty_like(x0)
+    rc = lib.hig_q_sample(_ptr(x0), _ptr(noise), _ptr(t), _ptr(sqrt_ac), _ptr(sqrt_1mac), S, TC, _ptr(out), _stream())
+    _lib.check(rc, "hig_q_sample")
+    return out

@@ -1,0 +1,98 @@
+/* hig_b200 — C ABI of the B200-native denoising hot path of line/Human-Interaction-Generation.
+ *
+ * The reference has no FFI: its hot path is PyTorch eager code.  Each entry point below names the reference
+ * Python it replaces (paths relative to the reference's codes/ directory).  All pointers are DEVICE pointers
+ * owned by the caller (PyTorch), nothing is allocated inside, every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*), and every call returns 0 or a negative HIG_ERR_* code
+ * (message via hig_last_error()).  There is no CPU fallback: without a CUDA device the calls fail.
+ *
+ * dtype arguments: HIG_BF16 (0) = __nv_bfloat16 storage, HIG_F32 (1) = float storage ("fp32 mode").
+ */
+#ifndef HIG_B200_H
+#define HIG_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HIG_OK 0
+#define HIG_ERR_INVALID (-1)
+#define HIG_ERR_CUDA (-2)
+#define HIG_ERR_UNSUPPORTED (-3)
+#define HIG_ERR_NO_DRIVER (-4)
+
+#define HIG_BF16 0
+#define HIG_F32 1
+
+#define HIG_ACT_NONE 0
+#define HIG_ACT_GELU 1 /* exact erf GELU, nn.GELU() */
+#define HIG_ACT_SILU 2
+
+#define HIG_ATTN_SELF 0    /* LinearTemporalSelfAttention              models/interaction_transformer.py:112-130 */
+#define HIG_ATTN_INTER 1   /* LinearTemporalInteractionCrossAttention  models/interaction_transformer.py:181-207 */
+#define HIG_ATTN_KV_ONLY 2 /* LinearTemporalCrossAttention, K/V half   models/interaction_transformer.py:155-161 */
+#define HIG_ATTN_Q_ONLY 3  /* LinearTemporalCrossAttention, Q half     models/interaction_transformer.py:153,156,162 */
+
+/* library info */
+int hig_version(void);
+const char* hig_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long hig_launch_count(void);
+
+/* out = act(A[M,K] . W[N,K]^T + bias + residual), bf16 operands, fp32 accumulate on tcgen05/TMEM.
+ * Replaces every nn.Linear on the path (models/interaction_transformer.py:74-97,105-128,137-163,172-205,
+ * 254-263,471-478,508-509) with the bias add, GELU (FFN, :262), SiLU (time_embed, :476) and the residual
+ * `x + proj_out(...)` (:129,164,203,263) fused in the epilogue.
+ * lda/ldw/K multiples of 8; residual is fp32 [*, ldr], row = m % res_row_mod when res_row_mod > 0;
+ * either/both of out_f32 / out_bf16 may be given. */
+int hig_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                  const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, void* out_bf16,
+                  int ldo_bf16, int act, void* stream);
+
+/* the same contract in fp32 storage and fp32 FFMA arithmetic ("fp32 mode", parity <= 1e-5) */
+int hig_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const float* bias,
+                 const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, int act, void* stream);
+
+/* out = [SiLU]( LayerNorm(x; gamma, beta, eps=1e-5) * (1 + scale[s]) + shift[s] ), s = row / rows_per_seq.
+ * Replaces StylizationBlock.forward's norm/FiLM/SiLU (models/interaction_transformer.py:86-97) and the
+ * pre-attention LayerNorms (:119,153,155,190,194).  scale_shift (nullable) points at fp32
+ * [S, ss_stride] with scale at [0,width) and shift at [width, 2*width) of each row.  width = 512 or 256. */
+int hig_ln_film_silu(const void* x, int x_dtype, int rows, int width, int rows_per_seq, const float* gamma,
+                     const float* beta, const float* scale_shift, int ss_stride, int apply_silu, void* out,
+                     int out_dtype, void* stream);
+
+/* fused efficient attention, one CTA per (sequence, head), head dim 64; see HIG_ATTN_* for the reference lines.
+ * q [S*T, ldq], k/v [S*T, ldkv] (pointers at head 0), y [S*T, ldy]; a_in/a_out [S,H,64,64] (dtype storage);
+ * length int32 [S] (nullable = no mask); INTER reads K,V of sequence (s + pair_shift) % S and masks with
+ * length[s] (the reference's query-side quirk, :194). */
+int hig_eff_attn(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
+                 void* a_out, void* y, int ldy, const int* length, int S, int T, int H, int pair_shift, int mask_v,
+                 int dtype, void* stream);
+
+/* out[s] = [cos(t_s f) | sin(t_s f)] — timestep_embedding (models/interaction_transformer.py:26-43);
+ * freqs = fp32 [half] table computed once on the host exactly as the reference does. */
+int hig_timestep_embed(const long long* t, const float* freqs, int S, int half, void* out, int out_dtype,
+                       void* stream);
+
+/* x fp32 [S,T,C] -> operand [S*T, ld_out] laid out so one GEMM with [joint_embed.weight | joint_embed2.weight]
+ * reproduces embed_motion (models/interaction_transformer.py:593-602). */
+int hig_pack_motion(const float* x, int S, int T, int C, int ld_out, void* out, int out_dtype, void* stream);
+
+/* one reverse-diffusion update, in place on x: p_sample + p_mean_variance (EPSILON / FIXED_SMALL,
+ * clip_denoised=False) — models/gaussian_diffusion.py:606-666,443-537.  coef = fp32 [5][n_steps]
+ * {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2,
+ * exp(0.5*posterior_log_variance_clipped)}.  noise nullable -> Philox4x32-10(seed, t, index) + Box-Muller.
+ * packed nullable: also writes the next step's pack_motion operand.  t_next nullable: t_next[s] = t[s]-1
+ * (may alias t; issued as a trailing launch). */
+int hig_ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
+                  int n_steps, int S, int T, int C, unsigned long long seed, void* packed, int ld_packed,
+                  int packed_dtype, long long* t_next, void* stream);
+
+/* x_t = sqrt(abar_t) x0 + sqrt(1 - abar_t) noise — GaussianDiffusion.q_sample (models/gaussian_diffusion.py:399-417) */
+int hig_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
+                 const float* sqrt_1mac, int S, int TC, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIG_B200_H */
