@@ -1,0 +1,269 @@
+"""DenoiserEngine — the kernel schedule of one role-aware denoiser forward on a B200.
+
+Owns (a) the packed weights (fp32 master parameters -> bf16 GEMM operands, Q/K/V and all 4L stylization
+emb-linears concatenated, joint_embed/joint_embed2 fused into one K-padded operand) and (b) persistent
+activation workspaces in HBM, and issues the C-ABI kernels in order on the current stream.  No torch math on
+the path: torch only allocates the buffers.  The whole schedule is capturable in a CUDA graph (no allocation,
+no host sync, tensor maps are kernel parameters) — gaussian_diffusion.p_sample_loop does exactly that.
+
+HBM layout for S sequences x T frames (tok = S*T rows, D = 512):
+  xres  fp32 [tok, 512]   residual stream (kept fp32: 32 residual adds per step would cost ~0.6% in bf16)
+  xb    act  [tok, 512]   copy of the residual stream in the GEMM operand type (FFN / output heads read it)
+  n     act  [tok, 512]   LayerNorm output feeding the Q/K/V projections
+  qkv   act  [tok, 1536]  projections (Q | K | V), also reused as [tok, 512] for the text-CA query
+  y     act  [tok, 512]   attention / FFN branch output
+  sact  act  [tok, 512]   SiLU(FiLM(LN(y))) feeding the block's output projection
+  g     act  [tok, 1024]  GELU(linear1)
+  ss    fp32 [S, 4L*1024] (scale | shift) of every StylizationBlock, one GEMM per step
+  eps   fp32 [tok, 264]   network output (leading dim padded 263 -> 264 for 16-byte rows)
+"act" = bf16 in the product path, fp32 in fp32 mode.
+Reference: MotionInteractionTransformer.forward, codes/models/interaction_transformer.py:577-616.
+"""
+import math
+
+import torch
+
+from . import ops
+
+HEAD_DIM = 64
+
+
+class DenoiserEngine:
+    def __init__(self, module, precision="bf16"):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.m = module
+        self.precision = precision
+        self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.D = module.latent_dim
+        self.F = module.ff_size
+        self.E = module.time_embed_dim
+        self.C = module.input_feats
+        self.H = module.num_heads
+        self.L = module.num_layers
+        self.has_ic = not module.no_cross_attn
+        if self.D != 512 or self.D // self.H != HEAD_DIM:
+            raise NotImplementedError("hig_b200 kernels are built for latent_dim=512, head_dim=64 (the repo default)")
+        self.CP = (self.C + 4 + 7) // 8 * 8          # 263 + 4 -> 272: K padded for TMA's 16-byte rule
+        self.LD_EPS = (self.C + 3) // 4 * 4          # 264
+        self._packed = None
+        self._packed_key = None
+        self._ws = {}
+        self._text_cache = None
+
+    # ------------------------------------------------------------------------------------------ weights
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.m.parameters())
+
+    def packed(self):
+        key = self._param_key()
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        m, dt = self.m, self.act_dtype
+        dev = m.joint_embed.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("hig_b200: the denoiser runs on CUDA only (no CPU fallback); move the module to a GPU")
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        op = lambda t: t.detach().to(dt).contiguous()
+        W = {}
+        with torch.no_grad():
+            w_in = torch.zeros(self.D, self.CP, device=dev, dtype=torch.float32)
+            w_in[:, :self.C] = m.joint_embed.weight
+            w_in[:, self.C:self.C + 4] = m.joint_embed2.weight
+            W["in.w"] = op(w_in)
+            pos = torch.empty(m.num_frames, self.D, device=dev, dtype=torch.float32)
+            pos[0] = m.joint_embed2.bias
+            pos[1:] = m.joint_embed.bias[None] + m.sequence_embedding[:m.num_frames - 1]
+            W["in.pos"] = pos.contiguous()
+            W["te0.w"], W["te0.b"] = op(m.time_embed[0].weight), f32(m.time_embed[0].bias)
+            W["te2.w"], W["te2.b"] = op(m.time_embed[2].weight), f32(m.time_embed[2].bias)
+            emb_w, emb_b = [], []
+            for i, blk in enumerate(m.temporal_decoder_blocks):
+                p = f"l{i}."
+                subs = [("sa", blk.sa_block), ("ca", blk.ca_block)]
+                if self.has_ic:
+                    subs.append(("ic", blk.int_ca_block))
+                for name, a in subs:
+                    W[p + name + ".ln.w"], W[p + name + ".ln.b"] = f32(a.norm.weight), f32(a.norm.bias)
+                    if name == "ca":
+                        W[p + "ca.tln.w"], W[p + "ca.tln.b"] = f32(a.text_norm.weight), f32(a.text_norm.bias)
+                        W[p + "ca.q.w"], W[p + "ca.q.b"] = op(a.query.weight), f32(a.query.bias)
+                        W[p + "ca.kv.w"] = op(torch.cat([a.key.weight, a.value.weight], 0))
+                        W[p + "ca.kv.b"] = f32(torch.cat([a.key.bias, a.value.bias], 0))
+                    else:
+                        W[p + name + ".qkv.w"] = op(torch.cat([a.query.weight, a.key.weight, a.value.weight], 0))
+                        W[p + name + ".qkv.b"] = f32(torch.cat([a.query.bias, a.key.bias, a.value.bias], 0))
+                W[p + "ffn.w1"], W[p + "ffn.b1"] = op(blk.ffn.linear1.weight), f32(blk.ffn.linear1.bias)
+                W[p + "ffn.w2"], W[p + "ffn.b2"] = op(blk.ffn.linear2.weight), f32(blk.ffn.linear2.bias)
+                for name, a in subs + [("ffn", blk.ffn)]:
+                    st = a.proj_out
+                    W[p + name + ".po.ln.w"], W[p + name + ".po.ln.b"] = f32(st.norm.weight), f32(st.norm.bias)
+                    W[p + name + ".po.w"], W[p + name + ".po.b"] = op(st.out_layers[2].weight), f32(st.out_layers[2].bias)
+                    W[p + name + ".ss"] = len(emb_w)      # index of this block's (scale|shift) slab
+                    emb_w.append(st.emb_layers[1].weight)
+                    emb_b.append(st.emb_layers[1].bias)
+            W["emb.w"] = op(torch.cat(emb_w, 0))          # [n_styl * 2D, E]
+            W["emb.b"] = f32(torch.cat(emb_b, 0))
+            W["n_styl"] = len(emb_w)
+            W["out.w"], W["out.b"] = op(m.out.weight), f32(m.out.bias)
+            W["out2.w"], W["out2.b"] = op(m.out2.weight), f32(m.out2.bias)
+            half = self.D // 2
+            W["freqs"] = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(dev)
+        self._packed, self._packed_key = W, key
+        self._text_cache = None
+        return W
+
+    # ------------------------------------------------------------------------------------------ workspaces
+    def workspace(self, S, T):
+        key = (S, T)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        dev = self.m.joint_embed.weight.device
+        tok, D, dt = S * T, self.D, self.act_dtype
+        n_styl = self.packed()["n_styl"]
+        e = lambda *shape, dtype=dt: torch.empty(*shape, device=dev, dtype=dtype)
+        ws = {
+            "xa": torch.zeros(tok, self.CP, device=dev, dtype=dt),
+            "xres": e(tok, D, dtype=torch.float32), "xb": e(tok, D), "n": e(tok, D), "qkv": e(tok, 3 * D),
+            "y": e(tok, D), "sact": e(tok, D), "g": e(tok, self.F),
+            "temb": e(S, D), "te_h": e(S, self.E), "semb": e(S, self.E),
+            "ss": e(S, n_styl * 2 * D, dtype=torch.float32),
+            "eps": e(tok, self.LD_EPS, dtype=torch.float32),
+            "len": torch.empty(S, device=dev, dtype=torch.int32),
+        }
+        if self.precision == "fp32":
+            ws["xb"] = ws["xres"]            # fp32 mode: the operand copy IS the residual stream
+        if len(self._ws) > 8:
+            self._ws.clear()
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------------ text (step-invariant)
+    def text_state(self, xf_out):
+        """A_text[l] = softmax_tokens(K_l)^T V_l for every layer: depends only on xf_out, so it is computed once
+        per batch and reused by all 1000 steps (the reference recomputes it every step, :145-161)."""
+        key = (xf_out.data_ptr(), xf_out._version, tuple(xf_out.shape))
+        if self._text_cache is not None and self._text_cache[0] == key:
+            return self._text_cache[1]
+        W = self.packed()
+        S, N, Dt = xf_out.shape
+        dt, dev = self.act_dtype, xf_out.device
+        xf = xf_out.detach().to(torch.float32).contiguous().view(S * N, Dt)
+        tn = torch.empty(S * N, Dt, device=dev, dtype=dt)
+        kv = torch.empty(S * N, 2 * self.D, device=dev, dtype=dt)
+        a_all = torch.empty(self.L, S, self.H, HEAD_DIM, HEAD_DIM, device=dev, dtype=dt)
+        for i in range(self.L):
+            p = f"l{i}.ca."
+            ops.ln_film_silu(xf, W[p + "tln.w"], W[p + "tln.b"], tn)
+            self._gemm(tn, W[p + "kv.w"], W[p + "kv.b"], out=kv)
+            ops.eff_attn(ops.ATTN_KV_ONLY, S, N, self.H, k=kv[:, :self.D], v=kv[:, self.D:], a_out=a_all[i])
+        self._text_cache = (key, a_all)
+        return a_all
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _gemm(self, a, w, bias, out=None, residual=None, res_row_mod=0, out_f32=None, act=ops.ACT_NONE):
+        """out: activation-typed output; out_f32: fp32 output (residual stream / eps)."""
+        if self.precision == "bf16":
+            ops.gemm(a, w, bias=bias, residual=residual, res_row_mod=res_row_mod, out_f32=out_f32, out_bf16=out, act=act)
+        else:
+            if out_f32 is not None:
+                ops.gemm(a, w, bias=bias, residual=residual, res_row_mod=res_row_mod, out_f32=out_f32, act=act)
+                if out is not None and out.data_ptr() != out_f32.data_ptr():
+                    raise RuntimeError("fp32 mode aliases the operand copy with the fp32 output")
+            else:
+                ops.gemm(a, w, bias=bias, residual=residual, res_row_mod=res_row_mod, out_f32=out, act=act)
+
+    def set_lengths(self, ws, length, S, T):
+        if length is None:
+            ws["len"].fill_(T)
+            return
+        ln = torch.as_tensor(length).reshape(-1)
+        if ln.numel() != S:
+            raise ValueError(f"length must have {S} entries, got {ln.numel()}")
+        ws["len"].copy_(ln.to(device=ws["len"].device, dtype=torch.int32, non_blocking=True).clamp(min=0, max=T))
+
+    # ------------------------------------------------------------------------------------------ forward
+    def embed(self, ws, t_dev, xf_proj, S):
+        """emb = time_embed(timestep_embedding(t)) + xf_proj (:591), then every block's (scale|shift) in one GEMM."""
+        W = self.packed()
+        ops.timestep_embed(t_dev, W["freqs"], ws["temb"])
+        self._gemm(ws["temb"], W["te0.w"], W["te0.b"], out=ws["te_h"], act=ops.ACT_SILU)
+        # StylizationBlock applies SiLU(emb) before its linear (:74-77): fold it into this epilogue
+        self._gemm(ws["te_h"], W["te2.w"], W["te2.b"], out=ws["semb"], residual=xf_proj, act=ops.ACT_SILU)
+        self._gemm(ws["semb"], W["emb.w"], W["emb.b"], out_f32=ws["ss"])
+
+    def _stylize_and_project(self, ws, W, p, T, write_xb):
+        D = self.D
+        i = W[p + ".ss"]
+        ss = ws["ss"][:, i * 2 * D:(i + 1) * 2 * D]
+        ops.ln_film_silu(ws["y"], W[p + ".po.ln.w"], W[p + ".po.ln.b"], ws["sact"], rows_per_seq=T, scale_shift=ss,
+                         silu=True)
+        self._gemm(ws["sact"], W[p + ".po.w"], W[p + ".po.b"], residual=ws["xres"], out_f32=ws["xres"],
+                   out=ws["xb"] if write_xb else None)
+
+    def layers(self, ws, a_text, S, T):
+        W, D, H = self.packed(), self.D, self.H
+        qkv = ws["qkv"]
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+        tok = S * T
+        q_ca = qkv.view(-1)[:tok * D].view(tok, D)   # dense [tok, 512] alias for the text-CA query
+        for li in range(self.L):
+            p = f"l{li}."
+            # --- self attention (:112-130)
+            ops.ln_film_silu(ws["xres"], W[p + "sa.ln.w"], W[p + "sa.ln.b"], ws["n"])
+            self._gemm(ws["n"], W[p + "sa.qkv.w"], W[p + "sa.qkv.b"], out=qkv)
+            ops.eff_attn(ops.ATTN_SELF, S, T, H, q=q, k=k, v=v, y=ws["y"], length=ws["len"], mask_v=True)
+            self._stylize_and_project(ws, W, p + "sa", T, False)
+            # --- text cross attention (:145-165), K/V side precomputed in text_state()
+            ops.ln_film_silu(ws["xres"], W[p + "ca.ln.w"], W[p + "ca.ln.b"], ws["n"])
+            self._gemm(ws["n"], W[p + "ca.q.w"], W[p + "ca.q.b"], out=q_ca)
+            ops.eff_attn(ops.ATTN_Q_ONLY, S, T, H, q=q_ca, a_in=a_text[li], y=ws["y"])
+            self._stylize_and_project(ws, W, p + "ca", T, not self.has_ic)
+            # --- inter-person cross attention (:181-207): K,V of the partner, mask of the query side
+            if self.has_ic:
+                ops.ln_film_silu(ws["xres"], W[p + "ic.ln.w"], W[p + "ic.ln.b"], ws["n"])
+                self._gemm(ws["n"], W[p + "ic.qkv.w"], W[p + "ic.qkv.b"], out=qkv)
+                ops.eff_attn(ops.ATTN_INTER, S, T, H, q=q, k=k, v=v, y=ws["y"], length=ws["len"],
+                             pair_shift=S // 2, mask_v=False)
+                self._stylize_and_project(ws, W, p + "ic", T, True)
+            # --- FFN (:261-264): no pre-norm, exact GELU fused in the linear1 epilogue
+            self._gemm(ws["xb"], W[p + "ffn.w1"], W[p + "ffn.b1"], out=ws["g"], act=ops.ACT_GELU)
+            self._gemm(ws["g"], W[p + "ffn.w2"], W[p + "ffn.b2"], out=ws["y"])
+            self._stylize_and_project(ws, W, p + "ffn", T, True)
+
+    def heads(self, ws, S, T):
+        """out on frames 1.., out2 on frame 0 (:613-616) into eps [tok, 264]."""
+        W = self.packed()
+        eps, xb = ws["eps"], ws["xb"]
+        self._gemm(xb, W["out.w"], W["out.b"], out_f32=eps[:, :self.C])
+        a0 = xb.view(S, T * self.D)[:, :self.D]
+        o0 = eps.view(S, T * self.LD_EPS)[:, :self.C]
+        self._gemm(a0, W["out2.w"], W["out2.b"], out_f32=o0)
+
+    def embed_motion(self, ws, T):
+        W = self.packed()
+        self._gemm(ws["xa"], W["in.w"], None, residual=W["in.pos"], res_row_mod=T, out_f32=ws["xres"])
+
+    def run_packed(self, ws, t_dev, xf_proj, a_text, S, T):
+        """Everything after pack_motion: ws['xa'] must hold the packed motion, ws['len'] the lengths."""
+        self.embed(ws, t_dev, xf_proj, S)
+        self.embed_motion(ws, T)
+        self.layers(ws, a_text, S, T)
+        self.heads(ws, S, T)
+        return ws["eps"]
+
+    def forward(self, x, timesteps, length, xf_proj, xf_out):
+        S, T, C = x.shape
+        if S % 2:
+            raise ValueError("the batch stacks person 1 and person 2 on dim 0: S must be even")
+        if T > self.m.num_frames:
+            raise ValueError(f"T={T} exceeds num_frames={self.m.num_frames}")
+        ws = self.workspace(S, T)
+        self.set_lengths(ws, length, S, T)
+        a_text = self.text_state(xf_out)
+        ops.pack_motion(x.detach().to(torch.float32).contiguous(), ws["xa"])
+        t_dev = timesteps.to(device=x.device, dtype=torch.int64).contiguous()
+        xfp = xf_proj.detach().to(torch.float32).contiguous()
+        eps = self.run_packed(ws, t_dev, xfp, a_text, S, T)
+        return eps.view(S, T, self.LD_EPS)[:, :, :C].contiguous()

@@ -1,0 +1,262 @@
+"""Model-level parity on the B200, all through the public drop-in API (which calls the C ABI):
+  * against the committed goldens produced by the REAL reference (tests/golden, oracle/make_golden.py),
+  * against the oracle (CPU, fp32) on seeded inputs at full depth / full length,
+  * size-independent reference properties at the BASELINE sizes (padding invariance, role-swap equivariance,
+    batch-composition independence, identity at zero-init, t == 0 adds no noise).
+Tolerances (BASELINE.json north_star): per-step rel-L2 <= 1e-2 in bf16, <= 1e-5 in fp32 mode."""
+import ast
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"bf16": 1e-2, "fp32": 1e-5}
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def valid_rel(a, b, length):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    T = a.shape[1]
+    m = (torch.arange(T)[None] < torch.as_tensor(length).reshape(-1, 1).cpu())
+    return ((a - b)[m].norm() / b[m].norm()).item()
+
+
+def build(layers, precision, cuda, cap_id=True, seed=0, zero_init=False):
+    import weights
+    from hig_b200.interaction_transformer import MotionInteractionTransformer
+    m = MotionInteractionTransformer(263, num_frames=196, num_layers=layers, latent_dim=512, cap_id=cap_id,
+                                     precision=precision)
+    sd = weights.make_state_dict(seed=seed, num_layers=layers)
+    if zero_init:
+        for k in sd:
+            if k.endswith(("out_layers.2.weight", "out_layers.2.bias", "linear2.weight", "linear2.bias")) or \
+                    k.startswith(("out.", "out2.")):
+                sd[k] = torch.zeros_like(sd[k])
+    m.load_state_dict(sd, strict=True)
+    return m.to(cuda).eval(), sd
+
+
+def load_case(name):
+    import weights
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = ast.literal_eval(str(d["cfg"]))
+    inp = weights.make_inputs(cfg["seed"], cfg["S"], cfg["T"], n_text=cfg.get("n_text", 1), lengths=cfg["lengths"],
+                              timesteps=cfg.get("timesteps"))
+    return d, cfg, inp
+
+
+def run(m, inp, mode, cuda):
+    g = lambda k: inp[k].to(cuda)
+    with torch.no_grad():
+        if mode == "cap":
+            m.cap_id = True
+            return m(g("x"), g("t"), length=g("length"), text=[g("cap1"), g("cap2")])
+        m.cap_id = False
+        return m(g("x"), g("t"), length=g("length"), xf_proj=g("xf_proj"), xf_out=g("xf_out"))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["fwd_cap", "fwd_text", "fwd_text_full"])
+def test_forward_matches_reference_golden(cuda, name, precision):
+    d, cfg, inp = load_case(name)
+    m, _ = build(cfg["layers"], precision, cuda)
+    out = run(m, inp, cfg["mode"], cuda)
+    assert out.shape == d["eps"].shape and out.dtype == torch.float32
+    err = valid_rel(out, d["eps"], cfg["lengths"])
+    print(f"{name} {precision}: valid-region rel-L2 {err:.3e}, full {rel(out, d['eps']):.3e}")
+    assert err < TOL[precision], err
+    assert rel(out, d["eps"]) < 2 * TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_depth_against_oracle(cuda, precision):
+    """8 layers, T=196, mixed per-person lengths (BASELINE config 5 semantics incl. the query-side mask quirk)."""
+    import denoiser_oracle as DO
+    import weights
+    m, sd = build(8, precision, cuda)
+    inp = weights.make_inputs(31, 6, 196, n_text=77, lengths=[196, 150, 60, 120, 196, 33])
+    with torch.no_grad():
+        ref = DO.denoiser_forward(sd, inp["x"], inp["t"], inp["length"], inp["xf_proj"], inp["xf_out"])
+    out = run(m, inp, "text", cuda)
+    err = valid_rel(out, ref, inp["length"])
+    print(f"full depth {precision}: rel-L2 {err:.3e}")
+    assert err < TOL[precision], err
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sampling_loop_golden_and_graph(cuda, precision):
+    """50-step chain (BASELINE config 1 schedule) with injected noise: fp32 mode against the real reference's final
+    sample; graph replay must be bit-identical to eager stepping in both precisions."""
+    import weights
+    from hig_b200.gaussian_diffusion import (GaussianDiffusion, LossType, ModelMeanType, ModelVarType,
+                                             get_named_beta_schedule)
+    d, cfg, inp = load_case("loop")
+    m, _ = build(cfg["layers"], precision, cuda)
+    m.cap_id = False
+    diff = GaussianDiffusion(betas=get_named_beta_schedule("linear", cfg["steps"]),
+                             model_mean_type=ModelMeanType.EPSILON, model_var_type=ModelVarType.FIXED_SMALL,
+                             loss_type=LossType.MSE)
+    noise = weights.make_noise(cfg["seed"] + 100, cfg["steps"], cfg["S"], cfg["T"]).to(cuda)
+    kw = {"xf_proj": inp["xf_proj"].to(cuda), "xf_out": inp["xf_out"].to(cuda), "length": inp["length"].to(cuda)}
+    shape = (cfg["S"], cfg["T"], 263)
+    a = diff.p_sample_loop(m, shape, noise=noise[0], clip_denoised=False, model_kwargs=kw, noise_seq=noise[1:],
+                           use_graph=True)
+    b = diff.p_sample_loop(m, shape, noise=noise[0], clip_denoised=False, model_kwargs=kw, noise_seq=noise[1:],
+                           use_graph=False)
+    c = diff.p_sample_loop(m, shape, noise=noise[0], clip_denoised=False, model_kwargs=kw, noise_seq=noise[1:],
+                           use_graph=True)  # cached graph
+    assert torch.equal(a, b) and torch.equal(a, c)
+    err = rel(a, d["final"])
+    print(f"loop {precision}: final-sample rel-L2 vs reference {err:.3e}")
+    # 50 steps through an untrained eps-network are expansive (|x| reaches 1e4): fp32-vs-fp32 sits at
+    # ~1e-4; bf16 is only required to stay finite and in the same regime here (per-step parity is the bf16 gate)
+    assert err < (2e-3 if precision == "fp32" else 0.5), err
+    # generic per-step API (public model call + fused posterior kernel) agrees with the fast path
+    img = noise[0].clone()
+    for k, i in enumerate(range(cfg["steps"] - 1, -1, -1)):
+        t = torch.full((cfg["S"],), i, device=cuda, dtype=torch.long)
+        img = diff.p_sample(m, img, t, clip_denoised=False, model_kwargs=kw, noise=noise[1 + k])["sample"]
+    assert rel(img, a) < (1e-6 if precision == "fp32" else 1e-6)
+
+
+def test_teacher_forced_steps_bf16(cuda):
+    """Primary bf16 gate: feed the ORACLE's x_t to the CUDA path at several t and compare eps and x_{t-1}."""
+    import denoiser_oracle as DO
+    import diffusion_oracle as DF
+    import weights
+    from hig_b200 import ops
+    from hig_b200.gaussian_diffusion import (GaussianDiffusion, LossType, ModelMeanType, ModelVarType,
+                                             get_named_beta_schedule)
+    m, sd = build(4, "bf16", cuda)
+    m.cap_id = False
+    S, T = 4, 64
+    inp = weights.make_inputs(77, S, T, n_text=77, lengths=[64, 50, 64, 50])
+    sch = DF.Schedule(1000)
+    diff = GaussianDiffusion(betas=get_named_beta_schedule("linear", 1000), model_mean_type=ModelMeanType.EPSILON,
+                             model_var_type=ModelVarType.FIXED_SMALL, loss_type=LossType.MSE)
+    z = weights.make_noise(5, 0, S, T)[0]
+    for tv in (999, 500, 1, 0):
+        t = torch.full((S,), tv, dtype=torch.long)
+        with torch.no_grad():
+            eps_ref = DO.denoiser_forward(sd, inp["x"], t, inp["length"], inp["xf_proj"], inp["xf_out"])
+            x_ref = DF.p_sample_step(sch, inp["x"], eps_ref, t, z)
+            out = diff.p_sample(m, inp["x"].to(cuda), t.to(cuda), clip_denoised=False,
+                                model_kwargs={"xf_proj": inp["xf_proj"].to(cuda), "xf_out": inp["xf_out"].to(cuda),
+                                              "length": inp["length"].to(cuda)}, noise=z.to(cuda))
+            eps = m(inp["x"].to(cuda), t.to(cuda), length=inp["length"].to(cuda), xf_proj=inp["xf_proj"].to(cuda),
+                    xf_out=inp["xf_out"].to(cuda))
+        e1, e2 = valid_rel(eps, eps_ref, inp["length"]), valid_rel(out["sample"], x_ref, inp["length"])
+        print(f"t={tv}: eps rel {e1:.3e}  x_prev rel {e2:.3e}")
+        assert e1 < 1e-2 and e2 < 1e-2
+
+
+# ------------------------------------------------------------------------------------------ properties at BASELINE sizes
+@pytest.fixture(scope="module")
+def big(cuda):
+    import weights
+    m, sd = build(8, "bf16", cuda)
+    m.cap_id = False
+    S, T = 128, 196   # BASELINE config 2 shape: 64 pairs, 196 frames
+    rs = np.random.RandomState(3)
+    pair_len = rs.randint(20, 197, size=S // 2)
+    pair_len[:4] = 196
+    inp = weights.make_inputs(41, S, T, n_text=77, lengths=np.concatenate([pair_len, pair_len]))
+    inp = {k: v.to(cuda) for k, v in inp.items()}
+    with torch.no_grad():
+        base = m(inp["x"], inp["t"], length=inp["length"], xf_proj=inp["xf_proj"], xf_out=inp["xf_out"])
+    return m, inp, base
+
+
+def _mask(inp):
+    T = inp["x"].shape[1]
+    return torch.arange(T, device=inp["x"].device)[None] < inp["length"][:, None]
+
+
+def test_big_finite_and_nontrivial(big):
+    m, inp, base = big
+    assert torch.isfinite(base).all()
+    assert base.abs().mean().item() > 0.05
+
+
+def test_big_pad_garbage_invariance(big):
+    m, inp, base = big
+    x2 = inp["x"].clone()
+    x2[~_mask(inp)] = 1e3
+    with torch.no_grad():
+        out = m(x2, inp["t"], length=inp["length"], xf_proj=inp["xf_proj"], xf_out=inp["xf_out"])
+    assert torch.equal(out[_mask(inp)], base[_mask(inp)])
+
+
+def test_big_role_swap_equivariance(big):
+    m, inp, base = big
+    B = inp["x"].shape[0] // 2
+    sw = lambda a: torch.cat([a[B:], a[:B]])
+    with torch.no_grad():
+        out = m(sw(inp["x"]), sw(inp["t"]), length=sw(inp["length"]), xf_proj=sw(inp["xf_proj"]),
+                xf_out=sw(inp["xf_out"]))
+    assert torch.equal(sw(out)[_mask(inp)], base[_mask(inp)])
+
+
+def test_big_batch_composition_independence(big):
+    m, inp, base = big
+    B = inp["x"].shape[0] // 2
+    idx = torch.tensor([3, 17, 40, B + 3, B + 17, B + 40], device=inp["x"].device)
+    with torch.no_grad():
+        out = m(inp["x"][idx], inp["t"][idx], length=inp["length"][idx], xf_proj=inp["xf_proj"][idx],
+                xf_out=inp["xf_out"][idx].contiguous())
+    mk = _mask(inp)[idx]
+    assert rel(out[mk], base[idx][mk]) < 1e-6   # same kernels, same per-row arithmetic: only tile placement differs
+
+
+def test_padding_vs_trimmed(cuda):
+    """The reference's __main__ smoke (interaction_transformer.py:849-854): T=32,len=31 padded vs T=31 trimmed."""
+    import weights
+    m, _ = build(2, "bf16", cuda)
+    m.cap_id = False
+    inp = weights.make_inputs(8, 2, 32, n_text=77, lengths=[31, 31])
+    g = lambda k: inp[k].to(cuda)
+    with torch.no_grad():
+        a = m(g("x"), g("t"), length=g("length"), xf_proj=g("xf_proj"), xf_out=g("xf_out"))
+        b = m(g("x")[:, :31].contiguous(), g("t"), length=g("length"), xf_proj=g("xf_proj"), xf_out=g("xf_out"))
+    assert rel(a[:, :31], b) < 1e-6
+
+
+def test_zero_init_identity(cuda):
+    import weights
+    m, _ = build(2, "bf16", cuda, zero_init=True)
+    m.cap_id = False
+    inp = weights.make_inputs(9, 4, 40, n_text=77)
+    g = lambda k: inp[k].to(cuda)
+    with torch.no_grad():
+        out = m(g("x"), g("t"), length=g("length"), xf_proj=g("xf_proj"), xf_out=g("xf_out"))
+    assert out.abs().max().item() == 0.0
+
+
+def test_length_forms_and_errors(cuda):
+    import weights
+    m, _ = build(1, "bf16", cuda)
+    m.cap_id = False
+    inp = weights.make_inputs(10, 4, 24, n_text=3, lengths=[24, 10, 24, 10])
+    g = lambda k: inp[k].to(cuda)
+    with torch.no_grad():
+        a = m(g("x"), g("t"), length=g("length"), xf_proj=g("xf_proj"), xf_out=g("xf_out"))
+        b = m(g("x"), g("t"), length=g("length").view(-1, 1), xf_proj=g("xf_proj"), xf_out=g("xf_out"))  # [2B,1]
+        c = m(g("x"), g("t"), length=[24, 10, 24, 10], xf_proj=g("xf_proj"), xf_out=g("xf_out"))         # list
+    assert torch.equal(a, b) and torch.equal(a, c)
+    with pytest.raises(RuntimeError):
+        m(inp["x"], inp["t"], length=inp["length"], xf_proj=inp["xf_proj"], xf_out=inp["xf_out"])  # CPU input
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            m(g("x")[:3], g("t")[:3], length=g("length")[:3], xf_proj=g("xf_proj")[:3], xf_out=g("xf_out")[:3])
