@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — interactions/sec of full-DDPM two-person sampling (BASELINE.json metric) on N B200s.
+
+One bench "step" = one pass of the hot path over one batch: a complete 1000-step DDPM sample of B=64 pairs
+(S=128 sequences, T=196 frames, 263 features; BASELINE config 2), i.e. 1000 x (denoiser forward + posterior update).
+  value  : whole-job interactions/s with the text state, x_T and lengths already in HBM (CUDA events, max over ranks)
+  e2e    : the same through the reference-facing API  DDPMMulTrainer.generate(captions, lengths)  with host inputs
+           (caption strings + host lengths) and the sampled motions copied back to host memory
+  roofline / cpu_baseline / clocks / gpu_launches: see the module docstrings of the helpers below.
+`--impl reference` times the reference's algorithm on the host CPU (the oracle port, all host threads).
+Multi-GPU: one process per GPU (torchrun), pairs sharded across ranks, no collective in the loop; the e2e arm
+gathers the samples to rank 0.  Scaling is weak (64 pairs per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(pairs=64, frames=196, feats=263, diffusion_steps=1000, layers=8, latent=512, ff=1024, heads=8,
+           text_tokens=77, text_dim=256)
+
+CAPTIONS = [
+    ("a person pushes the other person", "a person is pushed by the other person"),
+    ("a person kicks the other person", "a person is kicked by the other person"),
+    ("a person pats the other person on the back", "a person is patted on the back by the other person"),
+    ("a person points a finger at the other person", "a person is pointed at by the other person"),
+    ("a person hugs the other person", "a person hugs the other person"),
+    ("a person gives an object to the other person", "a person receives an object from the other person"),
+    ("a person touches the pocket of the other person", "a person has the pocket touched by the other person"),
+    ("two people shake hands", "two people shake hands"),
+    ("a person walks towards the other person", "a person walks towards the other person"),
+    ("a person punches the other person", "a person is punched by the other person"),
+]
+
+
+def flops_per_denoiser_step(S, T, L=8, D=512, F=1024, hd=64, E=2048, Dt=256, N=77, C=263):
+    """Algorithmic FLOPs of one reference denoiser forward (SURVEY.md §8d formula; multiply-add = 2)."""
+    tok = S * T
+    per_layer = 2 * tok * (11 * D * D + 2 * D * F) + 10 * tok * D * hd + S * (4 * N * Dt * D + 2 * N * D * hd) \
+        + 16 * S * E * D
+    return L * per_layer + 4 * S * T * C * D + 2 * S * (D * E + E * E)
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    f = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(f):
+        try:
+            d = json.load(open(f))
+            p.update({k: d[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in d})
+            p["source"] = "measured"
+        except Exception:
+            pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_model(device, precision="bf16"):
+    """Random-init denoiser of the repo-default architecture with a random-init CLIP-shaped text encoder; the
+    reference zero-initialises 34 projections (identity network), so those are re-drawn N(0, 0.02^2)."""
+    import hig_b200  # noqa: F401
+    from hig_b200.interaction_transformer import MotionInteractionTransformer
+    torch.manual_seed(0)
+    m = MotionInteractionTransformer(CFG["feats"], num_frames=CFG["frames"], num_layers=CFG["layers"],
+                                     latent_dim=CFG["latent"], cap_id=False, precision=precision)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if not name.startswith("clip.") and p.abs().max() == 0 and "norm.bias" not in name:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    return m.to(device).eval()
+
+
+def make_trainer(model, device, steps):
+    from hig_b200.mul_ddpm_trainer import DDPMMulTrainer
+    opt = argparse.Namespace(device=device, multi=True, label_path=None, cap_id=False, diffusion_steps=steps,
+                             is_train=False)
+    return DDPMMulTrainer(opt, model)
+
+
+def time_qkv_kernel(device, peak_burst):
+    """The dominant kernel alone: the SA/IC QKV projection [25088 x 1536 x 512], CUDA events, L2 flushed."""
+    from hig_b200 import ops
+    M, N, K = CFG["pairs"] * 2 * CFG["frames"], 1536, 512
+    a = torch.randn(M, K, device=device).bfloat16()
+    w = (torch.randn(N, K, device=device) / 22.6).bfloat16()
+    b = torch.randn(N, device=device)
+    o = torch.empty(M, N, device=device, dtype=torch.bfloat16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    for _ in range(3):
+        ops.gemm(a, w, bias=b, out_bf16=o)
+    ts = []
+    for _ in range(20):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.gemm(a, w, bias=b, out_bf16=o); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    t = sorted(ts)[len(ts) // 2]
+    ach = 2.0 * M * N * K / t / 1e12
+    return {"name": "gemm_bf16_tcgen05 (QKV 25088x1536x512)", "us": t * 1e6, "achieved": ach, "peak": peak_burst,
+            "unit": "TFLOP/s", "frac": ach / peak_burst, "l2": "flushed between iterations"}
+
+
+def cpu_reference_arm(state_dict, B, T, n_denoiser_steps, warm):
+    """The reference's algorithm on the host cores: oracle port (CPU fp32, all threads); one step = one denoiser
+    forward + posterior update at the bench batch.  Returns seconds per denoiser step."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import denoiser_oracle as DO
+    import diffusion_oracle as DF
+    torch.set_num_threads(os.cpu_count() or 1)
+    S = 2 * B
+    g = torch.Generator().manual_seed(0)
+    sd = {k: v.detach().float().cpu() for k, v in state_dict.items() if not k.startswith(("clip.", "textTrans", "text_pre", "text_ln"))}
+    x = torch.randn(S, T, CFG["feats"], generator=g)
+    xf_proj = torch.randn(S, 4 * CFG["latent"], generator=g) * 0.5
+    xf_out = torch.randn(S, CFG["text_tokens"], CFG["text_dim"], generator=g)
+    length = torch.full((S,), T, dtype=torch.long)
+    sch = DF.Schedule(CFG["diffusion_steps"])
+    times = []
+    with torch.no_grad():
+        for i in range(warm + n_denoiser_steps):
+            t = torch.full((S,), CFG["diffusion_steps"] - 1 - i, dtype=torch.long)
+            t0 = time.perf_counter()
+            eps = DO.denoiser_forward(sd, x, t, length, xf_proj, xf_out)
+            x = DF.p_sample_step(sch, x, eps, t, torch.randn(x.shape, generator=g))
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    return sum(times) / len(times), times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=CFG["pairs"])
+    ap.add_argument("--diffusion-steps", type=int, default=CFG["diffusion_steps"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    CFG["pairs"], CFG["diffusion_steps"] = args.pairs, args.diffusion_steps
+    B, T, C, NS = CFG["pairs"], CFG["frames"], CFG["feats"], CFG["diffusion_steps"]
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    workload = {"workload": f"configs[1]: full {NS}-step DDPM sampling, {B} pairs/GPU x {T} frames x {C} feats, "
+                            f"8-layer role-aware denoiser, random-init CLIP-shaped text encoder",
+                "pairs_per_gpu": B, "frames": T, "diffusion_steps": NS, "parallelism": f"batch-shard x{world}",
+                "l2": "working set per denoiser step (~1.5 GB of activations + 214 MB weights) exceeds the 126 MB L2"}
+    unit = "interactions/s"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # weights of the same architecture (CPU construction only; no CUDA kernel is involved in this arm)
+        import hig_b200  # noqa: F401
+        from hig_b200.interaction_transformer import MotionInteractionTransformer
+        torch.manual_seed(0)
+        m = MotionInteractionTransformer(C, num_frames=T, num_layers=CFG["layers"], latent_dim=CFG["latent"], cap_id=True)
+        g = torch.Generator().manual_seed(1)
+        with torch.no_grad():
+            for name, p in m.named_parameters():
+                if p.abs().max() == 0 and "norm.bias" not in name:
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+        s_per, times = cpu_reference_arm(m.state_dict(), B, T, args.steps, args.warmup)
+        val = B / (s_per * NS)
+        cores = os.cpu_count() or 1
+        print(json.dumps({
+            "impl": "reference", "metric": "interactions/sec (full DDPM sample, 196f)", "value": val, "unit": unit,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per * NS * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload,
+            "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} of {NS} denoiser+posterior steps at {B} pairs x {T} frames "
+                                       f"({s_per:.3f} s each), extrapolated x{NS}/{1}"},
+            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hig_b200 product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    from hig_b200 import _lib
+
+    model = build_model(device)
+    trainer = make_trainer(model, device, NS)
+    diff = trainer.diffusion
+    S = 2 * B
+    caps1 = [CAPTIONS[(i + rank * B) % len(CAPTIONS)][0] for i in range(B)]
+    caps2 = [CAPTIONS[(i + rank * B) % len(CAPTIONS)][1] for i in range(B)]
+    m_lens_host = torch.full((B,), T, dtype=torch.long)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm: text state, lengths and x_T live in HBM ----------------
+    with torch.no_grad():
+        xf_proj, xf_out = model.encode_text(caps1 + caps2, device)
+    kw = {"xf_proj": xf_proj, "xf_out": xf_out, "length": torch.full((S,), T, device=device, dtype=torch.long)}
+    x_T = torch.randn(S, T, C, device=device)
+
+    def resident_step():
+        return diff.p_sample_loop(model, (S, T, C), noise=x_T, clip_denoised=False, model_kwargs=kw)
+
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = _lib.launch_count()
+    launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        resident_step()
+        launches += diff.last_launches
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    dt = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        tt = torch.tensor([dt], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = tt.item()
+    value = world * B * args.steps / dt
+
+    # ---------------- end-to-end arm: host captions + host lengths in, host motions out ----------------
+    def e2e_step():
+        out = trainer.generate(caps1, caps2, m_lens_host, C)
+        res = torch.stack([torch.stack(p) for p in out])          # [B, 2, T, C] on device
+        if world > 1:
+            gl = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
+            dist.gather(res, gl, dst=0)
+            if rank == 0:
+                return torch.cat(gl).cpu()
+            return None
+        return res.cpu()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    dt_e2e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt_e2e], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt_e2e = tt.item()
+    e2e_val = world * B * args.steps / dt_e2e
+    h2d = S * 77 * 8 + B * 8                      # token ids [S,77] int64 + lengths [B] int64
+    d2h = B * 2 * T * C * 4 * (world if world > 1 else 1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    f_step = flops_per_denoiser_step(S, T)
+    ach = f_step * NS * args.steps / dt / 1e12      # per GPU: each rank runs the same per-GPU workload
+    roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+            "basis": f"{f_step / 1e9:.1f} algorithmic GFLOP per denoiser step (SURVEY §8d) x {NS} steps per sample, "
+                     f"per GPU, over the CUDA-event time of the timed region; peak = {pk['source']} sustained bf16",
+            "us_per_denoiser_step": dt / (args.steps * NS) * 1e6}
+    try:
+        roof["kernel"] = time_qkv_kernel(device, pk["bf16_tflops"])
+    except Exception as ex:  # noqa
+        roof["kernel"] = {"error": str(ex)}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        sd = {k: v for k, v in model.state_dict().items()}
+        s_per, _ = cpu_reference_arm(sd, B, T, 2, 1)
+        cpu = {"value": B / (s_per * NS), "unit": unit, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"2 of {NS} denoiser+posterior steps at {B} pairs x {T} frames on the host CPU "
+                         f"({s_per:.2f} s each, oracle port, torch fp32, all threads), extrapolated to {NS} steps"}
+
+    print(json.dumps({
+        "metric": "interactions/sec (full DDPM sample, 196f)", "value": value, "unit": unit, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload,
+        "us_per_denoiser_step": dt / (args.steps * NS) * 1e6,
+        "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "DDPMMulTrainer.generate(caption strings, host lengths) -> host tensors"},
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

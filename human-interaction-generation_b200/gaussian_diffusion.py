@@ -19,7 +19,7 @@ import math
 import numpy as np
 import torch as th
 
-from . import ops
+from . import _lib, ops
 
 
 class ModelMeanType(enum.Enum):
@@ -249,17 +249,25 @@ class GaussianDiffusion:
             # The Philox seed is a kernel argument frozen into the graph: production runs capture once per call,
             # injected-noise (parity) runs keep the graph across calls.
             graph = st["graph"] if noise_seq is not None else None
+            launches, c_prev = 0, _lib.launch_count()
             for k in steps:
                 if noise_seq is not None:
                     st["z"].copy_(noise_seq[k])
                 if k == 0 or not use_graph:
                     step()                      # eager: also performs every lazy initialisation before capture
+                    c_now = _lib.launch_count()
+                    launches, c_prev = launches + (c_now - c_prev), c_now
+                    st["nodes"] = st.get("nodes") or launches
                     continue
                 if graph is None:
                     graph = self._capture(step)
+                    c_prev = _lib.launch_count()   # capture records kernels, it does not run them
                     if noise_seq is not None:
                         st["graph"] = graph
                 graph.replay()
+                launches += st["nodes"]            # one replay launches every recorded kernel node
+            # kernels of this library launched on the GPU during this call (eager + graph replays)
+            self.last_launches = launches
             return st["x"].clone()
 
     @staticmethod
