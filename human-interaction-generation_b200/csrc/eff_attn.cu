@@ -27,7 +27,8 @@ namespace hig {
 
 constexpr int HD = 64;           // head dim (latent_dim / num_heads = 512 / 8)
 constexpr int ATT_STRIDE = 72;   // bf16 elements per smem row (144 B)
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_WARPS = ATT_THREADS / 32;
 
 HIG_DEVICE void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -75,7 +76,8 @@ eff_attn_bf16_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, con
   __nv_bfloat16* sV = sK + TP * ATT_STRIDE;
   __nv_bfloat16* sQ = sV + TP * ATT_STRIDE;
   __nv_bfloat16* sA = sQ + TP * ATT_STRIDE;
-  float* sred = reinterpret_cast<float*>(sA + HD * ATT_STRIDE);  // [2][64] max, [2][64] sum
+  float* sred = reinterpret_cast<float*>(sA + HD * ATT_STRIDE);  // [ATT_WARPS][64] partials, then [64] inverse sums
+  float* sinv = sred + ATT_WARPS * 64;
 
   const int h = blockIdx.x, s = blockIdx.y, H = gridDim.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -92,8 +94,7 @@ eff_attn_bf16_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, con
     stage_tile(sK, k + (size_t)s_kv * T * ldkv + h * HD, ldkv, T);
     stage_tile(sV, v + (size_t)s_kv * T * ldkv + h * HD, ldkv, T);
   } else {
-    // A tile [64,64] from global (bf16, dense)
-    stage_tile(sA, a_in + ((size_t)s * H + h) * HD * HD, HD, HD);
+    stage_tile(sA, a_in + ((size_t)s * H + h) * HD * HD, HD, HD);  // A tile [64,64] from global (bf16, dense)
   }
   cp_async_commit();
   if (do_q) stage_tile(sQ, q + (size_t)s * T * ldq + h * HD, ldq, T);
@@ -104,35 +105,62 @@ eff_attn_bf16_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, con
   __syncthreads();
 
   if (do_kv) {
-    // ---------------- phase 1: time softmax of K columns over rows [0,len) ----------------
-    const int c = tid & 63, half = tid >> 6;
-    float m = -INFINITY;
-    for (int t = half; t < len; t += 2) m = fmaxf(m, __bfloat162float(sK[t * ATT_STRIDE + c]));
-    sred[half * 64 + c] = m;
+    // ---------------- phase 1: time softmax of K over rows [0,len); lane owns the column pair (2*lane, 2*lane+1),
+    // warp w owns rows w, w+8, ...  Unnormalised exp() is written back in place; 1/sum is folded into A. ----------
+    uint32_t* sK32 = reinterpret_cast<uint32_t*>(sK);
+    constexpr int ROW32 = ATT_STRIDE / 2;
+    float m0 = -INFINITY, m1 = -INFINITY;
+    for (int t = warp; t < len; t += ATT_WARPS) {
+      const float2 kv2 = unpack_bf16x2(sK32[t * ROW32 + lane]);
+      m0 = fmaxf(m0, kv2.x);
+      m1 = fmaxf(m1, kv2.y);
+    }
+    sred[warp * 64 + 2 * lane] = m0;
+    sred[warp * 64 + 2 * lane + 1] = m1;
     __syncthreads();
-    m = fmaxf(sred[c], sred[64 + c]);
-    float sum = 0.f;
-    for (int t = half; t < len; t += 2) sum += __expf(__bfloat162float(sK[t * ATT_STRIDE + c]) - m);
-    sred[128 + half * 64 + c] = sum;
+#pragma unroll
+    for (int w = 0; w < ATT_WARPS; ++w) {
+      m0 = fmaxf(m0, sred[w * 64 + 2 * lane]);
+      m1 = fmaxf(m1, sred[w * 64 + 2 * lane + 1]);
+    }
     __syncthreads();
-    const float inv = 1.0f / (sred[128 + c] + sred[192 + c]);
-    for (int t = half; t < TP; t += 2) {
-      float e = 0.f;
-      if (t < len) e = __expf(__bfloat162float(sK[t * ATT_STRIDE + c]) - m) * inv;
-      sK[t * ATT_STRIDE + c] = __float2bfloat16(e);
+    float s0 = 0.f, s1 = 0.f;
+    for (int t = warp; t < T; t += ATT_WARPS) {
+      uint32_t packed = 0u;
+      if (t < len) {
+        const float2 kv2 = unpack_bf16x2(sK32[t * ROW32 + lane]);
+        // sum what the MMA will actually see (the bf16-rounded weights) so the normalisation is exact
+        const __nv_bfloat162 e2 = __floats2bfloat162_rn(__expf(kv2.x - m0), __expf(kv2.y - m1));
+        const float2 ef = __bfloat1622float2(e2);
+        s0 += ef.x;
+        s1 += ef.y;
+        packed = *reinterpret_cast<const uint32_t*>(&e2);
+      }
+      sK32[t * ROW32 + lane] = packed;
     }
     if (mask_v) {
-      for (int t = len + half; t < T; t += 2) sV[t * ATT_STRIDE + c] = __float2bfloat16(0.f);
+      uint32_t* sV32 = reinterpret_cast<uint32_t*>(sV);
+      for (int t = len + warp; t < T; t += ATT_WARPS) sV32[t * ROW32 + lane] = 0u;
+    }
+    sred[warp * 64 + 2 * lane] = s0;
+    sred[warp * 64 + 2 * lane + 1] = s1;
+    __syncthreads();
+    if (tid < 64) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < ATT_WARPS; ++w) tot += sred[w * 64 + tid];
+      sinv[tid] = tot > 0.f ? 1.0f / tot : 0.f;
     }
     __syncthreads();
 
-    // ---------------- phase 2: A[d,l] = sum_t Ks[t,d] V[t,l]   (warp w owns d in [16w,16w+16)) ----------------
-    float acc[8][4];
+    // ---------------- phase 2: A[d,l] = (sum_t e[t,d] V[t,l]) / sum_t e[t,d]
+    // warp w owns d in [16*(w&3), +16) and l in [32*(w>>2), +32) ----------------
+    float acc[4][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const int dw = warp * 16;
+    const int dw = (warp & 3) * 16, lw = (warp >> 2) * 32;
     const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV);
     for (int kt = 0; kt < TP; kt += 16) {
       uint32_t a[4];
@@ -142,37 +170,31 @@ eff_attn_bf16_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, con
         ldsm_x4_t(sK_u + (row * ATT_STRIDE + col) * 2, a[0], a[1], a[2], a[3]);
       }
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {
+      for (int np = 0; np < 2; ++np) {
         uint32_t b0, b1, b2, b3;
         const int row = kt + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int col = np * 16 + ((lane >> 4) & 1) * 8;
+        const int col = lw + np * 16 + ((lane >> 4) & 1) * 8;
         ldsm_x4_t(sV_u + (row * ATT_STRIDE + col) * 2, b0, b1, b2, b3);
         mma_bf16_16816(acc[2 * np], a, b0, b1);
         mma_bf16_16816(acc[2 * np + 1], a, b2, b3);
       }
     }
     const int g = lane >> 2, tg = lane & 3;
-    if (mode == 2) {
-      __nv_bfloat16* ao = a_out + ((size_t)s * H + h) * HD * HD;
+    const float i0 = sinv[dw + g], i1 = sinv[dw + g + 8];
+    __nv_bfloat16* dst = (mode == 2) ? a_out + ((size_t)s * H + h) * HD * HD : sA;
+    const int dstride = (mode == 2) ? HD : ATT_STRIDE;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = nt * 8 + 2 * tg;
-        *reinterpret_cast<uint32_t*>(ao + (dw + g) * HD + col) = pack_bf16x2(acc[nt][0], acc[nt][1]);
-        *reinterpret_cast<uint32_t*>(ao + (dw + g + 8) * HD + col) = pack_bf16x2(acc[nt][2], acc[nt][3]);
-      }
-      return;
+    for (int nt = 0; nt < 4; ++nt) {
+      const int col = lw + nt * 8 + 2 * tg;
+      *reinterpret_cast<uint32_t*>(dst + (dw + g) * dstride + col) = pack_bf16x2(acc[nt][0] * i0, acc[nt][1] * i0);
+      *reinterpret_cast<uint32_t*>(dst + (dw + g + 8) * dstride + col) = pack_bf16x2(acc[nt][2] * i1, acc[nt][3] * i1);
     }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int col = nt * 8 + 2 * tg;
-      *reinterpret_cast<uint32_t*>(sA + (dw + g) * ATT_STRIDE + col) = pack_bf16x2(acc[nt][0], acc[nt][1]);
-      *reinterpret_cast<uint32_t*>(sA + (dw + g + 8) * ATT_STRIDE + col) = pack_bf16x2(acc[nt][2], acc[nt][3]);
-    }
+    if (mode == 2) return;
   }
   cp_async_wait<0>();
   __syncthreads();
 
-  // ---------------- phase 3: Y = softmax_feat(Q) · A ----------------
+  // ---------------- phase 3: Y = softmax_feat(Q) · A, one 16-row tile per warp iteration ----------------
   const uint32_t sQ_u = smem_u32(sQ), sA_u = smem_u32(sA);
   uint32_t bfrag[4][8][2];  // [k-step][n-tile][2]
 #pragma unroll
@@ -185,7 +207,7 @@ eff_attn_bf16_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, con
                 bfrag[kk][2 * np + 1][0], bfrag[kk][2 * np + 1][1]);
     }
   const int g = lane >> 2, tg = lane & 3;
-  for (int mt = warp; mt * 16 < T; mt += 4) {
+  for (int mt = warp; mt * 16 < T; mt += ATT_WARPS) {
     uint32_t af[4][4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -378,7 +400,7 @@ int eff_attn(int mode, const void* q, int ldq, const void* k, const void* v, int
     if ((do_q && ((ldq % 8) || (ldy % 8))) || (do_kv && (ldkv % 8)))
       return set_error(HIG_ERR_INVALID, "eff_attn: bf16 leading dimensions must be multiples of 8");
     const int TP = (T + 15) & ~15;
-    const size_t smem = (size_t)(3 * TP + HD) * ATT_STRIDE * 2 + 4 * 64 * sizeof(float);
+    const size_t smem = (size_t)(3 * TP + HD) * ATT_STRIDE * 2 + (ATT_WARPS + 1) * 64 * sizeof(float);
     static size_t configured = 0;
     if (smem > configured) {
       e = cudaFuncSetAttribute(eff_attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

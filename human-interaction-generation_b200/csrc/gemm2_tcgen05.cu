@@ -1,0 +1,202 @@
+// hig_gemm_bf16, CTA-pair variant:  C[M,N] = act( A[M,K] · W[N,K]^T + bias + residual ) with tcgen05 cta_group::2.
+//
+// Two CTAs of a cluster (one TPC) cooperate on a 256 x 256 output tile: each CTA TMA-loads ITS 128 rows of A and ITS
+// 128 rows of W per k-block (32 KB per stage instead of 48 KB), the leader CTA issues one
+// tcgen05.mma.cta_group::2 (M=256, N=256, K=16) that reads both CTAs' shared memory, and each CTA ends up with its
+// 128 x 256 fp32 accumulator half in its own TMEM.  Operand traffic per flop drops by a third against the
+// single-CTA 128 x 256 kernel — at the K=512 shapes of the denoiser the single-CTA kernel is bound by L2->SMEM
+// bandwidth (~7.8 TB/s measured), not by the tensor pipe, so this is the lever that matters.
+//
+// Pipeline (per CTA): warp 0 = TMA producer, warp 1 = TMEM allocator (+ MMA issuer in the leader),
+// warps 2..9 = epilogue.  Barriers: full[s] lives in the leader (both CTAs' TMA bytes complete on it),
+// empty[s] / tmem_full[a] are signalled in BOTH CTAs by multicast tcgen05.commit, tmem_empty[a] lives in the leader
+// and collects the 16 epilogue warps of the pair.
+#include <cuda.h>
+#include <string>
+#include "hig_common.cuh"
+#include "gemm_epilogue.cuh"
+#include "hig_internal.h"
+
+namespace hig {
+
+constexpr int G2_BM = 128;       // rows of A per CTA (256 per pair)
+constexpr int G2_BN = 256;       // tile columns (128 rows of W per CTA)
+constexpr int G2_BK = 64;
+constexpr int G2_STAGES = 6;
+constexpr int G2_EPI_WARPS = 8;
+constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
+constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;          // 16 KB
+constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;    // 16 KB
+constexpr int G2_EPI_BYTES = G2_EPI_WARPS * 32 * 16 * 4;
+constexpr int G2_BAR_BYTES = (2 * G2_STAGES + 4) * 8 + 16;
+constexpr int G2_SMEM = G2_STAGES * (G2_A_BYTES + G2_B_BYTES) + G2_EPI_BYTES + G2_BAR_BYTES + 1024;
+
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                      int K, GemmEpilogue ep, int vec_ok) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + G2_STAGES * G2_A_BYTES;
+  float* sEpi = reinterpret_cast<float*>(sB + G2_STAGES * G2_B_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + G2_EPI_BYTES);
+  uint64_t* empty_bar = full_bar + G2_STAGES;
+  uint64_t* tfull_bar = empty_bar + G2_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  const int m_tiles = (M + 2 * G2_BM - 1) / (2 * G2_BM);
+  const int n_tiles = (N + G2_BN - 1) / G2_BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (K + G2_BK - 1) / G2_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + s, 1);
+      mbar_init(tempty_bar + s, 2 * G2_EPI_WARPS);  // every epilogue warp of BOTH CTAs arrives on the leader's
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int n_blk = tile % n_tiles;
+        const int m_blk = tile / n_tiles;
+        for (int kb = 0; kb < k_blocks && ep.act != 101; ++kb, ++it) {
+          const uint32_t stage = it % G2_STAGES;
+          const uint32_t phase = (it / G2_STAGES) & 1u;
+          mbar_wait(empty_bar + stage, phase ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * (G2_A_BYTES + G2_B_BYTES));
+          tma_load_2d_2cta(sA + stage * G2_A_BYTES, &tmA, full_bar + stage, kb * G2_BK,
+                           m_blk * 2 * G2_BM + (int)rank * G2_BM);
+          tma_load_2d_2cta(sB + stage * G2_B_BYTES, &tmB, full_bar + stage, kb * G2_BK,
+                           n_blk * G2_BN + (int)rank * (G2_BN / 2));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * G2_BM, G2_BN);
+      uint32_t it = 0, lt = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
+        const uint32_t as = lt & 1u;
+        const uint32_t aphase = (lt >> 1) & 1u;
+        mbar_wait(tempty_bar + as, aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * G2_BN;
+        for (int kb = 0; kb < k_blocks && ep.act != 101; ++kb, ++it) {
+          const uint32_t stage = it % G2_STAGES;
+          const uint32_t phase = (it / G2_STAGES) & 1u;
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * G2_A_BYTES));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * G2_B_BYTES));
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k)
+            umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta_mc(empty_bar + stage, 0b11);  // frees this smem slot in both CTAs
+        }
+        umma_commit_2cta_mc(tfull_bar + as, 0b11);  // accumulator halves ready in both CTAs
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue warps (2..9, both CTAs) =================
+    const int q = warp & 3;
+    const int ch = (warp - 2) >> 2;
+    constexpr int COLS_PER_WARP = G2_BN / 2;
+    const uint32_t slab = smem_u32(sEpi) + (warp - 2) * 32 * 16 * 4;
+    uint32_t lt = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
+      const int n_blk = tile % n_tiles;
+      const int m_blk = tile / n_tiles;
+      const uint32_t as = lt & 1u;
+      const uint32_t aphase = (lt >> 1) & 1u;
+      mbar_wait(tfull_bar + as, aphase);
+      tc_fence_after();
+      const int row0 = m_blk * 2 * G2_BM + (int)rank * G2_BM + q * 32;
+      const int cbase = ch * COLS_PER_WARP;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BN + cbase;
+      const int gc0 = n_blk * G2_BN + cbase;
+      EpiLane L;
+      epi_setup(L, slab, ep, row0, M, lane);
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP; c += 64) {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(taddr + c, ra);
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + c + 32, rb);
+        if (gc0 + c < N && ep.act != 100) epilogue_chunk<KIND>(ra, L, slab, ep, row0, M, gc0 + c, N, vec_ok, lane);
+        tmem_ld_wait();
+        if (gc0 + c + 32 < N && ep.act != 100) epilogue_chunk<KIND>(rb, L, slab, ep, row0, M, gc0 + c + 32, N, vec_ok, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar + as, 0);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<512>(tmem_base);
+  }
+}
+
+template <int KIND>
+static int launch_2cta_kind(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
+                            int vec_ok, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm_bf16_2cta_kernel<KIND>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("cudaFuncSetAttribute(2cta): ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int m_tiles = (M + 2 * G2_BM - 1) / (2 * G2_BM);
+  const int n_tiles = (N + G2_BN - 1) / G2_BN;
+  int pairs = m_tiles * n_tiles;
+  if (pairs > num_sms / 2) pairs = num_sms / 2;
+  kern<<<2 * pairs, G2_THREADS, G2_SMEM, stream>>>(tmA, tmB, M, N, K, ep, vec_ok);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("gemm 2cta launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
+                     int vec_ok, int num_sms, cudaStream_t stream) {
+  const int kind = (ep.act >= 100) ? EPI_GENERIC : classify_epilogue(ep, vec_ok, N);
+  switch (kind) {
+    case EPI_BF16: return launch_2cta_kind<EPI_BF16>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, stream);
+    case EPI_BF16_GELU: return launch_2cta_kind<EPI_BF16_GELU>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, stream);
+    case EPI_RES_F32: return launch_2cta_kind<EPI_RES_F32>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, stream);
+    case EPI_RES_F32_BF16: return launch_2cta_kind<EPI_RES_F32_BF16>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, stream);
+    default: return launch_2cta_kind<EPI_GENERIC>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, stream);
+  }
+}
+
+}  // namespace hig

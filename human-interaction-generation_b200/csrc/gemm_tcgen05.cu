@@ -13,105 +13,29 @@
 //   * 128 x BN x 64 tiles, STAGES-deep smem ring, accumulator double-buffered in TMEM (2 x BN columns) so the
 //     epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include <string>
 #include "hig_common.cuh"
+#include "gemm_epilogue.cuh"
 #include "hig_internal.h"
 
 namespace hig {
 
-struct GemmEpilogue {
-  const float* bias;      // [N] or nullptr
-  const float* residual;  // fp32 [rows, ldr] or nullptr
-  int ldr;
-  int res_row_mod;        // >0: residual row = m % res_row_mod (positional tables)
-  float* out_f32;         // nullable
-  int ldo_f32;
-  __nv_bfloat16* out_bf16;  // nullable
-  int ldo_bf16;
-  int act;                // 0 none, 1 GELU(erf), 2 SiLU
-};
-
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 template <int BN, int STAGES>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int TOTAL = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;  // +1024 for manual alignment
+  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * 32 * 16 * 4;  // one 32 x 16-word transpose slab per epilogue warp
+  static constexpr int TOTAL = STAGES * (A_BYTES + B_BYTES) + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
 };
-
-template <bool kVec>
-HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const GemmEpilogue& ep, int row, bool row_ok, int col0, int N) {
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-
-  if (kVec) {
-    if (ep.bias) {
-      const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 b = __ldg(b4 + j);
-        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-      }
-    }
-    if (!row_ok) return;
-    if (ep.residual) {
-      const int rr = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
-      const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (size_t)rr * ep.ldr + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 b = __ldg(r4 + j);
-        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-      }
-    }
-    if (ep.act == 1) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
-    } else if (ep.act == 2) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-    }
-    if (ep.out_f32) {
-      float4* o4 = reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ldo_f32 + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
-    if (ep.out_bf16) {
-      uint4* o4 = reinterpret_cast<uint4*>(ep.out_bf16 + (size_t)row * ep.ldo_bf16 + col0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 p;
-        p.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-        p.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-        p.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-        p.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-        o4[j] = p;
-      }
-    }
-  } else {
-    if (!row_ok) return;
-    const int rr = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = col0 + j;
-      if (col < N) {
-        float x = v[j];
-        if (ep.bias) x += __ldg(ep.bias + col);
-        if (ep.residual) x += __ldg(ep.residual + (size_t)rr * ep.ldr + col);
-        if (ep.act == 1) x = gelu_erf_f(x);
-        else if (ep.act == 2) x = silu_f(x);
-        if (ep.out_f32) ep.out_f32[(size_t)row * ep.ldo_f32 + col] = x;
-        if (ep.out_bf16) ep.out_bf16[(size_t)row * ep.ldo_bf16 + col] = __float2bfloat16(x);
-      }
-    }
-  }
-}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -122,7 +46,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * L::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * L::B_BYTES);
+  float* sEpi = reinterpret_cast<float*>(sB + STAGES * L::B_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * L::B_BYTES + L::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -145,7 +70,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + s, 1);
-      mbar_init(tempty_bar + s, 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar + s, GEMM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -205,8 +130,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     __syncwarp();
   } else {
-    // ================= epilogue warps (2..5) =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    // ================= epilogue warps (2..9) =================
+    // warp%4 selects the TMEM lane quarter (hardware rule); the two warps of a quarter split the tile's columns.
+    const int q = warp & 3;
+    const int ch = (warp - 2) >> 2;
+    constexpr int COLS_PER_WARP = BN / 2;
+    const uint32_t slab = smem_u32(sEpi) + (warp - 2) * 32 * 16 * 4;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int n_blk = tile % n_tiles;
@@ -215,18 +144,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const uint32_t aphase = (lt >> 1) & 1u;
       mbar_wait(tfull_bar + as, aphase);
       tc_fence_after();
-      const int row = m_blk * GEMM_BM + q * 32 + lane;
-      const bool row_ok = row < M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      const int row0 = m_blk * GEMM_BM + q * 32;
+      const int cbase = ch * COLS_PER_WARP;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + cbase;
+      const int gc0 = n_blk * BN + cbase;
+      EpiLane L;
+      epi_setup(L, slab, ep, row0, M, lane);
+      // two chunks per iteration: the TMEM load of the second overlaps the stores of the first
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        const int col0 = n_blk * BN + c;
-        if (col0 >= N) break;
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
+      for (int c = 0; c < COLS_PER_WARP; c += 64) {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(taddr + c, ra);
         tmem_ld_wait();
-        if (vec_ok && col0 + 32 <= N) epilogue_chunk<true>(r, ep, row, row_ok, col0, N);
-        else epilogue_chunk<false>(r, ep, row, row_ok, col0, N);
+        tmem_ld_32x32(taddr + c + 32, rb);
+        if (gc0 + c < N) epilogue_chunk<EPI_GENERIC>(ra, L, slab, ep, row0, M, gc0 + c, N, vec_ok, lane);
+        tmem_ld_wait();
+        if (gc0 + c + 32 < N) epilogue_chunk<EPI_GENERIC>(rb, L, slab, ep, row0, M, gc0 + c + 32, N, vec_ok, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -309,6 +242,9 @@ static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, C
   return HIG_OK;
 }
 
+int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
+                     int vec_ok, int num_sms, cudaStream_t stream);
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -350,7 +286,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   if ((lda % 8) || (ldw % 8) || (K % 8)) return set_error(HIG_ERR_INVALID, "gemm: lda/ldw/K must be multiples of 8 (TMA 16B rule)");
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
     return set_error(HIG_ERR_INVALID, "gemm: operands must be 16-byte aligned");
-  if (act < 0 || act > 2) return set_error(HIG_ERR_INVALID, "gemm: bad activation");
+  if ((act < 0 || act > 2) && act != 100 && act != 101) return set_error(HIG_ERR_INVALID, "gemm: bad activation");
 
   GemmEpilogue ep;
   ep.bias = bias; ep.residual = residual; ep.ldr = ldr; ep.res_row_mod = res_row_mod;
@@ -362,10 +298,19 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) vec_ok = 0;
   if (residual && ((reinterpret_cast<uintptr_t>(residual) & 15) || (ldr % 4))) vec_ok = 0;
   if (out_f32 && ((reinterpret_cast<uintptr_t>(out_f32) & 15) || (ldo_f32 % 4))) vec_ok = 0;
-  if (out_bf16 && ((reinterpret_cast<uintptr_t>(out_bf16) & 15) || (ldo_bf16 % 8))) vec_ok = 0;
+  if (out_bf16 && ((reinterpret_cast<uintptr_t>(out_bf16) & 7) || (ldo_bf16 % 4))) vec_ok = 0;
 
-  const bool big_n = N > 128;
   CUtensorMap tmA, tmB;
+  // CTA-pair kernel (256 x 256 tiles, cta_group::2) for the large projections; HIG_GEMM_2CTA=0 disables it
+  static const bool allow_2cta = []() { const char* e = getenv("HIG_GEMM_2CTA"); return !(e && e[0] == '0'); }();
+  if (allow_2cta && M >= 512 && N >= 256) {
+    int rc2 = get_tmap(A, M, K, lda, 128, &tmA);
+    if (rc2) return rc2;
+    rc2 = get_tmap(W, N, K, ldw, 128, &tmB);
+    if (rc2) return rc2;
+    return launch_gemm_2cta(tmA, tmB, M, N, K, ep, vec_ok, num_sms(), stream);
+  }
+  const bool big_n = N > 128;
   int rc = get_tmap(A, M, K, lda, GEMM_BM, &tmA);
   if (rc) return rc;
   rc = get_tmap(W, N, K, ldw, big_n ? 256 : 128, &tmB);

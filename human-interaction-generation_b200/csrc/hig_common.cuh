@@ -41,7 +41,32 @@ HIG_DEVICE float warp_max(float v) {
   return v;
 }
 
-HIG_DEVICE float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+HIG_DEVICE float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// erf via Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7): exact-GELU semantics at a third of erff's instruction
+// count; used by the bf16 GEMM epilogue (the fp32-mode kernels call erff).
+HIG_DEVICE float erf_as_f(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(e, x);
+}
+HIG_DEVICE float gelu_as_f(float v) { return 0.5f * v * (1.0f + erf_as_f(v * 0.70710678118654752440f)); }
+HIG_DEVICE float tanh_approx_f(float v) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+// GELU for the bf16 epilogue: 0.5 v (1 + tanh(sqrt(2/pi) (v + 0.044715 v^3))) on the single-MUFU tanh.approx.
+// |difference to the exact erf GELU| <= 5e-4 absolute (well inside one bf16 ulp of the stored result); the
+// fp32-mode kernels keep erff.  The GEMM epilogue is issue-bound, and erff costs ~4x the instructions.
+HIG_DEVICE float gelu_fast_f(float v) {
+  const float u = v * fmaf(0.044715f * v, v, 1.0f);
+  return 0.5f * v * (1.0f + tanh_approx_f(0.7978845608028654f * u));
+}
 // exact (erf) GELU, as torch.nn.GELU() default
 HIG_DEVICE float gelu_erf_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
@@ -170,6 +195,63 @@ HIG_DEVICE constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
          | (1u << 10)         // B format = BF16
          | ((N >> 3) << 17)   // N / 8
          | ((M >> 4) << 24);  // M / 16
+}
+
+
+// ----------------------------------------------------------------------------------------------
+// thread-block clusters / CTA pairs (cta_group::2)
+// ----------------------------------------------------------------------------------------------
+HIG_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+HIG_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `cta` of this cluster
+HIG_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t}\n"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// 2-CTA TMA load: lands in this CTA's smem, completes tx bytes on the LEADER CTA's mbarrier (peer bit cleared)
+HIG_DEVICE void tma_load_2d_2cta(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0),
+      "r"(c1)
+      : "memory");
+}
+template <uint32_t kCols>
+HIG_DEVICE void tmem_alloc_2cta(uint32_t* smem_result) {  // one warp in EACH CTA of the pair, same warp index
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+HIG_DEVICE void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 x 16: 128 rows from each CTA's smem] * B[N x 16: N/2 rows from each CTA's smem]
+HIG_DEVICE void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once) on the mbarrier at this smem offset in every CTA of `mask` when the issued MMAs have completed
+HIG_DEVICE void umma_commit_2cta_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
 }
 
 }  // namespace hig

@@ -5,8 +5,8 @@
 // LayerNorms (:119,153,155,190,194).  The reference computes self.norm(x) three times per attention block;
 // here it is computed once and written in the GEMM operand type.
 //
-// One warp per row (row width 512 = latent_dim, or 256 = text_latent_dim); every lane owns 8 contiguous
-// elements per 256-wide chunk, so loads are 2x float4 (fp32 in) or 1x uint4 (bf16 in) and stores are 16 B.
+// A warp processes one row at a time (row width 512 = latent_dim, or 256 = text_latent_dim); every lane owns 8
+// contiguous elements per 256-wide chunk, so loads are 2x float4 (fp32 in) or 1x uint4 (bf16 in), stores 16 B.
 // Statistics are two-pass in registers (mean, then centred variance) in fp32, eps = 1e-5, biased variance —
 // the same arithmetic as ATen's native_layer_norm.
 #include "hig_common.cuh"
@@ -43,68 +43,132 @@ template <> struct Io<__nv_bfloat16> {
   }
 };
 
+// Each warp owns a run of `rows_per_warp` consecutive rows inside ONE sequence, so gamma, beta and that
+// sequence's (scale, shift) are loaded once per warp into registers and the row loop only streams x: parameter
+// traffic through L1 drops from 8 KB per row to 8 KB per run.  The arithmetic keeps the reference's order
+// ((n * gamma + beta) * (1 + scale) + shift).  Two rows are in flight per iteration to cover HBM latency.
+constexpr int LN_WARPS = 4;
+
 template <int WIDTH, typename TIn, typename TOut>
-__global__ void __launch_bounds__(256)
-ln_film_silu_kernel(const TIn* __restrict__ x, int rows, int rows_per_seq, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, const float* __restrict__ scale_shift, int ss_stride,
-                    int apply_silu, TOut* __restrict__ out) {
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_film_silu_kernel(const TIn* __restrict__ x, int rows, int rows_per_seq, int rows_per_warp, int runs_per_seq,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ scale_shift, int ss_stride, int apply_silu, TOut* __restrict__ out) {
   constexpr int CHUNKS = WIDTH / 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  if (row >= rows) return;
-  const TIn* xr = x + (size_t)row * WIDTH;
-  float v[CHUNKS][8];
-  float s = 0.f;
+  const int run = blockIdx.x * LN_WARPS + warp;
+  const int seq = run / runs_per_seq, piece = run - seq * runs_per_seq;
+  int r0 = seq * rows_per_seq + piece * rows_per_warp;
+  int r1 = min(r0 + rows_per_warp, (seq + 1) * rows_per_seq);
+  r1 = min(r1, rows);
+  if (r0 >= r1) return;
+
+  float A[CHUNKS][8], B[CHUNKS][8];
 #pragma unroll
   for (int c = 0; c < CHUNKS; ++c) {
-    Io<TIn>::load8(xr + c * 256 + lane * 8, v[c]);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[c][j];
+    Io<float>::load8(gamma + c * 256 + lane * 8, A[c]);
+    Io<float>::load8(beta + c * 256 + lane * 8, B[c]);
   }
-  const float mean = warp_sum(s) * (1.0f / WIDTH);
-  float ss = 0.f;
-#pragma unroll
-  for (int c = 0; c < CHUNKS; ++c)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float d = v[c][j] - mean;
-      ss = fmaf(d, d, ss);
-    }
-  const float var = warp_sum(ss) * (1.0f / WIDTH);
-  const float rstd = 1.0f / sqrtf(var + 1e-5f);
-
-  const float* ssp = scale_shift ? scale_shift + (size_t)(row / rows_per_seq) * ss_stride : nullptr;
+  // bf16 output (product path): fold FiLM into the affine once per run, y = n * A' + B' with A' = gamma (1 + scale),
+  // B' = beta (1 + scale) + shift, and use single-MUFU sigmoid (tanh.approx) — the kernel is issue-bound, not
+  // HBM-bound, at ~25 instructions per element.  fp32 output (fp32 mode): reference evaluation order, precise expf.
+  constexpr bool kFast = sizeof(TOut) == 2;
+  float SC[CHUNKS][8], SH[CHUNKS][8];
 #pragma unroll
   for (int c = 0; c < CHUNKS; ++c) {
     const int col = c * 256 + lane * 8;
-    float g[8], b[8];
-    Io<float>::load8(gamma + col, g);
-    Io<float>::load8(beta + col, b);
-    float o[8];
+    if (scale_shift) {
+      const float* ssp = scale_shift + (size_t)seq * ss_stride;
+      Io<float>::load8(ssp + col, SC[c]);
+      Io<float>::load8(ssp + WIDTH + col, SH[c]);
+      if (kFast) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[j] + b[j];
-    if (ssp) {
-      float sc[8], sh[8];
-      Io<float>::load8(ssp + col, sc);
-      Io<float>::load8(ssp + WIDTH + col, sh);
+        for (int j = 0; j < 8; ++j) {
+          const float m1 = 1.0f + SC[c][j];
+          A[c][j] *= m1;
+          B[c][j] = fmaf(B[c][j], m1, SH[c][j]);
+        }
+      }
+    } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = o[j] * (1.0f + sc[j]) + sh[j];
+      for (int j = 0; j < 8; ++j) { SC[c][j] = 0.f; SH[c][j] = 0.f; }
     }
-    if (apply_silu) {
+  }
+
+  auto finish = [&](float (&v)[CHUNKS][8], int row) {
+    float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = o[j] / (1.0f + expf(-o[j]));
+    for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[c][j];
+    const float mean = warp_sum(s) * (1.0f / WIDTH);
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[c][j] -= mean;
+        ss = fmaf(v[c][j], v[c][j], ss);
+      }
+    const float var = warp_sum(ss) * (1.0f / WIDTH) + 1e-5f;
+    const float rstd = kFast ? rsqrtf(var) : 1.0f / sqrtf(var);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t;
+        if (kFast) {
+          t = fmaf(v[c][j] * rstd, A[c][j], B[c][j]);
+          if (apply_silu) {
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * t));
+            t = t * fmaf(th, 0.5f, 0.5f);
+          }
+        } else {
+          t = v[c][j] * rstd * A[c][j] + B[c][j];
+          if (scale_shift) t = t * (1.0f + SC[c][j]) + SH[c][j];
+          if (apply_silu) t = t / (1.0f + expf(-t));
+        }
+        o[j] = t;
+      }
+      Io<TOut>::store8(out + (size_t)row * WIDTH + c * 256 + lane * 8, o);
     }
-    Io<TOut>::store8(out + (size_t)row * WIDTH + col, o);
+  };
+
+  int r = r0;
+  for (; r + 1 < r1; r += 2) {
+    float v0[CHUNKS][8], v1[CHUNKS][8];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      Io<TIn>::load8(x + (size_t)r * WIDTH + c * 256 + lane * 8, v0[c]);
+      Io<TIn>::load8(x + (size_t)(r + 1) * WIDTH + c * 256 + lane * 8, v1[c]);
+    }
+    finish(v0, r);
+    finish(v1, r + 1);
+  }
+  if (r < r1) {
+    float v0[CHUNKS][8];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) Io<TIn>::load8(x + (size_t)r * WIDTH + c * 256 + lane * 8, v0[c]);
+    finish(v0, r);
   }
 }
 
 template <int WIDTH, typename TIn, typename TOut>
 static void launch_ln(const void* x, int rows, int rows_per_seq, const float* gamma, const float* beta,
                       const float* scale_shift, int ss_stride, int apply_silu, void* out, cudaStream_t stream) {
-  const int blocks = (rows + 7) / 8;
-  ln_film_silu_kernel<WIDTH, TIn, TOut><<<blocks, 256, 0, stream>>>(
-      reinterpret_cast<const TIn*>(x), rows, rows_per_seq, gamma, beta, scale_shift, ss_stride, apply_silu,
-      reinterpret_cast<TOut*>(out));
+  // aim for ~24 runs (warps) per SM; a run never crosses a sequence boundary
+  const int n_seq = (rows + rows_per_seq - 1) / rows_per_seq;
+  int rows_per_warp = (int)(((long long)rows + 148 * 24 - 1) / (148 * 24));
+  if (rows_per_warp < 1) rows_per_warp = 1;
+  if (rows_per_warp > rows_per_seq) rows_per_warp = rows_per_seq;
+  const int runs_per_seq = (rows_per_seq + rows_per_warp - 1) / rows_per_warp;
+  const long long runs = (long long)n_seq * runs_per_seq;
+  const int blocks = (int)((runs + LN_WARPS - 1) / LN_WARPS);
+  ln_film_silu_kernel<WIDTH, TIn, TOut><<<blocks, LN_WARPS * 32, 0, stream>>>(
+      reinterpret_cast<const TIn*>(x), rows, rows_per_seq, rows_per_warp, runs_per_seq, gamma, beta, scale_shift,
+      ss_stride, apply_silu, reinterpret_cast<TOut*>(out));
 }
 
 int ln_film_silu(const void* x, int x_dtype, int rows, int width, int rows_per_seq, const float* gamma,
@@ -113,6 +177,7 @@ int ln_film_silu(const void* x, int x_dtype, int rows, int width, int rows_per_s
   if (!x || !out || !gamma || !beta || rows <= 0) return set_error(HIG_ERR_INVALID, "ln_film_silu: bad arguments");
   if (width != 512 && width != 256) return set_error(HIG_ERR_UNSUPPORTED, "ln_film_silu: width must be 256 or 512");
   if (rows_per_seq <= 0) rows_per_seq = 1;
+  if (!scale_shift) rows_per_seq = rows;  // no per-sequence parameters: runs may span sequences
   if (scale_shift && (ss_stride % 4)) return set_error(HIG_ERR_INVALID, "ln_film_silu: ss_stride % 4 != 0");
   using bf = __nv_bfloat16;
 #define HIG_LN_CASE(W, TI, TO) \

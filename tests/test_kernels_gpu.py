@@ -57,7 +57,9 @@ def test_gemm_bf16_epilogues(cuda, M, N, K, act):
     ops.gemm(a, w, bias=bias, residual=res, out_f32=o32, out_bf16=o16, act=act)
     ref = a.float() @ w.float().t() + bias + res
     ref = F.gelu(ref) if act == 1 else (F.silu(ref) if act == 2 else ref)
-    assert _rel(o32, ref) < 5e-6, _rel(o32, ref)
+    # act=1: the bf16 epilogue evaluates GELU with tanh.approx (|diff to erf-GELU| <= 5e-4 abs, below one bf16 ulp)
+    assert _rel(o32, ref) < (5e-6 if act != 1 else 1e-3), _rel(o32, ref)
+    assert (o32 - ref).abs().max().item() < (1e-4 if act != 1 else 1.5e-3)
     if o16 is not None:
         assert _rel(o16.float(), ref) < 4e-3
     # positional residual table (row = m % mod) and strided output
