@@ -1,5 +1,6 @@
 // extern "C" boundary of libhig_b200.so — see include/hig_b200.h for the contract of every entry point.
 #include <atomic>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include "hig_internal.h"
@@ -29,6 +30,36 @@ const char* hig_last_error(void) {
 }
 
 unsigned long long hig_launch_count(void) { return hig::g_launches.load(std::memory_order_relaxed); }
+
+int hig_l2_persist(const void* ptr, unsigned long long bytes, float hit_ratio, void* stream) {
+  // Pin a hot buffer (the fp32 residual stream) in the 126 MB L2 with an access-policy window on `stream`:
+  // every kernel launched (or captured) on that stream afterwards treats [ptr, ptr+bytes) as persisting.
+  int dev = 0, max_persist = 0, max_window = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  if (ptr && bytes > 0 && max_persist > 0) {
+    size_t want = bytes < (size_t)max_persist ? (size_t)bytes : (size_t)max_persist;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(static_cast<cudaStream_t>(stream), &cap);
+    if (cap == cudaStreamCaptureStatusNone) {  // device limits cannot change while a capture is open
+      cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      if (e != cudaSuccess) return hig::set_error(HIG_ERR_CUDA, std::string("cudaDeviceSetLimit: ") + cudaGetErrorString(e));
+    }
+    attr.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+    attr.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? (size_t)bytes : (size_t)max_window;
+    attr.accessPolicyWindow.hitRatio = hit_ratio;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  } else {
+    attr.accessPolicyWindow.num_bytes = 0;  // disable
+  }
+  cudaError_t e = cudaStreamSetAttribute(static_cast<cudaStream_t>(stream), cudaStreamAttributeAccessPolicyWindow, &attr);
+  if (e != cudaSuccess) return hig::set_error(HIG_ERR_CUDA, std::string("cudaStreamSetAttribute: ") + cudaGetErrorString(e));
+  return HIG_OK;
+}
 
 int hig_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                   const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, void* out_bf16,

@@ -72,9 +72,11 @@ eff_attn_bf16_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, con
                      const int* __restrict__ length, int S, int T, int pair_shift, int mask_v) {
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int TP = (T + 15) & ~15;
+  // Q_ONLY (text apply) only stages Q and A: a third of the shared memory, so five CTAs fit per SM instead of two
+  const int kv_rows = (mode == 3) ? 0 : TP;
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
-  __nv_bfloat16* sV = sK + TP * ATT_STRIDE;
-  __nv_bfloat16* sQ = sV + TP * ATT_STRIDE;
+  __nv_bfloat16* sV = sK + kv_rows * ATT_STRIDE;
+  __nv_bfloat16* sQ = sV + kv_rows * ATT_STRIDE;
   __nv_bfloat16* sA = sQ + TP * ATT_STRIDE;
   float* sred = reinterpret_cast<float*>(sA + HD * ATT_STRIDE);  // [ATT_WARPS][64] partials, then [64] inverse sums
   float* sinv = sred + ATT_WARPS * 64;
@@ -400,7 +402,7 @@ int eff_attn(int mode, const void* q, int ldq, const void* k, const void* v, int
     if ((do_q && ((ldq % 8) || (ldy % 8))) || (do_kv && (ldkv % 8)))
       return set_error(HIG_ERR_INVALID, "eff_attn: bf16 leading dimensions must be multiples of 8");
     const int TP = (T + 15) & ~15;
-    const size_t smem = (size_t)(3 * TP + HD) * ATT_STRIDE * 2 + (ATT_WARPS + 1) * 64 * sizeof(float);
+    const size_t smem = (size_t)((mode == 3 ? 1 : 3) * TP + HD) * ATT_STRIDE * 2 + (ATT_WARPS + 1) * 64 * sizeof(float);
     static size_t configured = 0;
     if (smem > configured) {
       e = cudaFuncSetAttribute(eff_attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

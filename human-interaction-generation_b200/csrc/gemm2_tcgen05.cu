@@ -27,7 +27,7 @@ constexpr int G2_EPI_WARPS = 8;
 constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
 constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;          // 16 KB
 constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;    // 16 KB
-constexpr int G2_EPI_BYTES = G2_EPI_WARPS * 32 * 16 * 4;
+constexpr int G2_EPI_BYTES = G2_EPI_WARPS * 32 * 32 * 4;
 constexpr int G2_BAR_BYTES = (2 * G2_STAGES + 4) * 8 + 16;
 constexpr int G2_SMEM = G2_STAGES * (G2_A_BYTES + G2_B_BYTES) + G2_EPI_BYTES + G2_BAR_BYTES + 1024;
 
@@ -127,30 +127,44 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int q = warp & 3;
     const int ch = (warp - 2) >> 2;
     constexpr int COLS_PER_WARP = G2_BN / 2;
-    const uint32_t slab = smem_u32(sEpi) + (warp - 2) * 32 * 16 * 4;
+    const uint32_t slab = smem_u32(sEpi) + (warp - 2) * 32 * 32 * 4;
     uint32_t lt = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
       const int n_blk = tile % n_tiles;
       const int m_blk = tile / n_tiles;
       const uint32_t as = lt & 1u;
       const uint32_t aphase = (lt >> 1) & 1u;
-      mbar_wait(tfull_bar + as, aphase);
-      tc_fence_after();
       const int row0 = m_blk * 2 * G2_BM + (int)rank * G2_BM + q * 32;
       const int cbase = ch * COLS_PER_WARP;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BN + cbase;
       const int gc0 = n_blk * G2_BN + cbase;
       EpiLane L;
       epi_setup(L, slab, ep, row0, M, lane);
+      if (KIND != EPI_GENERIC) {
+        // specialised kinds (N % 32 == 0, 16-byte friendly): bias / residual of chunk k+1 are fetched while chunk k
+        // is transposed and stored; chunk 0's are in flight before the accumulator is even ready.
+        EpiPre P[2];
+        epi_prefetch<KIND>(P[0], L, ep, gc0);
+        mbar_wait(tfull_bar + as, aphase);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < COLS_PER_WARP / 32; ++k) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + k * 32, r);
+          if (k + 1 < COLS_PER_WARP / 32 && gc0 + (k + 1) * 32 < N) epi_prefetch<KIND>(P[(k + 1) & 1], L, ep, gc0 + (k + 1) * 32);
+          tmem_ld_wait();
+          if (gc0 + k * 32 < N) epi_finish<KIND>(r, P[k & 1], L, ep, gc0 + k * 32);
+        }
+      } else {
+        mbar_wait(tfull_bar + as, aphase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP; c += 64) {
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(taddr + c, ra);
-        tmem_ld_wait();
-        tmem_ld_32x32(taddr + c + 32, rb);
-        if (gc0 + c < N && ep.act != 100) epilogue_chunk<KIND>(ra, L, slab, ep, row0, M, gc0 + c, N, vec_ok, lane);
-        tmem_ld_wait();
-        if (gc0 + c + 32 < N && ep.act != 100) epilogue_chunk<KIND>(rb, L, slab, ep, row0, M, gc0 + c + 32, N, vec_ok, lane);
+        for (int c = 0; c < COLS_PER_WARP; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait();
+          if (gc0 + c < N && ep.act != 100) epilogue_chunk<EPI_GENERIC>(r, L, slab, ep, row0, M, gc0 + c, N, vec_ok, lane);
+        }
       }
       tc_fence_before();
       __syncwarp();

@@ -32,19 +32,19 @@ HIG_DEVICE float ld_shared_f1(uint32_t addr) {
 
 // Rare path (N or a leading dimension not 16-byte friendly, e.g. the 263-wide output heads): element-wise with
 // bounds checks, still coalesced across the warp.  Kept out of line so the hot path stays small in the I-cache.
-static __device__ __noinline__ void epilogue_half_scalar(uint32_t slab, GemmEpilogue ep, int row0, int M, int col0, int N,
-                                                  int lane) {
-  const int sub = lane >> 2, cg = lane & 3;
+static __device__ __noinline__ void epilogue_chunk_scalar(uint32_t slab, GemmEpilogue ep, int row0, int M, int col0,
+                                                          int N, int lane) {
+  const int sub = lane >> 3, cg = lane & 7;
   const int gcol = col0 + cg * 4;
-  for (int i = 0; i < 4; ++i) {
-    const int rl = i * 8 + sub;
+  for (int i = 0; i < 8; ++i) {
+    const int rl = i * 4 + sub;
     const int row = row0 + rl;
     if (row >= M) continue;
     const int rr = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
     for (int j = 0; j < 4; ++j) {
       const int col = gcol + j;
       if (col < N) {
-        float x = ld_shared_f1(slab + (rl * 16 + ((cg ^ ((rl >> 1) & 3)) << 2) + j) * 4);
+        float x = ld_shared_f1(slab + rl * 128 + ((cg ^ (rl & 7)) << 4) + j * 4);
         if (ep.bias) x += __ldg(ep.bias + col);
         if (ep.residual) x += __ldg(ep.residual + (size_t)rr * ep.ldr + col);
         if (ep.act == 1) x = gelu_fast_f(x);
@@ -66,115 +66,162 @@ enum EpiKind : int {
   EPI_RES_F32_BF16 = 4  // ... and a bf16 copy of the stream  (feeds the FFN / output heads)
 };
 
-// Per-warp, per-tile constants hoisted out of the chunk loop.  Lane l works on rows sub + 8 i (i = 0..3) and the
-// 16-byte column group cg of every half-chunk; its four rows are 8 rows apart, so one base pointer per tensor plus a
-// constant stride reaches all of them.  (rl >> 1) & 3 is the same for the four rows, hence one swizzled slab address.
+// Epilogue of one 32-row x 32-column fp32 chunk owned by one warp.
+// tcgen05.ld hands every lane one ROW (32 consecutive columns): storing that straight to global memory makes each
+// warp-wide store touch 32 different cache lines.  The chunk is therefore transposed through a per-warp 4 KB
+// shared-memory slab (32 rows x 128 B, 16-byte chunks XOR-swizzled with row & 7: conflict-free both for the
+// row-owner writes and for the coalesced reads), after which lane l owns columns 4*(l%8)..+3 of rows l/8 + 4 i
+// (i = 0..7): bias / residual / activation are applied and stored from that layout, so every global access of a
+// warp covers 4 rows x 128 contiguous bytes.  Everything that does not depend on the accumulator (bias and
+// residual loads, addresses) is issued before the shared-memory round trip: the epilogue warps are latency-bound.
 struct EpiLane {
   uint32_t slab_st;    // shared address of this lane's row in the slab (row-owner writes)
-  uint32_t slab_ld0;   // shared address of (row sub, chunk cg) in the coalesced layout; row i*8+sub = + i*512 B
+  uint32_t slab_ld[2]; // shared address of (row sub, chunk cg) for even / odd i; row sub + 4 i = + i * 512 B
   int sw, cg, row_first;
-  uint32_t row_ok;     // bit i: row_first + 8 i < M
+  uint32_t row_ok;     // bit i: row_first + 4 i < M
   float* o32;          // element (row_first, cg*4) of each tensor; null when unused
   __nv_bfloat16* o16;
   const float* res;
 };
 
 HIG_DEVICE void epi_setup(EpiLane& L, uint32_t slab, const GemmEpilogue& ep, int row0, int M, int lane) {
-  const int sub = lane >> 2;
-  L.cg = lane & 3;
-  L.sw = (lane >> 1) & 3;
-  L.slab_st = slab + lane * 64;
-  L.slab_ld0 = slab + (sub * 16 + ((L.cg ^ ((sub >> 1) & 3)) << 2)) * 4;
+  const int sub = lane >> 3;
+  L.cg = lane & 7;
+  L.sw = lane & 7;
+  L.slab_st = slab + lane * 128;
+  L.slab_ld[0] = slab + sub * 128 + ((L.cg ^ sub) << 4);
+  L.slab_ld[1] = slab + sub * 128 + ((L.cg ^ sub ^ 4) << 4);
   L.row_first = row0 + sub;
   L.row_ok = 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) L.row_ok |= ((L.row_first + 8 * i < M) ? 1u : 0u) << i;
+  for (int i = 0; i < 8; ++i) L.row_ok |= ((L.row_first + 4 * i < M) ? 1u : 0u) << i;
   const size_t r = (size_t)L.row_first;
   L.o32 = ep.out_f32 ? ep.out_f32 + r * ep.ldo_f32 + L.cg * 4 : nullptr;
   L.o16 = ep.out_bf16 ? ep.out_bf16 + r * ep.ldo_bf16 + L.cg * 4 : nullptr;
   L.res = ep.residual ? ep.residual + r * ep.ldr + L.cg * 4 : nullptr;
 }
 
-// One 32-row x 16-column half-chunk: row-owner registers -> swizzled slab -> coalesced layout -> global.
-// col0 is the global column of the half-chunk's first column.
 template <int KIND>
-HIG_DEVICE void epilogue_half(const uint32_t* r16, const EpiLane& L, uint32_t slab, const GemmEpilogue& ep, int row0,
-                              int M, int col0, int N, int vec_ok, int lane) {
+HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const EpiLane& L, uint32_t slab, const GemmEpilogue& ep,
+                               int row0, int M, int col0, int N, int vec_ok, int lane) {
   const int gcol = col0 + L.cg * 4;
-  const bool vec = (KIND != EPI_GENERIC) || (vec_ok && (gcol + 4 <= N));
+  // warp-uniform: the whole chunk takes the vector path or the scalar one
+  const bool vec = (KIND != EPI_GENERIC) || (vec_ok && (col0 + 32 <= N));
   const bool has_res = (KIND == EPI_GENERIC) ? (ep.residual != nullptr) : (KIND >= EPI_RES_F32);
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 rs[4];
+  float4 rs[8];
   if (vec) {
     if (KIND != EPI_GENERIC || ep.bias) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol));
     if (has_res) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
         rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if ((L.row_ok >> i) & 1u) {
-          const float* rp = L.res + (size_t)(8 * i) * ep.ldr + col0;
+          const float* rp = L.res + (size_t)(4 * i) * ep.ldr + col0;
           if (KIND == EPI_GENERIC && ep.res_row_mod > 0)
-            rp = ep.residual + (size_t)((L.row_first + 8 * i) % ep.res_row_mod) * ep.ldr + gcol;
+            rp = ep.residual + (size_t)((L.row_first + 4 * i) % ep.res_row_mod) * ep.ldr + gcol;
           rs[i] = __ldg(reinterpret_cast<const float4*>(rp));
         }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    st_shared_f4(L.slab_st + ((j ^ L.sw) << 4), __uint_as_float(r16[4 * j]), __uint_as_float(r16[4 * j + 1]),
-                 __uint_as_float(r16[4 * j + 2]), __uint_as_float(r16[4 * j + 3]));
+  for (int j = 0; j < 8; ++j)
+    st_shared_f4(L.slab_st + ((j ^ L.sw) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
   __syncwarp();
   if (vec) {
-    float4 v[4];
+    float4 v[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[i] = ld_shared_f4(L.slab_ld0 + i * 512);
+    for (int i = 0; i < 8; ++i) {
+      v[i] = ld_shared_f4(L.slab_ld[i & 1] + i * 512);
       v[i].x += bias4.x; v[i].y += bias4.y; v[i].z += bias4.z; v[i].w += bias4.w;
     }
     if (has_res) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { v[i].x += rs[i].x; v[i].y += rs[i].y; v[i].z += rs[i].z; v[i].w += rs[i].w; }
+      for (int i = 0; i < 8; ++i) { v[i].x += rs[i].x; v[i].y += rs[i].y; v[i].z += rs[i].z; v[i].w += rs[i].w; }
     }
     const int act = (KIND == EPI_GENERIC) ? ep.act : (KIND == EPI_BF16_GELU ? 1 : 0);
     if (act == 1) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
         v[i].x = gelu_fast_f(v[i].x); v[i].y = gelu_fast_f(v[i].y); v[i].z = gelu_fast_f(v[i].z); v[i].w = gelu_fast_f(v[i].w);
       }
     } else if (act == 2) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
         v[i].x = silu_f(v[i].x); v[i].y = silu_f(v[i].y); v[i].z = silu_f(v[i].z); v[i].w = silu_f(v[i].w);
       }
     }
     const bool w32 = (KIND == EPI_GENERIC) ? (L.o32 != nullptr) : (KIND >= EPI_RES_F32);
     const bool w16 = (KIND == EPI_GENERIC) ? (L.o16 != nullptr) : (KIND != EPI_RES_F32);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       if ((L.row_ok >> i) & 1u) {
-        if (w32) *reinterpret_cast<float4*>(L.o32 + (size_t)(8 * i) * ep.ldo_f32 + col0) = v[i];
+        if (w32) *reinterpret_cast<float4*>(L.o32 + (size_t)(4 * i) * ep.ldo_f32 + col0) = v[i];
         if (w16)
-          *reinterpret_cast<uint2*>(L.o16 + (size_t)(8 * i) * ep.ldo_bf16 + col0) =
+          *reinterpret_cast<uint2*>(L.o16 + (size_t)(4 * i) * ep.ldo_bf16 + col0) =
               make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
       }
     }
   } else {
-    epilogue_half_scalar(slab, ep, row0, M, col0, N, lane);
+    epilogue_chunk_scalar(slab, ep, row0, M, col0, N, lane);
   }
-  __syncwarp();  // the slab is rewritten by the next half-chunk
+  __syncwarp();  // the slab is rewritten by the next chunk
+}
+
+// ---- split form used by the specialised kinds: global loads one chunk ahead of the accumulator ----------------
+struct EpiPre {
+  float4 bias4;
+  float4 rs[8];
+};
+
+template <int KIND>
+HIG_DEVICE void epi_prefetch(EpiPre& P, const EpiLane& L, const GemmEpilogue& ep, int col0) {
+  P.bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + L.cg * 4));
+  if (KIND >= EPI_RES_F32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      P.rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((L.row_ok >> i) & 1u)
+        P.rs[i] = __ldg(reinterpret_cast<const float4*>(L.res + (size_t)(4 * i) * ep.ldr + col0));
+    }
+  }
 }
 
 template <int KIND>
-HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const EpiLane& L, uint32_t slab, const GemmEpilogue& ep,
-                               int row0, int M, int col0, int N, int vec_ok, int lane) {
-  epilogue_half<KIND>(&r[0], L, slab, ep, row0, M, col0, N, vec_ok, lane);
-  if (col0 + 16 < N) epilogue_half<KIND>(&r[16], L, slab, ep, row0, M, col0 + 16, N, vec_ok, lane);
+HIG_DEVICE void epi_finish(const uint32_t (&r)[32], const EpiPre& P, const EpiLane& L, const GemmEpilogue& ep,
+                           int col0) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    st_shared_f4(L.slab_st + ((j ^ L.sw) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+  __syncwarp();
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = ld_shared_f4(L.slab_ld[i & 1] + i * 512);
+    v[i].x += P.bias4.x; v[i].y += P.bias4.y; v[i].z += P.bias4.z; v[i].w += P.bias4.w;
+    if (KIND >= EPI_RES_F32) { v[i].x += P.rs[i].x; v[i].y += P.rs[i].y; v[i].z += P.rs[i].z; v[i].w += P.rs[i].w; }
+    if (KIND == EPI_BF16_GELU) {
+      v[i].x = gelu_fast_f(v[i].x); v[i].y = gelu_fast_f(v[i].y); v[i].z = gelu_fast_f(v[i].z); v[i].w = gelu_fast_f(v[i].w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if ((L.row_ok >> i) & 1u) {
+      if (KIND >= EPI_RES_F32) *reinterpret_cast<float4*>(L.o32 + (size_t)(4 * i) * ep.ldo_f32 + col0) = v[i];
+      if (KIND != EPI_RES_F32)
+        *reinterpret_cast<uint2*>(L.o16 + (size_t)(4 * i) * ep.ldo_bf16 + col0) =
+            make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+    }
+  }
+  __syncwarp();  // the slab is rewritten by the next chunk
 }
 
 // classify a runtime epilogue into the specialised kinds (host side)
 inline int classify_epilogue(const GemmEpilogue& ep, int vec_ok, int N) {
-  if (!vec_ok || (N % 16) != 0 || !ep.bias || ep.res_row_mod > 0) return EPI_GENERIC;
+  if (!vec_ok || (N % 32) != 0 || !ep.bias || ep.res_row_mod > 0) return EPI_GENERIC;
   if (!ep.residual && !ep.out_f32 && ep.out_bf16) {
     if (ep.act == 0) return EPI_BF16;
     if (ep.act == 1) return EPI_BF16_GELU;

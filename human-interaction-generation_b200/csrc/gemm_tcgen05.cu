@@ -33,7 +33,7 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * 32 * 16 * 4;  // one 32 x 16-word transpose slab per epilogue warp
+  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * 32 * 32 * 4;  // one 32 x 16-word transpose slab per epilogue warp
   static constexpr int TOTAL = STAGES * (A_BYTES + B_BYTES) + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
 };
 
@@ -135,7 +135,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int q = warp & 3;
     const int ch = (warp - 2) >> 2;
     constexpr int COLS_PER_WARP = BN / 2;
-    const uint32_t slab = smem_u32(sEpi) + (warp - 2) * 32 * 16 * 4;
+    const uint32_t slab = smem_u32(sEpi) + (warp - 2) * 32 * 32 * 4;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int n_blk = tile % n_tiles;

@@ -235,7 +235,12 @@ class GaussianDiffusion:
             seed = self.seed
             self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
 
+            import os as _os
+            persist = _os.environ.get("HIG_L2_PERSIST", "1") != "0"
+
             def step():
+                if persist:
+                    ops.l2_persist(ws["xres"])
                 eps = eng.run_packed(ws, st["t"], st["xfp"], st["a_text"], S, T)
                 ops.ddpm_step(st["x"], eps, st["t"], coef, noise=st["z"], seed=seed, packed=ws["xa"], t_next=st["t"])
 

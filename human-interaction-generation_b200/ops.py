@@ -155,3 +155,13 @@ def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, out=None):
     rc = lib.hig_q_sample(_ptr(x0), _ptr(noise), _ptr(t), _ptr(sqrt_ac), _ptr(sqrt_1mac), S, TC, _ptr(out), _stream())
     _lib.check(rc, "hig_q_sample")
     return out
+
+
+def l2_persist(t, hit_ratio=1.0):
+    """Pin tensor `t` in L2 for kernels launched/captured on the current stream (None clears the window)."""
+    lib = _lib.load()
+    if t is None:
+        rc = lib.hig_l2_persist(None, 0, 0.0, _stream())
+    else:
+        rc = lib.hig_l2_persist(_ptr(t), t.numel() * t.element_size(), float(hit_ratio), _stream())
+    _lib.check(rc, "hig_l2_persist")

@@ -39,6 +39,10 @@ const char* hig_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long hig_launch_count(void);
 
+/* L2 residency hint (no reference counterpart): pins [ptr, ptr+bytes) — the fp32 residual stream — in the 126 MB L2
+ * through an access-policy window on `stream`; ptr == NULL clears it. */
+int hig_l2_persist(const void* ptr, unsigned long long bytes, float hit_ratio, void* stream);
+
 /* out = act(A[M,K] . W[N,K]^T + bias + residual), bf16 operands, fp32 accumulate on tcgen05/TMEM.
  * Replaces every nn.Linear on the path (models/interaction_transformer.py:74-97,105-128,137-163,172-205,
  * 254-263,471-478,508-509) with the bias add, GELU (FFN, :262), SiLU (time_embed, :476) and the residual
