@@ -35,6 +35,17 @@ SIGNATURES = {
     "hig_ddpm_step": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ull,
                       c_void_p, c_int, c_int, c_void_p, c_void_p],
     "hig_q_sample": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
+    # training path
+    "hig_gemm_bf16_splitk": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
+    "hig_transpose": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
+                      c_void_p],
+    "hig_colsum": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "hig_act_fwd": [c_void_p, c_int, ctypes.c_longlong, c_int, c_void_p, c_int, c_void_p],
+    "hig_act_bwd": [c_void_p, c_int, c_void_p, c_int, ctypes.c_longlong, c_int, c_void_p, c_int, c_void_p],
+    "hig_ln_film_silu_bwd": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                             c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "hig_eff_attn_bwd": [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                         c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
 }
 _RESTYPE = {"hig_last_error": ctypes.c_char_p, "hig_launch_count": c_ull}
 

@@ -1,0 +1,361 @@
+// Training-path helper kernels (HBM-bound): operand transposition for the dgrad/wgrad GEMMs, column sums (bias and
+// positional-table gradients), elementwise activation forward/backward, and the backward of the fused
+// LayerNorm + FiLM + SiLU kernel.
+//
+// Reference: the reference has no backward code of its own — torch.autograd differentiates
+//   StylizationBlock.forward            codes/models/interaction_transformer.py:86-97
+//   nn.LayerNorm call sites             :119,153,155,190,194
+//   FFN.forward (exact erf GELU)        :261-264
+//   time_embed (SiLU)                   :474-478
+// These kernels are the hand-written derivatives of the forward kernels in ln_film.cu / gemm_*.cu.
+#include "hig_common.cuh"
+#include "hig_internal.h"
+
+namespace hig {
+
+template <typename T> HIG_DEVICE float ld_as_f(const T* p);
+template <> HIG_DEVICE float ld_as_f<float>(const float* p) { return *p; }
+template <> HIG_DEVICE float ld_as_f<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> HIG_DEVICE void st_from_f(T* p, float v);
+template <> HIG_DEVICE void st_from_f<float>(float* p, float v) { *p = v; }
+template <> HIG_DEVICE void st_from_f<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// ------------------------------------------------------------------------------------------------
+// transpose: in [M,N] (ld_in) -> outT [N,M] (ld_t), optional straight copy in the output type (ld_c) and optional
+// column sums (fp32, atomically accumulated: the caller zeroes them).  64x64 tiles through padded shared memory,
+// coalesced on both sides.  rows_keep_mod > 0: rows with (m % rows_keep_mod) == 0 are treated as zero (frame 0 of
+// every sequence belongs to the out2 head, :613-616).
+// ------------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const TIn* __restrict__ in, int M, int N, int ld_in, TOut* __restrict__ outT, int ld_t,
+                 TOut* __restrict__ copy, int ld_c, float* __restrict__ colsum, int rows_zero_mod) {
+  __shared__ float tile[64][65];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tid = threadIdx.x;
+  // load: thread -> (row = tid / 16 + 16 i, 4 consecutive columns)
+  {
+    const int c4 = (tid & 15) * 4, r = tid >> 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rl = r + 16 * i, m = m0 + rl;
+      const bool zero_row = rows_zero_mod > 0 && (m % rows_zero_mod) == 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + c4 + j;
+        float v = 0.f;
+        if (m < M && n < N && !zero_row) v = ld_as_f(in + (size_t)m * ld_in + n);
+        tile[rl][c4 + j] = v;
+        if (copy && m < M && n < N) st_from_f(copy + (size_t)m * ld_c + n, v);
+      }
+    }
+  }
+  __syncthreads();
+  // store: thread -> (output row = input column nl = tid / 8 + 32 p, 8 consecutive input rows)
+  const int seg = (tid & 7) * 8;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int nl = (tid >> 3) + 32 * p, n = n0 + nl;
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = tile[seg + j][nl];
+      part += v;
+      const int m = m0 + seg + j;
+      if (outT && n < N && m < M) st_from_f(outT + (size_t)n * ld_t + m, v);
+    }
+    if (colsum) {
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      if ((tid & 7) == 0 && n < N) atomicAdd(colsum + n, part);
+    }
+  }
+}
+
+int transpose(const void* in, int in_dtype, int M, int N, int ld_in, void* outT, int ld_t, void* copy, int ld_c,
+              int out_dtype, float* colsum, int rows_zero_mod, cudaStream_t stream) {
+  if (!in || M <= 0 || N <= 0 || (!outT && !copy && !colsum)) return set_error(HIG_ERR_INVALID, "transpose: bad arguments");
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  using bf = __nv_bfloat16;
+#define HIG_TR(TI, TO) \
+  transpose_kernel<TI, TO><<<grid, 256, 0, stream>>>((const TI*)in, M, N, ld_in, (TO*)outT, ld_t, (TO*)copy, ld_c, colsum, rows_zero_mod)
+  if (in_dtype == HIG_F32 && out_dtype == HIG_F32) HIG_TR(float, float);
+  else if (in_dtype == HIG_F32 && out_dtype == HIG_BF16) HIG_TR(float, bf);
+  else if (in_dtype == HIG_BF16 && out_dtype == HIG_BF16) HIG_TR(bf, bf);
+  else if (in_dtype == HIG_BF16 && out_dtype == HIG_F32) HIG_TR(bf, float);
+  else return set_error(HIG_ERR_INVALID, "transpose: bad dtype");
+#undef HIG_TR
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("transpose launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// colsum: out[n] (+)= sum_m in[m, n].  Threads own columns (coalesced), blockIdx.y owns a chunk of rows; the
+// partial sums are combined with fp32 atomics, so the caller zeroes `out` (accumulate semantics).
+// ------------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const TIn* __restrict__ in, int M, int N, int ld, int rows_per_chunk, float* __restrict__ out) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N) return;
+  const int m0 = blockIdx.y * rows_per_chunk, m1 = min(M, m0 + rows_per_chunk);
+  float acc = 0.f;
+  for (int m = m0; m < m1; ++m) acc += ld_as_f(in + (size_t)m * ld + n);
+  atomicAdd(out + n, acc);
+}
+
+int colsum(const void* in, int dtype, int M, int N, int ld, float* out, cudaStream_t stream) {
+  if (!in || !out || M <= 0 || N <= 0) return set_error(HIG_ERR_INVALID, "colsum: bad arguments");
+  const int xb = (N + 255) / 256;
+  int chunks = (148 * 8 + xb - 1) / xb;
+  if (chunks > M) chunks = M;
+  if (chunks < 1) chunks = 1;
+  const int rpc = (M + chunks - 1) / chunks;
+  dim3 grid(xb, (M + rpc - 1) / rpc);
+  if (dtype == HIG_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)in, M, N, ld, rpc, out);
+  else if (dtype == HIG_F32) colsum_kernel<float><<<grid, 256, 0, stream>>>((const float*)in, M, N, ld, rpc, out);
+  else return set_error(HIG_ERR_INVALID, "colsum: bad dtype");
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("colsum launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise activation forward / backward (exact erf GELU :257, SiLU :476/:77); also a plain cast when act == 0.
+//   fwd: out = act(x)            bwd: dx = dy * act'(x)   (x = the saved pre-activation)
+// ------------------------------------------------------------------------------------------------
+HIG_DEVICE float act_fwd_f(float v, int act) {
+  if (act == 1) return gelu_erf_f(v);
+  if (act == 2) return v / (1.0f + expf(-v));
+  return v;
+}
+HIG_DEVICE float act_grad_f(float v, int act) {
+  if (act == 1) {
+    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+    const float pdf = 0.3989422804014327f * expf(-0.5f * v * v);
+    return cdf + v * pdf;
+  }
+  if (act == 2) {
+    const float s = 1.0f / (1.0f + expf(-v));
+    return s * (1.0f + v * (1.0f - s));
+  }
+  return 1.0f;
+}
+
+template <typename TIn, typename TOut>
+__global__ void act_fwd_kernel(const TIn* __restrict__ x, long long n, int act, TOut* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) st_from_f(out + i, act_fwd_f(ld_as_f(x + i), act));
+}
+template <typename TX, typename TG, typename TOut>
+__global__ void act_bwd_kernel(const TX* __restrict__ x, const TG* __restrict__ dy, long long n, int act,
+                               TOut* __restrict__ dx) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) st_from_f(dx + i, ld_as_f(dy + i) * act_grad_f(ld_as_f(x + i), act));
+}
+
+static int ew_blocks(long long n) {
+  long long b = (n + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)(b < 1 ? 1 : b);
+}
+
+int act_fwd(const void* x, int x_dtype, long long n, int act, void* out, int out_dtype, cudaStream_t stream) {
+  if (!x || !out || n <= 0 || act < 0 || act > 2) return set_error(HIG_ERR_INVALID, "act_fwd: bad arguments");
+  using bf = __nv_bfloat16;
+  const int b = ew_blocks(n);
+  if (x_dtype == HIG_F32 && out_dtype == HIG_F32) act_fwd_kernel<float, float><<<b, 256, 0, stream>>>((const float*)x, n, act, (float*)out);
+  else if (x_dtype == HIG_F32 && out_dtype == HIG_BF16) act_fwd_kernel<float, bf><<<b, 256, 0, stream>>>((const float*)x, n, act, (bf*)out);
+  else if (x_dtype == HIG_BF16 && out_dtype == HIG_BF16) act_fwd_kernel<bf, bf><<<b, 256, 0, stream>>>((const bf*)x, n, act, (bf*)out);
+  else if (x_dtype == HIG_BF16 && out_dtype == HIG_F32) act_fwd_kernel<bf, float><<<b, 256, 0, stream>>>((const bf*)x, n, act, (float*)out);
+  else return set_error(HIG_ERR_INVALID, "act_fwd: bad dtype");
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("act_fwd launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+int act_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, long long n, int act, void* dx, int dx_dtype,
+            cudaStream_t stream) {
+  if (!x || !dy || !dx || n <= 0 || act < 0 || act > 2) return set_error(HIG_ERR_INVALID, "act_bwd: bad arguments");
+  using bf = __nv_bfloat16;
+  const int b = ew_blocks(n);
+#define HIG_AB(TX, TG, TO) act_bwd_kernel<TX, TG, TO><<<b, 256, 0, stream>>>((const TX*)x, (const TG*)dy, n, act, (TO*)dx)
+  if (x_dtype == HIG_BF16 && dy_dtype == HIG_BF16 && dx_dtype == HIG_BF16) HIG_AB(bf, bf, bf);
+  else if (x_dtype == HIG_F32 && dy_dtype == HIG_F32 && dx_dtype == HIG_F32) HIG_AB(float, float, float);
+  else if (x_dtype == HIG_BF16 && dy_dtype == HIG_F32 && dx_dtype == HIG_BF16) HIG_AB(bf, float, bf);
+  else if (x_dtype == HIG_BF16 && dy_dtype == HIG_F32 && dx_dtype == HIG_F32) HIG_AB(bf, float, float);
+  else if (x_dtype == HIG_F32 && dy_dtype == HIG_BF16 && dx_dtype == HIG_F32) HIG_AB(float, bf, float);
+  else if (x_dtype == HIG_F32 && dy_dtype == HIG_BF16 && dx_dtype == HIG_BF16) HIG_AB(float, bf, bf);
+  else return set_error(HIG_ERR_INVALID, "act_bwd: unsupported dtype combination");
+#undef HIG_AB
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("act_bwd launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of ln_film_silu:   u = n_hat * gamma + beta,  t = u * (1 + scale_s) + shift_s,  out = [SiLU](t)
+//   dt      = dout * SiLU'(t)
+//   dscale  = sum_rows(dt * u)      dshift = sum_rows(dt)            (per sequence)
+//   du      = dt * (1 + scale)
+//   dgamma  = sum_rows(du * n_hat)  dbeta  = sum_rows(du)            (per-sequence partials; the caller column-sums)
+//   dx      = rstd * (dn - mean(dn) - n_hat * mean(dn * n_hat)),  dn = du * gamma
+// One CTA per (sequence, row slice); a warp walks rows, a lane owns 8 contiguous columns per 256-wide chunk exactly
+// as the forward kernel does; the per-lane column partials are combined through shared-memory atomics and flushed
+// with global fp32 atomics (partial buffers are zeroed by the caller).
+// ------------------------------------------------------------------------------------------------
+constexpr int LNB_WARPS = 8;
+
+template <int WIDTH, typename TX, typename TG, typename TDX>
+__global__ void __launch_bounds__(LNB_WARPS * 32)
+ln_film_silu_bwd_kernel(const TX* __restrict__ x, int rows, int rows_per_seq, int slices, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const float* __restrict__ scale_shift, int ss_stride,
+                        int apply_silu, const TG* __restrict__ dout, TDX* __restrict__ dx, int dx_accumulate,
+                        float* __restrict__ d_ss, int dss_stride, float* __restrict__ d_gb, int dgb_stride) {
+  constexpr int CH = WIDTH / 256;
+  __shared__ float red[4][WIDTH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seq = blockIdx.x / slices, slice = blockIdx.x - seq * slices;
+  for (int i = threadIdx.x; i < 4 * WIDTH; i += LNB_WARPS * 32) (&red[0][0])[i] = 0.f;
+  __syncthreads();
+
+  float G[CH][8], Bt[CH][8], SC[CH][8], SH[CH][8];
+  float a_sc[CH][8], a_sh[CH][8], a_g[CH][8], a_b[CH][8];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = c * 256 + lane * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      G[c][j] = gamma[col + j];
+      Bt[c][j] = beta[col + j];
+      SC[c][j] = scale_shift ? scale_shift[(size_t)seq * ss_stride + col + j] : 0.f;
+      SH[c][j] = scale_shift ? scale_shift[(size_t)seq * ss_stride + WIDTH + col + j] : 0.f;
+      a_sc[c][j] = a_sh[c][j] = a_g[c][j] = a_b[c][j] = 0.f;
+    }
+  }
+  const int r_begin = seq * rows_per_seq;
+  const int r_end = min(rows, r_begin + rows_per_seq);
+  for (int r = r_begin + slice * LNB_WARPS + warp; r < r_end; r += slices * LNB_WARPS) {
+    float v[CH][8], g[CH][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const size_t idx = (size_t)r * WIDTH + c * 256 + lane * 8 + j;
+        v[c][j] = ld_as_f(x + idx);
+        g[c][j] = ld_as_f(dout + idx);
+        s += v[c][j];
+      }
+    const float mean = warp_sum(s) * (1.0f / WIDTH);
+    float ssq = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[c][j] -= mean;
+        ssq = fmaf(v[c][j], v[c][j], ssq);
+      }
+    const float rstd = 1.0f / sqrtf(warp_sum(ssq) * (1.0f / WIDTH) + 1e-5f);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float nh = v[c][j] * rstd;
+        const float u = nh * G[c][j] + Bt[c][j];
+        float dt = g[c][j];
+        if (apply_silu) {
+          const float t = u * (1.0f + SC[c][j]) + SH[c][j];
+          const float sg = 1.0f / (1.0f + expf(-t));
+          dt *= sg * (1.0f + t * (1.0f - sg));
+        }
+        a_sc[c][j] = fmaf(dt, u, a_sc[c][j]);
+        a_sh[c][j] += dt;
+        const float du = dt * (1.0f + SC[c][j]);
+        a_g[c][j] = fmaf(du, nh, a_g[c][j]);
+        a_b[c][j] += du;
+        const float dn = du * G[c][j];
+        m1 += dn;
+        m2 = fmaf(dn, nh, m2);
+        v[c][j] = nh;
+        g[c][j] = dn;
+      }
+    m1 = warp_sum(m1) * (1.0f / WIDTH);
+    m2 = warp_sum(m2) * (1.0f / WIDTH);
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const size_t idx = (size_t)r * WIDTH + c * 256 + lane * 8 + j;
+        float d = rstd * (g[c][j] - m1 - v[c][j] * m2);
+        if (dx_accumulate) d += ld_as_f(dx + idx);
+        st_from_f(dx + idx, d);
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = c * 256 + lane * 8 + j;
+      atomicAdd(&red[0][col], a_sc[c][j]);
+      atomicAdd(&red[1][col], a_sh[c][j]);
+      atomicAdd(&red[2][col], a_g[c][j]);
+      atomicAdd(&red[3][col], a_b[c][j]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < WIDTH; i += LNB_WARPS * 32) {
+    if (d_ss) {
+      atomicAdd(d_ss + (size_t)seq * dss_stride + i, red[0][i]);
+      atomicAdd(d_ss + (size_t)seq * dss_stride + WIDTH + i, red[1][i]);
+    }
+    if (d_gb) {
+      atomicAdd(d_gb + (size_t)seq * dgb_stride + i, red[2][i]);
+      atomicAdd(d_gb + (size_t)seq * dgb_stride + WIDTH + i, red[3][i]);
+    }
+  }
+}
+
+int ln_film_silu_bwd(const void* x, int x_dtype, int rows, int width, int rows_per_seq, const float* gamma,
+                     const float* beta, const float* scale_shift, int ss_stride, int apply_silu, const void* dout,
+                     int dout_dtype, void* dx, int dx_dtype, int dx_accumulate, float* d_ss, int dss_stride,
+                     float* d_gb, int dgb_stride, cudaStream_t stream) {
+  if (!x || !dout || !dx || !gamma || !beta || rows <= 0 || rows_per_seq <= 0)
+    return set_error(HIG_ERR_INVALID, "ln_film_silu_bwd: bad arguments");
+  if (width != 512 && width != 256) return set_error(HIG_ERR_UNSUPPORTED, "ln_film_silu_bwd: width must be 256 or 512");
+  const int n_seq = (rows + rows_per_seq - 1) / rows_per_seq;
+  // enough CTAs to fill the machine: split a sequence's rows over `slices` CTAs when there are few sequences
+  int slices = (148 * 2 + n_seq - 1) / n_seq;
+  const int max_slices = (rows_per_seq + LNB_WARPS - 1) / LNB_WARPS;
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  const int blocks = n_seq * slices;
+  using bf = __nv_bfloat16;
+#define HIG_LNB(W, TX, TG, TD)                                                                                        \
+  ln_film_silu_bwd_kernel<W, TX, TG, TD><<<blocks, LNB_WARPS * 32, 0, stream>>>(                                      \
+      (const TX*)x, rows, rows_per_seq, slices, gamma, beta, scale_shift, ss_stride, apply_silu, (const TG*)dout,     \
+      (TD*)dx, dx_accumulate, d_ss, dss_stride, d_gb, dgb_stride)
+#define HIG_LNB_W(W)                                                                                                  \
+  if (x_dtype == HIG_F32 && dout_dtype == HIG_BF16 && dx_dtype == HIG_F32) HIG_LNB(W, float, bf, float);             \
+  else if (x_dtype == HIG_BF16 && dout_dtype == HIG_BF16 && dx_dtype == HIG_BF16) HIG_LNB(W, bf, bf, bf);            \
+  else if (x_dtype == HIG_F32 && dout_dtype == HIG_F32 && dx_dtype == HIG_F32) HIG_LNB(W, float, float, float);      \
+  else if (x_dtype == HIG_F32 && dout_dtype == HIG_BF16 && dx_dtype == HIG_BF16) HIG_LNB(W, float, bf, bf);          \
+  else return set_error(HIG_ERR_UNSUPPORTED, "ln_film_silu_bwd: dtype combination")
+  if (width == 512) { HIG_LNB_W(512); } else { HIG_LNB_W(256); }
+#undef HIG_LNB_W
+#undef HIG_LNB
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("ln_film_silu_bwd launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+}  // namespace hig

@@ -109,4 +109,45 @@ int hig_q_sample(const float* x0, const float* noise, const long long* t, const 
   return hig::q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, S, TC, out, static_cast<cudaStream_t>(stream));
 }
 
+// ---------------------------------------------------------------- training path
+int hig_gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32,
+                         int ldo_f32, int k_splits, void* stream) {
+  return hig::gemm_bf16_splitk(A, lda, W, ldw, M, N, K, out_f32, ldo_f32, k_splits, static_cast<cudaStream_t>(stream));
+}
+
+int hig_transpose(const void* in, int in_dtype, int M, int N, int ld_in, void* outT, int ld_t, void* copy, int ld_c,
+                  int out_dtype, float* colsum, int rows_zero_mod, void* stream) {
+  return hig::transpose(in, in_dtype, M, N, ld_in, outT, ld_t, copy, ld_c, out_dtype, colsum, rows_zero_mod,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int hig_colsum(const void* in, int dtype, int M, int N, int ld, float* out, void* stream) {
+  return hig::colsum(in, dtype, M, N, ld, out, static_cast<cudaStream_t>(stream));
+}
+
+int hig_act_fwd(const void* x, int x_dtype, long long n, int act, void* out, int out_dtype, void* stream) {
+  return hig::act_fwd(x, x_dtype, n, act, out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int hig_act_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, long long n, int act, void* dx, int dx_dtype,
+                void* stream) {
+  return hig::act_bwd(x, x_dtype, dy, dy_dtype, n, act, dx, dx_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int hig_ln_film_silu_bwd(const void* x, int x_dtype, int rows, int width, int rows_per_seq, const float* gamma,
+                         const float* beta, const float* scale_shift, int ss_stride, int apply_silu, const void* dout,
+                         int dout_dtype, void* dx, int dx_dtype, int dx_accumulate, float* d_ss, int dss_stride,
+                         float* d_gb, int dgb_stride, void* stream) {
+  return hig::ln_film_silu_bwd(x, x_dtype, rows, width, rows_per_seq, gamma, beta, scale_shift, ss_stride, apply_silu,
+                               dout, dout_dtype, dx, dx_dtype, dx_accumulate, d_ss, dss_stride, d_gb, dgb_stride,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int hig_eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
+                     const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
+                     const int* length, int S, int T, int H, int pair_shift, int dtype, void* stream) {
+  return hig::eff_attn_bwd(mode, q, ldq, k, v, ldkv, a_in, dy, lddy, dq, lddq, dk, dv, lddkv, dA, length, S, T, H,
+                           pair_shift, dtype, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -34,7 +34,7 @@ constexpr int G2_SMEM = G2_STAGES * (G2_A_BYTES + G2_B_BYTES) + G2_EPI_BYTES + G
 template <int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                      int K, GemmEpilogue ep, int vec_ok) {
+                      int K, GemmEpilogue ep, int vec_ok, int k_splits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -54,8 +54,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   const int m_tiles = (M + 2 * G2_BM - 1) / (2 * G2_BM);
   const int n_tiles = (N + G2_BN - 1) / G2_BN;
-  const int num_tiles = m_tiles * n_tiles;
-  const int k_blocks = (K + G2_BK - 1) / G2_BK;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int num_tiles = mn_tiles * k_splits;  // split-K slices accumulate atomically in the epilogue
+  const int k_blocks_all = (K + G2_BK - 1) / G2_BK;
+  const int kb_per = (k_blocks_all + k_splits - 1) / k_splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -81,9 +83,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int n_blk = tile % n_tiles;
-        const int m_blk = tile / n_tiles;
-        for (int kb = 0; kb < k_blocks && ep.act != 101; ++kb, ++it) {
+        const int mn = tile % mn_tiles, ks = tile / mn_tiles;
+        const int n_blk = mn % n_tiles;
+        const int m_blk = mn / n_tiles;
+        const int kb0 = ks * kb_per, kb1 = min(k_blocks_all, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1 && ep.act != 101; ++kb, ++it) {
           const uint32_t stage = it % G2_STAGES;
           const uint32_t phase = (it / G2_STAGES) & 1u;
           mbar_wait(empty_bar + stage, phase ^ 1u);
@@ -106,7 +110,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         mbar_wait(tempty_bar + as, aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * G2_BN;
-        for (int kb = 0; kb < k_blocks && ep.act != 101; ++kb, ++it) {
+        const int ks = tile / mn_tiles;
+        const int kb0 = ks * kb_per, kb1 = min(k_blocks_all, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1 && ep.act != 101; ++kb, ++it) {
           const uint32_t stage = it % G2_STAGES;
           const uint32_t phase = (it / G2_STAGES) & 1u;
           mbar_wait(full_bar + stage, phase);
@@ -115,7 +121,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * G2_B_BYTES));
 #pragma unroll
           for (int k = 0; k < G2_BK / 16; ++k)
-            umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           umma_commit_2cta_mc(empty_bar + stage, 0b11);  // frees this smem slot in both CTAs
         }
         umma_commit_2cta_mc(tfull_bar + as, 0b11);  // accumulator halves ready in both CTAs
@@ -130,8 +136,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t slab = smem_u32(sEpi) + (warp - 2) * 32 * 32 * 4;
     uint32_t lt = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
-      const int n_blk = tile % n_tiles;
-      const int m_blk = tile / n_tiles;
+      const int mn = tile % mn_tiles;
+      const int n_blk = mn % n_tiles;
+      const int m_blk = mn / n_tiles;
       const uint32_t as = lt & 1u;
       const uint32_t aphase = (lt >> 1) & 1u;
       const int row0 = m_blk * 2 * G2_BM + (int)rank * G2_BM + q * 32;
@@ -182,7 +189,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
 template <int KIND>
 static int launch_2cta_kind(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
-                            int vec_ok, int num_sms, cudaStream_t stream) {
+                            int vec_ok, int num_sms, int k_splits, cudaStream_t stream) {
   static bool attr_set = false;
   auto kern = gemm_bf16_2cta_kernel<KIND>;
   if (!attr_set) {
@@ -192,9 +199,9 @@ static int launch_2cta_kind(const CUtensorMap& tmA, const CUtensorMap& tmB, int 
   }
   const int m_tiles = (M + 2 * G2_BM - 1) / (2 * G2_BM);
   const int n_tiles = (N + G2_BN - 1) / G2_BN;
-  int pairs = m_tiles * n_tiles;
+  int pairs = m_tiles * n_tiles * k_splits;
   if (pairs > num_sms / 2) pairs = num_sms / 2;
-  kern<<<2 * pairs, G2_THREADS, G2_SMEM, stream>>>(tmA, tmB, M, N, K, ep, vec_ok);
+  kern<<<2 * pairs, G2_THREADS, G2_SMEM, stream>>>(tmA, tmB, M, N, K, ep, vec_ok, k_splits);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("gemm 2cta launch: ") + cudaGetErrorString(e));
   count_launch();
@@ -202,14 +209,14 @@ static int launch_2cta_kind(const CUtensorMap& tmA, const CUtensorMap& tmB, int 
 }
 
 int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
-                     int vec_ok, int num_sms, cudaStream_t stream) {
+                     int vec_ok, int num_sms, int k_splits, cudaStream_t stream) {
   const int kind = (ep.act >= 100) ? EPI_GENERIC : classify_epilogue(ep, vec_ok, N);
   switch (kind) {
-    case EPI_BF16: return launch_2cta_kind<EPI_BF16>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, stream);
-    case EPI_BF16_GELU: return launch_2cta_kind<EPI_BF16_GELU>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, stream);
-    case EPI_RES_F32: return launch_2cta_kind<EPI_RES_F32>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, stream);
-    case EPI_RES_F32_BF16: return launch_2cta_kind<EPI_RES_F32_BF16>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, stream);
-    default: return launch_2cta_kind<EPI_GENERIC>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, stream);
+    case EPI_BF16: return launch_2cta_kind<EPI_BF16>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
+    case EPI_BF16_GELU: return launch_2cta_kind<EPI_BF16_GELU>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
+    case EPI_RES_F32: return launch_2cta_kind<EPI_RES_F32>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
+    case EPI_RES_F32_BF16: return launch_2cta_kind<EPI_RES_F32_BF16>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
+    default: return launch_2cta_kind<EPI_GENERIC>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
   }
 }
 

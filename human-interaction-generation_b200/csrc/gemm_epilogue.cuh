@@ -14,6 +14,7 @@ struct GemmEpilogue {
   __nv_bfloat16* out_bf16;  // nullable
   int ldo_bf16;
   int act;                // 0 none, 1 GELU(erf), 2 SiLU
+  int atomic;             // 1: split-K partial -> atomicAdd into out_f32 (generic kind only; no bias/act)
 };
 
 HIG_DEVICE void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
@@ -49,7 +50,10 @@ static __device__ __noinline__ void epilogue_chunk_scalar(uint32_t slab, GemmEpi
         if (ep.residual) x += __ldg(ep.residual + (size_t)rr * ep.ldr + col);
         if (ep.act == 1) x = gelu_fast_f(x);
         else if (ep.act == 2) x = silu_f(x);
-        if (ep.out_f32) ep.out_f32[(size_t)row * ep.ldo_f32 + col] = x;
+        if (ep.out_f32) {
+          if (ep.atomic) atomicAdd(ep.out_f32 + (size_t)row * ep.ldo_f32 + col, x);
+          else ep.out_f32[(size_t)row * ep.ldo_f32 + col] = x;
+        }
         if (ep.out_bf16) ep.out_bf16[(size_t)row * ep.ldo_bf16 + col] = __float2bfloat16(x);
       }
     }
@@ -158,7 +162,14 @@ HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const EpiLane& L, uint32
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if ((L.row_ok >> i) & 1u) {
-        if (w32) *reinterpret_cast<float4*>(L.o32 + (size_t)(4 * i) * ep.ldo_f32 + col0) = v[i];
+        if (w32) {
+          float* o = L.o32 + (size_t)(4 * i) * ep.ldo_f32 + col0;
+          if (KIND == EPI_GENERIC && ep.atomic) {
+            atomicAdd(o, v[i].x); atomicAdd(o + 1, v[i].y); atomicAdd(o + 2, v[i].z); atomicAdd(o + 3, v[i].w);
+          } else {
+            *reinterpret_cast<float4*>(o) = v[i];
+          }
+        }
         if (w16)
           *reinterpret_cast<uint2*>(L.o16 + (size_t)(4 * i) * ep.ldo_bf16 + col0) =
               make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
@@ -221,7 +232,7 @@ HIG_DEVICE void epi_finish(const uint32_t (&r)[32], const EpiPre& P, const EpiLa
 
 // classify a runtime epilogue into the specialised kinds (host side)
 inline int classify_epilogue(const GemmEpilogue& ep, int vec_ok, int N) {
-  if (!vec_ok || (N % 32) != 0 || !ep.bias || ep.res_row_mod > 0) return EPI_GENERIC;
+  if (!vec_ok || (N % 32) != 0 || !ep.bias || ep.res_row_mod > 0 || ep.atomic) return EPI_GENERIC;
   if (!ep.residual && !ep.out_f32 && ep.out_bf16) {
     if (ep.act == 0) return EPI_BF16;
     if (ep.act == 1) return EPI_BF16_GELU;

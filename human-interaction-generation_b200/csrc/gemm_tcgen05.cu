@@ -40,7 +40,7 @@ struct GemmSmem {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         int M, int N, int K, GemmEpilogue ep, int vec_ok) {
+                         int M, int N, int K, GemmEpilogue ep, int vec_ok, int k_splits) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -58,8 +58,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = (N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
-  const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int num_tiles = mn_tiles * k_splits;  // split-K: tile = (k slice, m block, n block), slices accumulate atomically
+  const int k_blocks_all = (K + GEMM_BK - 1) / GEMM_BK;
+  const int kb_per = (k_blocks_all + k_splits - 1) / k_splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -87,9 +89,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = tile % n_tiles;
-        const int m_blk = tile / n_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int mn = tile % mn_tiles, ks = tile / mn_tiles;
+        const int n_blk = mn % n_tiles;
+        const int m_blk = mn / n_tiles;
+        const int kb0 = ks * kb_per, kb1 = min(k_blocks_all, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t stage = it % STAGES;
           const uint32_t phase = (it / STAGES) & 1u;
           mbar_wait(empty_bar + stage, phase ^ 1u);
@@ -111,7 +115,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         mbar_wait(tempty_bar + as, aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int ks = tile / mn_tiles;
+        const int kb0 = ks * kb_per, kb1 = min(k_blocks_all, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t stage = it % STAGES;
           const uint32_t phase = (it / STAGES) & 1u;
           mbar_wait(full_bar + stage, phase);
@@ -121,7 +127,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in 16-byte units
-            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
         }
@@ -138,8 +144,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t slab = smem_u32(sEpi) + (warp - 2) * 32 * 32 * 4;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int n_blk = tile % n_tiles;
-      const int m_blk = tile / n_tiles;
+      const int mn = tile % mn_tiles;
+      const int n_blk = mn % n_tiles;
+      const int m_blk = mn / n_tiles;
       const uint32_t as = lt & 1u;
       const uint32_t aphase = (lt >> 1) & 1u;
       mbar_wait(tfull_bar + as, aphase);
@@ -243,7 +250,7 @@ static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, C
 }
 
 int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
-                     int vec_ok, int num_sms, cudaStream_t stream);
+                     int vec_ok, int num_sms, int k_splits, cudaStream_t stream);
 
 static int num_sms() {
   static int n = 0;
@@ -258,7 +265,7 @@ static int num_sms() {
 
 template <int BN, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
-                       int vec_ok, cudaStream_t stream) {
+                       int vec_ok, int k_splits, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
   static bool attr_set = false;
   auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES>;
@@ -269,21 +276,26 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   }
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = (N + BN - 1) / BN;
-  int grid = m_tiles * n_tiles;
+  int grid = m_tiles * n_tiles * k_splits;
   if (grid > num_sms()) grid = num_sms();
-  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, M, N, K, ep, vec_ok);
+  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, M, N, K, ep, vec_ok, k_splits);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(e));
   count_launch();
   return HIG_OK;
 }
 
-int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
-              const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, void* out_bf16,
-              int ldo_bf16, int act, cudaStream_t stream) {
+// split_k != 0: the K range is cut into slices that run as independent tiles and are combined with fp32 atomics into
+// out_f32 (which the caller has initialised: zeros, or a gradient to accumulate into).  Used by the weight-gradient
+// GEMMs, whose output is a handful of tiles while K = tokens is long.  split_k > 0 forces that many slices.
+static int gemm_bf16_impl(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                          const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, void* out_bf16,
+                          int ldo_bf16, int act, int split_k, cudaStream_t stream) {
   if (!A || !W || M <= 0 || N <= 0 || K <= 0) return set_error(HIG_ERR_INVALID, "gemm: null operand or empty shape");
   if (!out_f32 && !out_bf16) return set_error(HIG_ERR_INVALID, "gemm: no output");
-  if ((lda % 8) || (ldw % 8) || (K % 8)) return set_error(HIG_ERR_INVALID, "gemm: lda/ldw/K must be multiples of 8 (TMA 16B rule)");
+  if ((lda % 8) || (ldw % 8)) return set_error(HIG_ERR_INVALID, "gemm: lda/ldw must be multiples of 8 (TMA 16B rule)");
+  if (split_k && (bias || residual || out_bf16 || act != 0 || !out_f32))
+    return set_error(HIG_ERR_INVALID, "gemm: split-K accumulates raw products into out_f32 only");
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
     return set_error(HIG_ERR_INVALID, "gemm: operands must be 16-byte aligned");
   if ((act < 0 || act > 2) && act != 100 && act != 101) return set_error(HIG_ERR_INVALID, "gemm: bad activation");
@@ -293,6 +305,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   ep.out_f32 = out_f32; ep.ldo_f32 = ldo_f32;
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); ep.ldo_bf16 = ldo_bf16;
   ep.act = act;
+  ep.atomic = split_k ? 1 : 0;
 
   int vec_ok = 1;
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) vec_ok = 0;
@@ -303,20 +316,45 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   CUtensorMap tmA, tmB;
   // CTA-pair kernel (256 x 256 tiles, cta_group::2) for the large projections; HIG_GEMM_2CTA=0 disables it
   static const bool allow_2cta = []() { const char* e = getenv("HIG_GEMM_2CTA"); return !(e && e[0] == '0'); }();
+  const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  auto pick_splits = [&](int mn_tiles, int workers) {
+    if (!split_k) return 1;
+    int want = split_k > 0 ? split_k : (workers + mn_tiles - 1) / mn_tiles;
+    if (want > k_blocks) want = k_blocks;
+    if (want < 1) want = 1;
+    const int per = (k_blocks + want - 1) / want;
+    return (k_blocks + per - 1) / per;  // every slice owns at least one k-block
+  };
   if (allow_2cta && M >= 512 && N >= 256) {
     int rc2 = get_tmap(A, M, K, lda, 128, &tmA);
     if (rc2) return rc2;
     rc2 = get_tmap(W, N, K, ldw, 128, &tmB);
     if (rc2) return rc2;
-    return launch_gemm_2cta(tmA, tmB, M, N, K, ep, vec_ok, num_sms(), stream);
+    const int mn = ((M + 255) / 256) * ((N + 255) / 256);
+    return launch_gemm_2cta(tmA, tmB, M, N, K, ep, vec_ok, num_sms(), pick_splits(mn, num_sms() / 2), stream);
   }
   const bool big_n = N > 128;
   int rc = get_tmap(A, M, K, lda, GEMM_BM, &tmA);
   if (rc) return rc;
   rc = get_tmap(W, N, K, ldw, big_n ? 256 : 128, &tmB);
   if (rc) return rc;
-  if (big_n) return launch_gemm<256, 4>(tmA, tmB, M, N, K, ep, vec_ok, stream);
-  return launch_gemm<128, 6>(tmA, tmB, M, N, K, ep, vec_ok, stream);
+  const int mn1 = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + (big_n ? 255 : 127)) / (big_n ? 256 : 128));
+  const int ks1 = pick_splits(mn1, num_sms());
+  if (big_n) return launch_gemm<256, 4>(tmA, tmB, M, N, K, ep, vec_ok, ks1, stream);
+  return launch_gemm<128, 6>(tmA, tmB, M, N, K, ep, vec_ok, ks1, stream);
+}
+
+int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+              const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, void* out_bf16,
+              int ldo_bf16, int act, cudaStream_t stream) {
+  return gemm_bf16_impl(A, lda, W, ldw, M, N, K, bias, residual, ldr, res_row_mod, out_f32, ldo_f32, out_bf16, ldo_bf16,
+                        act, 0, stream);
+}
+
+int gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32, int ldo_f32,
+                     int k_splits, cudaStream_t stream) {
+  return gemm_bf16_impl(A, lda, W, ldw, M, N, K, nullptr, nullptr, 0, 0, out_f32, ldo_f32, nullptr, 0, 0,
+                        k_splits > 0 ? k_splits : -1, stream);
 }
 
 }  // namespace hig

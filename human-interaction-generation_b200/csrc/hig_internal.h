@@ -39,4 +39,26 @@ int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const 
 int q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac, const float* sqrt_1mac,
              int S, int TC, float* out, cudaStream_t stream);
 
+// ---- training path (bwd_ops.cu, eff_attn_bwd.cu, gemm_tcgen05.cu) ----
+int gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32, int ldo_f32,
+                     int k_splits, cudaStream_t stream);
+
+int transpose(const void* in, int in_dtype, int M, int N, int ld_in, void* outT, int ld_t, void* copy, int ld_c,
+              int out_dtype, float* colsum, int rows_zero_mod, cudaStream_t stream);
+
+int colsum(const void* in, int dtype, int M, int N, int ld, float* out, cudaStream_t stream);
+
+int act_fwd(const void* x, int x_dtype, long long n, int act, void* out, int out_dtype, cudaStream_t stream);
+int act_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, long long n, int act, void* dx, int dx_dtype,
+            cudaStream_t stream);
+
+int ln_film_silu_bwd(const void* x, int x_dtype, int rows, int width, int rows_per_seq, const float* gamma,
+                     const float* beta, const float* scale_shift, int ss_stride, int apply_silu, const void* dout,
+                     int dout_dtype, void* dx, int dx_dtype, int dx_accumulate, float* d_ss, int dss_stride,
+                     float* d_gb, int dgb_stride, cudaStream_t stream);
+
+int eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
+                 const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
+                 const int* length, int S, int T, int H, int pair_shift, int dtype, cudaStream_t stream);
+
 }  // namespace hig

@@ -47,6 +47,7 @@ class DenoiserEngine:
         self.CP = (self.C + 4 + 7) // 8 * 8          # 263 + 4 -> 272: K padded for TMA's 16-byte rule
         self.LD_EPS = (self.C + 3) // 4 * 4          # 264
         self._packed = None
+        self._packed_T = None
         self._packed_key = None
         self._ws = {}
         self._text_cache = None
@@ -110,8 +111,31 @@ class DenoiserEngine:
             half = self.D // 2
             W["freqs"] = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(dev)
         self._packed, self._packed_key = W, key
+        self._packed_T = None
         self._text_cache = None
         return W
+
+    def packed_T(self):
+        """W^T copies in the operand dtype: the B operand of the data-gradient GEMMs dx = dy . W (training only).
+        The 263-row output heads are zero-padded to 264 columns (TMA 16-byte rule)."""
+        W = self.packed()
+        if self._packed_T is not None:
+            return self._packed_T
+        WT = {}
+        with torch.no_grad():
+            for k, v in W.items():
+                if not (torch.is_tensor(v) and v.dim() == 2 and v.dtype == self.act_dtype):
+                    continue
+                if not (k.endswith(".w") or k.endswith(".w1") or k.endswith(".w2")) or k in ("in.w", "te0.w"):
+                    continue
+                t = v.t().contiguous()
+                if k in ("out.w", "out2.w"):
+                    pad = torch.zeros(t.shape[0], (t.shape[1] + 7) // 8 * 8, device=t.device, dtype=t.dtype)
+                    pad[:, :t.shape[1]] = t
+                    t = pad
+                WT[k] = t
+        self._packed_T = WT
+        return WT
 
     # ------------------------------------------------------------------------------------------ workspaces
     def workspace(self, S, T):

@@ -165,3 +165,98 @@ def l2_persist(t, hit_ratio=1.0):
     else:
         rc = lib.hig_l2_persist(_ptr(t), t.numel() * t.element_size(), float(hit_ratio), _stream())
     _lib.check(rc, "hig_l2_persist")
+
+
+# ---------------------------------------------------------------------------------------------- training path
+def gemm_splitk(a, w, out_f32, k_splits=0):
+    """out_f32[M,N] += a[M,K] @ w[N,K].T, bf16 operands, K split over CTAs and combined with fp32 atomics."""
+    lib = _lib.load()
+    M, K = a.shape
+    N = w.shape[0]
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or out_f32.dtype != torch.float32:
+        raise TypeError("hig_b200.gemm_splitk: bf16 operands and an fp32 accumulator are required")
+    if w.shape[1] != K or tuple(out_f32.shape) != (M, N):
+        raise ValueError("hig_b200.gemm_splitk: shape mismatch")
+    rc = lib.hig_gemm_bf16_splitk(_ptr(a), _rowmajor(a, "A"), _ptr(w), _rowmajor(w, "W"), M, N, K, _ptr(out_f32),
+                                  _rowmajor(out_f32, "out_f32"), int(k_splits), _stream())
+    _lib.check(rc, "hig_gemm_bf16_splitk")
+    return out_f32
+
+
+def transpose(x, out_t=None, copy=None, colsum=None, rows_zero_mod=0):
+    """x [M,N] -> out_t [N,>=M] (transposed), copy [M,N] (cast), colsum[N] += column sums; any subset."""
+    lib = _lib.load()
+    M, N = x.shape
+    ref = out_t if out_t is not None else copy
+    odt = _dt(ref) if ref is not None else _dt(x)
+    if out_t is not None and copy is not None and out_t.dtype != copy.dtype:
+        raise TypeError("hig_b200.transpose: out_t and copy must share a dtype")
+    if colsum is not None and (colsum.dtype != torch.float32 or colsum.numel() < N):
+        raise ValueError("hig_b200.transpose: colsum must be fp32 [N]")
+    rc = lib.hig_transpose(_ptr(x), _dt(x), M, N, _rowmajor(x, "x"), _ptr(out_t),
+                           _rowmajor(out_t, "out_t") if out_t is not None else 0, _ptr(copy),
+                           _rowmajor(copy, "copy") if copy is not None else 0, odt, _ptr(colsum), int(rows_zero_mod),
+                           _stream())
+    _lib.check(rc, "hig_transpose")
+
+
+def colsum(x, out):
+    """out[N] += x[M,N].sum(0)  (fp32 atomics; zero `out` first for a plain sum)."""
+    lib = _lib.load()
+    M, N = x.shape
+    if out.dtype != torch.float32 or out.numel() < N:
+        raise ValueError("hig_b200.colsum: out must be fp32 [N]")
+    rc = lib.hig_colsum(_ptr(x), _dt(x), M, N, _rowmajor(x, "x"), _ptr(out), _stream())
+    _lib.check(rc, "hig_colsum")
+    return out
+
+
+def act_fwd(x, act, out):
+    lib = _lib.load()
+    if not x.is_contiguous() or not out.is_contiguous() or x.numel() != out.numel():
+        raise ValueError("hig_b200.act_fwd: contiguous tensors of equal size required")
+    rc = lib.hig_act_fwd(_ptr(x), _dt(x), x.numel(), act, _ptr(out), _dt(out), _stream())
+    _lib.check(rc, "hig_act_fwd")
+    return out
+
+
+def act_bwd(x, dy, act, dx):
+    lib = _lib.load()
+    if not (x.is_contiguous() and dy.is_contiguous() and dx.is_contiguous()) or x.numel() != dy.numel():
+        raise ValueError("hig_b200.act_bwd: contiguous tensors of equal size required")
+    rc = lib.hig_act_bwd(_ptr(x), _dt(x), _ptr(dy), _dt(dy), x.numel(), act, _ptr(dx), _dt(dx), _stream())
+    _lib.check(rc, "hig_act_bwd")
+    return dx
+
+
+def ln_film_silu_bwd(x, gamma, beta, dout, dx, rows_per_seq, scale_shift=None, silu=False, dx_accumulate=False,
+                     d_ss=None, d_gb=None):
+    """Backward of ln_film_silu.  d_ss: fp32 view [S, >=2W] (+=), d_gb: fp32 [S, 2W] per-sequence partials (+=)."""
+    lib = _lib.load()
+    rows, width = x.shape
+    if not (x.is_contiguous() and dout.is_contiguous() and dx.is_contiguous()):
+        raise ValueError("hig_b200.ln_film_silu_bwd: contiguous tensors required")
+    ss_stride = scale_shift.stride(0) if scale_shift is not None else 0
+    rc = lib.hig_ln_film_silu_bwd(_ptr(x), _dt(x), rows, width, rows_per_seq, _ptr(gamma), _ptr(beta),
+                                  _ptr(scale_shift), ss_stride, 1 if silu else 0, _ptr(dout), _dt(dout), _ptr(dx),
+                                  _dt(dx), 1 if dx_accumulate else 0, _ptr(d_ss),
+                                  d_ss.stride(0) if d_ss is not None else 0, _ptr(d_gb),
+                                  d_gb.stride(0) if d_gb is not None else 0, _stream())
+    _lib.check(rc, "hig_ln_film_silu_bwd")
+    return dx
+
+
+def eff_attn_bwd(mode, S, T, H, q=None, k=None, v=None, a_in=None, dy=None, dq=None, dk=None, dv=None, dA=None,
+                 length=None, pair_shift=0):
+    lib = _lib.load()
+    ref = q if q is not None else k
+    if dA is not None and dA.dtype != torch.float32:
+        raise TypeError("hig_b200.eff_attn_bwd: dA must be fp32")
+    if dk is not None and dv.stride(0) != dk.stride(0):
+        raise ValueError("hig_b200.eff_attn_bwd: dK and dV must share a leading dimension")
+    rc = lib.hig_eff_attn_bwd(mode, _ptr(q), q.stride(0) if q is not None else 0, _ptr(k), _ptr(v),
+                              k.stride(0) if k is not None else 0, _ptr(a_in), _ptr(dy),
+                              dy.stride(0) if dy is not None else 0, _ptr(dq), dq.stride(0) if dq is not None else 0,
+                              _ptr(dk), _ptr(dv), dk.stride(0) if dk is not None else 0, _ptr(dA), _ptr(length), S, T,
+                              H, pair_shift, _dt(ref), _stream())
+    _lib.check(rc, "hig_eff_attn_bwd")

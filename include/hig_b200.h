@@ -96,6 +96,44 @@ int hig_ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, co
 int hig_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
                  const float* sqrt_1mac, int S, int TC, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training path.  The reference has no backward code: torch.autograd differentiates the forward above
+ * (loss.backward() in DDPMMulTrainer.update, trainers/mul_ddpm_trainer.py:249-256).  These are the hand-written
+ * derivatives of the forward kernels; hig_b200/autograd.py schedules them.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* out_f32[M,N] += A[M,K] . W[N,K]^T with the K range split over CTAs and combined by fp32 atomics (the caller
+ * initialises out_f32).  Weight gradients dW = dY^T . X: M, N are weight dims, K = tokens.  k_splits <= 0: auto. */
+int hig_gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32,
+                         int ldo_f32, int k_splits, void* stream);
+
+/* in [M,N] -> outT [N,M] (nullable), copy [M,N] in the output dtype (nullable), colsum[n] += sum_m in[m,n] (nullable,
+ * fp32 atomics: bias gradients).  rows_zero_mod > 0 treats rows with m % rows_zero_mod == 0 as zero (frame 0 of a
+ * sequence belongs to the out2 head, models/interaction_transformer.py:613-616). */
+int hig_transpose(const void* in, int in_dtype, int M, int N, int ld_in, void* outT, int ld_t, void* copy, int ld_c,
+                  int out_dtype, float* colsum, int rows_zero_mod, void* stream);
+
+/* out[n] += sum_m in[m,n] (fp32 atomics; the caller zeroes out) */
+int hig_colsum(const void* in, int dtype, int M, int N, int ld, float* out, void* stream);
+
+/* out = act(x) and dx = dy * act'(x) for HIG_ACT_* (exact erf GELU of FFN :257/:262, SiLU of time_embed :476) */
+int hig_act_fwd(const void* x, int x_dtype, long long n, int act, void* out, int out_dtype, void* stream);
+int hig_act_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, long long n, int act, void* dx, int dx_dtype,
+                void* stream);
+
+/* backward of hig_ln_film_silu: dx (overwritten, or += when dx_accumulate), d_ss[s] += (dscale | dshift) (nullable),
+ * d_gb[s] += per-sequence partials of (dgamma | dbeta) (nullable; column-sum over s gives the parameter gradients) */
+int hig_ln_film_silu_bwd(const void* x, int x_dtype, int rows, int width, int rows_per_seq, const float* gamma,
+                         const float* beta, const float* scale_shift, int ss_stride, int apply_silu, const void* dout,
+                         int dout_dtype, void* dx, int dx_dtype, int dx_accumulate, float* d_ss, int dss_stride,
+                         float* d_gb, int dgb_stride, void* stream);
+
+/* backward of hig_eff_attn (same modes).  SELF/INTER: q,k,v,dy -> dq,dk,dv (INTER writes dk,dv to the partner's
+ * rows).  KV_ONLY: k,v,dA(in, fp32 [S,H,64,64]) -> dk,dv.  Q_ONLY: q,a_in,dy -> dq, dA(out). */
+int hig_eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
+                     const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
+                     const int* length, int S, int T, int H, int pair_shift, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,334 @@
+"""Training path on the B200: backward kernels against torch.autograd of the same op (fp32 reference), and the
+denoiser's parameter gradients against (a) the REAL reference's gradients (tests/golden/train.npz) and (b) the
+differentiable CPU oracle on seeded inputs.  Everything goes through the public module / the C ABI.
+Tolerances: fp32 mode 2e-4 relative (fp32 accumulation-order differences over tok-long reductions),
+bf16 3e-2 relative per gradient tensor (bf16 operand rounding of activations and activation gradients)."""
+import ast
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+GTOL = {"fp32": 2e-4, "bf16": 3e-2}
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _ops():
+    import hig_b200  # noqa: F401
+    from hig_b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("in_dt,out_dt", [(torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16),
+                                          (torch.float32, torch.float32)])
+@pytest.mark.parametrize("M,N", [(130, 263), (64, 64), (1000, 1536), (7, 5)])
+def test_transpose_copy_colsum(cuda, M, N, in_dt, out_dt):
+    ops = _ops()
+    x = torch.randn(M, N, device=cuda).to(in_dt)
+    xt = torch.zeros(N, (M + 7) // 8 * 8, device=cuda, dtype=out_dt)
+    cp = torch.zeros(M, N, device=cuda, dtype=out_dt)
+    cs = torch.zeros(N, device=cuda)
+    ops.transpose(x, out_t=xt, copy=cp, colsum=cs)
+    assert torch.equal(xt[:, :M], x.to(out_dt).t())
+    assert torch.equal(cp, x.to(out_dt))
+    assert rel(cs, x.float().sum(0)) < 1e-5
+    # frame-0 rows dropped
+    cs.zero_()
+    ops.transpose(x, out_t=xt, copy=cp, colsum=cs, rows_zero_mod=5)
+    keep = (torch.arange(M, device=cuda) % 5 != 0).to(x.dtype)[:, None]
+    assert torch.equal(cp, (x * keep).to(out_dt))
+    assert rel(cs, (x * keep).float().sum(0)) < 1e-5
+
+
+def test_colsum(cuda):
+    ops = _ops()
+    for M, N, dt in [(256, 91 * 512, torch.float32), (4, 1024, torch.float32), (3000, 77, torch.bfloat16)]:
+        x = torch.randn(M, N, device=cuda).to(dt)
+        out = torch.zeros(N, device=cuda)
+        ops.colsum(x, out)
+        assert rel(out, x.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("act", [1, 2])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_act_fwd_bwd(cuda, act, dt):
+    ops = _ops()
+    x = (2 * torch.randn(1000, 77, device=cuda)).to(dt)
+    dy = torch.randn(1000, 77, device=cuda).to(dt)
+    xr = x.float().requires_grad_(True)
+    yr = F.gelu(xr) if act == 1 else F.silu(xr)
+    yr.backward(dy.float())
+    y = ops.act_fwd(x, act, torch.empty_like(x))
+    dx = ops.act_bwd(x, dy, act, torch.empty_like(x))
+    tol = 1e-6 if dt == torch.float32 else 5e-3
+    assert rel(y, yr.detach()) < tol and rel(dx, xr.grad) < tol
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 512, 23296), (1536, 512, 1000), (264, 512, 784), (1024, 2048, 256),
+                                   (2048, 512, 14)])
+def test_gemm_splitk(cuda, M, N, K):
+    ops = _ops()
+    Kp = (K + 7) // 8 * 8
+    a = torch.randn(M, Kp, device=cuda).bfloat16()[:, :K]
+    w = torch.randn(N, Kp, device=cuda).bfloat16()[:, :K]
+    base = torch.randn(M, N, device=cuda)
+    out = base.clone()
+    ops.gemm_splitk(a, w, out)
+    ref = base.double() + a.double() @ w.double().t()
+    assert rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("width", [512, 256])
+@pytest.mark.parametrize("x_dt,g_dt,dx_dt", [(torch.float32, torch.float32, torch.float32),
+                                             (torch.float32, torch.bfloat16, torch.float32),
+                                             (torch.bfloat16, torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("film", [True, False])
+def test_ln_film_silu_bwd(cuda, width, x_dt, g_dt, dx_dt, film):
+    ops = _ops()
+    S, T = 6, 37
+    rows = S * T
+    x = torch.randn(rows, width, device=cuda).to(x_dt)
+    gamma = (1 + 0.1 * torch.randn(width, device=cuda))
+    beta = 0.1 * torch.randn(width, device=cuda)
+    ss = 0.5 * torch.randn(S, 2 * width + 64, device=cuda)[:, :2 * width] if film else None
+    dout = torch.randn(rows, width, device=cuda).to(g_dt)
+    # torch reference in fp32
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    h = F.layer_norm(xr, (width,), gr, br, 1e-5)
+    if film:
+        ssr = ss.clone().requires_grad_(True)
+        sc, sh = ssr[:, :width], ssr[:, width:]
+        h = h.view(S, T, width) * (1 + sc[:, None]) + sh[:, None]
+        h = F.silu(h).view(rows, width)
+    h.backward(dout.float())
+    base = torch.randn(rows, width, device=cuda).to(dx_dt)
+    dx = base.clone()
+    d_ss = torch.zeros(S, 2 * width, device=cuda) if film else None
+    d_gb = torch.zeros(S, 2 * width, device=cuda)
+    acc = dx_dt == torch.float32
+    ops.ln_film_silu_bwd(x, gamma, beta, dout, dx, T, scale_shift=ss, silu=film, dx_accumulate=acc, d_ss=d_ss, d_gb=d_gb)
+    tol = 2e-5 if dx_dt == torch.float32 else 6e-3
+    want = xr.grad + (base.float() if acc else 0)
+    assert rel(dx, want) < tol
+    assert rel(d_gb[:, :width].sum(0), gr.grad) < 1e-4 and rel(d_gb[:, width:].sum(0), br.grad) < 1e-4
+    if film:
+        assert rel(d_ss, ssr.grad) < 1e-4
+
+
+def _attn_ref(q, k, v, mask_k, mask_v):
+    """q [S,T,H,64], k/v [S,Tk,H,64], masks [S,Tk,1,1] (1 = valid)."""
+    k = k + (1 - mask_k) * -1000000
+    v = v * mask_v
+    qs = F.softmax(q, dim=-1)
+    ks = F.softmax(k, dim=1)
+    att = torch.einsum("bnhd,bnhl->bhdl", ks, v)
+    return torch.einsum("bnhd,bhdl->bnhl", qs, att)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("S,T,H", [(4, 196, 8), (6, 33, 8), (2, 1, 2)])
+def test_eff_attn_bwd_self_and_inter(cuda, dtype, S, T, H):
+    ops = _ops()
+    D = H * 64
+    g = torch.Generator(device=cuda).manual_seed(S * 1000 + T)
+    qkv = torch.randn(S * T, 3 * D, device=cuda, generator=g).to(dtype)
+    dy = torch.randn(S * T, D, device=cuda, generator=g).to(dtype)
+    lens = torch.randint(max(1, T // 3), T + 1, (S,), device=cuda, generator=g).int()
+    mask = (torch.arange(T, device=cuda)[None] < lens[:, None]).float().view(S, T, 1, 1)
+    tol = 3e-5 if dtype == torch.float32 else 2e-2
+    for mode in (ops.ATTN_SELF, ops.ATTN_INTER):
+        r = qkv.float().view(S, T, 3, H, 64).clone().requires_grad_(True)
+        q, k, v = r[:, :, 0], r[:, :, 1], r[:, :, 2]
+        if mode == ops.ATTN_INTER:
+            sw = lambda a: torch.cat([a[S // 2:], a[:S // 2]])
+            y = _attn_ref(q, sw(k), sw(v), mask, torch.ones_like(mask))
+        else:
+            y = _attn_ref(q, k, v, mask, mask)
+        y.backward(dy.float().view(S, T, H, 64))
+        want = r.grad.view(S * T, 3 * D)
+        d = torch.empty_like(qkv)
+        ops.eff_attn_bwd(mode, S, T, H, q=qkv[:, :D], k=qkv[:, D:2 * D], v=qkv[:, 2 * D:], dy=dy, dq=d[:, :D],
+                         dk=d[:, D:2 * D], dv=d[:, 2 * D:], length=lens, pair_shift=S // 2 if mode == ops.ATTN_INTER else 0)
+        for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+            if T == 1 and name != "dv":
+                # one key row: Ks == 1, A has identical rows, so dQ and dK are exactly zero analytically
+                assert (d[:, sl].float() - want[:, sl]).abs().max().item() < 1e-5
+                continue
+            e = rel(d[:, sl], want[:, sl])
+            assert e < tol, (mode, name, e)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N", [77, 1])
+def test_eff_attn_bwd_text(cuda, dtype, N):
+    ops = _ops()
+    S, T, H = 4, 50, 8
+    D = H * 64
+    q = torch.randn(S * T, D, device=cuda).to(dtype)
+    kv = torch.randn(S * N, 2 * D, device=cuda).to(dtype)
+    dy = torch.randn(S * T, D, device=cuda).to(dtype)
+    qr = q.float().view(S, T, H, 64).clone().requires_grad_(True)
+    kvr = kv.float().view(S, N, 2, H, 64).clone().requires_grad_(True)
+    ones = torch.ones(S, N, 1, 1, device=cuda)
+    y = _attn_ref(qr, kvr[:, :, 0], kvr[:, :, 1], ones, ones)
+    y.backward(dy.float().view(S, T, H, 64))
+    a = torch.empty(S, H, 64, 64, device=cuda, dtype=dtype)
+    ops.eff_attn(ops.ATTN_KV_ONLY, S, N, H, k=kv[:, :D], v=kv[:, D:], a_out=a)
+    dq = torch.empty_like(q)
+    dA = torch.empty(S, H, 64, 64, device=cuda)
+    ops.eff_attn_bwd(ops.ATTN_Q_ONLY, S, T, H, q=q, a_in=a, dy=dy, dq=dq, dA=dA)
+    dkv = torch.empty_like(kv)
+    ops.eff_attn_bwd(ops.ATTN_KV_ONLY, S, N, H, k=kv[:, :D], v=kv[:, D:], dk=dkv[:, :D], dv=dkv[:, D:], dA=dA)
+    tol = 3e-5 if dtype == torch.float32 else 2e-2
+    if N > 1:
+        assert rel(dq, qr.grad.view(S * T, D)) < tol
+    else:       # one token: A has identical rows, dQ is analytically zero (rounding noise ~1e-9 on both sides)
+        assert (dq.float() - qr.grad.view(S * T, D)).abs().max().item() < 1e-5
+    assert rel(dkv[:, D:], kvr.grad[:, :, 1].reshape(S * N, D)) < tol
+    if N > 1:   # a single token has softmax == 1 and a zero key gradient
+        assert rel(dkv[:, :D], kvr.grad[:, :, 0].reshape(S * N, D)) < tol
+    else:
+        assert dkv[:, :D].float().abs().max().item() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ model level
+def _build(layers, precision, cuda, seed=0):
+    import weights
+    import hig_b200  # noqa: F401
+    from hig_b200.interaction_transformer import MotionInteractionTransformer
+    m = MotionInteractionTransformer(263, num_frames=196, num_layers=layers, latent_dim=512, cap_id=True,
+                                     precision=precision)
+    sd = weights.make_state_dict(seed=seed, num_layers=layers)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(cuda).train()
+    m.cap_id = False
+    return m, sd
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_grads_match_reference_golden(cuda, precision):
+    """The labelled training step of the REAL reference (q_sample -> denoiser -> masked MSE -> backward): prediction,
+    loss and the gradient of EVERY parameter (norms) plus four full gradient tensors."""
+    import diffusion_oracle as DF
+    import weights
+    from hig_b200.gaussian_diffusion import (GaussianDiffusion, LossType, ModelMeanType, ModelVarType,
+                                             get_named_beta_schedule)
+    d = np.load(os.path.join(GOLDEN, "train.npz"))
+    cfg = ast.literal_eval(str(d["cfg"]))
+    inp = weights.make_inputs(cfg["seed"], cfg["S"], cfg["T"], n_text=cfg["n_text"], lengths=cfg["lengths"])
+    m, _ = _build(cfg["layers"], precision, cuda)
+    diff = GaussianDiffusion(betas=get_named_beta_schedule("linear", 1000), model_mean_type=ModelMeanType.EPSILON,
+                             model_var_type=ModelVarType.FIXED_SMALL, loss_type=LossType.MSE)
+    noise = weights.make_noise(cfg["seed"] + 100, 0, cfg["S"], cfg["T"])[0].to(cuda)
+    g = lambda k: inp[k].to(cuda)
+    terms = diff.training_losses(m, g("x"), g("t"), noise=noise,
+                                 model_kwargs={"xf_proj": g("xf_proj"), "xf_out": g("xf_out"), "length": g("length")})
+    tol = GTOL[precision]
+    ftol = 1e-5 if precision == "fp32" else 1e-2
+    assert rel(terms["pred"].detach(), d["pred"]) < ftol
+    mask = (torch.arange(cfg["T"], device=cuda)[None] < g("length")[:, None]).float()
+    loss = DF.masked_mse_loss(terms["pred"], noise, mask)
+    assert abs(loss.item() - float(d["loss_label"])) < max(ftol, 1e-5) * abs(float(d["loss_label"])) * 2
+    loss.backward()
+    named = dict(m.named_parameters())
+    for key in d.files:
+        if key.startswith("grad:"):
+            e = rel(named[key[5:]].grad, d[key])
+            assert e < tol, (key, e)
+    bad = []
+    for n, gn in zip([str(n) for n in d["grad_names"]], d["grad_norms"]):
+        if n.startswith(("text_proj", "cap_embedding")):
+            continue        # not reached on the xf_proj/xf_out-given branch
+        got = 0.0 if named[n].grad is None else named[n].grad.norm().item()
+        if gn < 0:
+            continue
+        # key.bias gradients are analytically zero (the time softmax is shift invariant): absolute floor in bf16
+        if abs(got - gn) > tol * max(gn, 1e-9) * 2 + (1e-9 if precision == "fp32" else 2e-5):
+            bad.append((n, got, float(gn)))
+    assert not bad, bad[:8]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_grads_against_oracle(cuda, precision):
+    """3 layers, T=64, 77 text tokens, mixed lengths: every parameter gradient and the gradients that flow back into
+    the text encoder (xf_proj, xf_out) against torch.autograd through the CPU oracle."""
+    import denoiser_oracle as DO
+    import diffusion_oracle as DF
+    import weights
+    L, S, T = 3, 6, 64
+    m, sd = _build(L, precision, cuda, seed=4)
+    inp = weights.make_inputs(41, S, T, n_text=77, lengths=[64, 40, 17, 64, 40, 17])
+    tgt = weights.make_noise(7, 0, S, T)[0]
+    # oracle
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xfp, xfo = inp["xf_proj"].clone().requires_grad_(True), inp["xf_out"].clone().requires_grad_(True)
+    pred_o = DO.denoiser_forward(sdg, inp["x"], inp["t"], inp["length"], xfp, xfo)
+    mask = DO.src_mask_from_length(T, inp["length"], "cpu")
+    DF.masked_mse_loss(pred_o, tgt, mask).backward()
+    # B200
+    g = lambda k: inp[k].to(cuda)
+    xfp_c, xfo_c = g("xf_proj").requires_grad_(True), g("xf_out").requires_grad_(True)
+    pred = m(g("x"), g("t"), length=g("length"), xf_proj=xfp_c, xf_out=xfo_c)
+    DF.masked_mse_loss(pred, tgt.to(cuda), mask.to(cuda)).backward()
+    tol = GTOL[precision]
+    assert rel(pred.detach(), pred_o.detach()) < (1e-5 if precision == "fp32" else 1e-2)
+    assert rel(xfp_c.grad, xfp.grad) < tol and rel(xfo_c.grad, xfo.grad) < tol
+    worst = []
+    for n, p in m.named_parameters():
+        if n.startswith(("text_proj", "cap_embedding")):
+            continue
+        go = sdg[n].grad
+        if n == "sequence_embedding":
+            assert p.grad[T - 1:].abs().max().item() == 0.0
+        if n.endswith("key.bias"):      # analytically zero (time-softmax shift invariance)
+            assert p.grad.abs().max().item() < 1e-4
+            continue
+        e = rel(p.grad, go)
+        worst.append((e, n))
+    worst.sort(reverse=True)
+    assert worst[0][0] < tol, worst[:6]
+
+
+def test_trainer_update_step_runs_and_learns(cuda):
+    """DDPMMulTrainer.forward/update (labelled and PIT) through Adam: the loss on a fixed batch goes down."""
+    import argparse
+    from hig_b200.interaction_transformer import MotionInteractionTransformer
+    from hig_b200.mul_ddpm_trainer import DDPMMulTrainer
+    torch.manual_seed(0)
+    np.random.seed(0)
+    m = MotionInteractionTransformer(263, num_frames=196, num_layers=2, latent_dim=512, cap_id=True)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if p.abs().max() == 0 and "norm.bias" not in name:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    for label_path in ("labels.npy", None):
+        opt = argparse.Namespace(device=cuda, multi=True, label_path=label_path, cap_id=True, diffusion_steps=1000,
+                                 is_train=True)
+        tr = DDPMMulTrainer(opt, m)
+        tr.opt_encoder = torch.optim.Adam(m.parameters(), lr=2e-4)
+        tr.train_mode()
+        B, T = 4, 24
+        batch = ([1, 2, 3, 4], [5, 6, 7, 8], torch.randn(B, T, 263), torch.randn(B, T, 263),
+                 torch.tensor([24, 20, 9, 24]), None)
+        losses = []
+        for _ in range(6):
+            np.random.seed(3)      # same timesteps every iteration
+            torch.manual_seed(3)   # same noise
+            tr.forward(batch)
+            losses.append(tr.update()["loss_mot_rec"])
+        assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
