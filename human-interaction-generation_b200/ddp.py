@@ -1,0 +1,160 @@
+"""Data parallelism for the two places the path shards.
+
+Training — `DataParallel` replaces `MMDistributedDataParallel` over Gloo (codes/tools/train.py:55,78-82): one process per
+GPU, gradients averaged across ranks.  The denoiser's backward (autograd.py) writes its gradients into one flat fp32
+buffer whose segments become final in a known order (heads | layer L-1 | ... | layer 0 | embeddings); each segment is
+handed to `GradReducer.segment_ready` the moment it is final and all-reduced asynchronously (NCCL over
+NVLink/NVSwitch runs on its own stream, ordered after the kernels that produced the segment), so the exchange of
+layer i overlaps the backward kernels of layers i-1..0.  Parameters outside the denoiser kernels (text encoder,
+text_proj, cap_embedding — differentiated by torch.autograd) are reduced as one flat bucket when the last of them
+has accumulated its gradient.  No collective is issued in forward; buffers are not broadcast
+(`broadcast_buffers=False` in the reference).
+
+Sampling — pairs are independent (both persons of a pair stay on one rank): `shard_pairs` cuts the batch
+contiguously, every rank samples its slice with no collective in the loop, `gather_pairs` brings the results to
+rank 0 (the reference samples on a single GPU, codes/trainers/mul_ddpm_trainer.py:200-221).
+
+The host logic is backend-agnostic: tests/test_ddp_cpu.py runs it with world_size 2 on `gloo`.
+"""
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+def _avg_supported(group):
+    return dist.get_backend(group) == "nccl"
+
+
+class GradReducer:
+    """Asynchronous mean all-reduce of gradient segments + one trailing bucket of 'other' parameters."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self._pending = []          # (work, tensor, needs_div)
+        self.bytes_reduced = 0
+        self.calls = 0
+
+    def segment_ready(self, index, flat):
+        """`flat` (a contiguous 1-D view) is final: start its all-reduce; the result is the mean over ranks."""
+        if self.world == 1:
+            return
+        if _avg_supported(self.group):
+            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            self._pending.append((work, flat, False))
+        else:
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._pending.append((work, flat, True))
+        self.bytes_reduced += flat.numel() * flat.element_size()
+        self.calls += 1
+
+    def finish(self):
+        """Make the current stream wait for every outstanding all-reduce (no host synchronisation on NCCL)."""
+        for work, flat, needs_div in self._pending:
+            work.wait()
+            if needs_div:
+                flat.div_(self.world)
+        self._pending = []
+
+    def reduce_params(self, params):
+        """Mean all-reduce of p.grad for `params` as ONE flat bucket (blocking on the stream, not the host)."""
+        grads = [p.grad for p in params if p.grad is not None]
+        if self.world == 1 or not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        self.segment_ready(-1, flat)
+        self.finish()
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+
+class DataParallel(nn.Module):
+    """`DataParallel(encoder)` — exposes `.module` like torch DDP (DDPMMulTrainer.backward_G reads
+    `self.encoder.module.two_embed`, trainers/mul_ddpm_trainer.py:225)."""
+
+    def __init__(self, module, process_group=None, broadcast_parameters=True):
+        super().__init__()
+        if not dist.is_initialized():
+            raise RuntimeError("hig_b200.ddp.DataParallel needs torch.distributed.init_process_group first")
+        self.module = module
+        self.group = process_group
+        self.reducer = GradReducer(process_group)
+        if broadcast_parameters and self.reducer.world > 1:
+            with torch.no_grad():
+                for p in module.parameters():
+                    dist.broadcast(p.data, src=0, group=process_group)
+        # the denoiser's flat gradient segments (autograd.py)
+        module._grad_segment_hook = self.reducer.segment_ready
+        module._grad_finish_hook = self.reducer.finish
+        # everything torch.autograd differentiates outside the denoiser kernels
+        self._other = []
+        if hasattr(module, "temporal_decoder_blocks"):
+            from .autograd import denoiser_param_names
+            mine = {n for seg in denoiser_param_names(module) for n in seg}
+        else:
+            mine = set()
+        for n, p in module.named_parameters():
+            if p.requires_grad and n not in mine:
+                self._other.append(p)
+                p.register_post_accumulate_grad_hook(self._other_hook)
+        self._other_seen = 0
+
+    def _other_hook(self, p):
+        self._other_seen += 1
+        if self._other_seen == len(self._other):
+            self._other_seen = 0
+            self.reducer.reduce_params(self._other)
+
+    def forward(self, *args, **kwargs):
+        self._other_seen = 0
+        return self.module(*args, **kwargs)
+
+
+# ---------------------------------------------------------------------------------------------- sampling shards
+def shard_pairs(n_pairs, world, rank):
+    """Contiguous [lo, hi) slice of the pairs for `rank`; sizes differ by at most one."""
+    base, extra = divmod(n_pairs, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_pairs(local, n_pairs, dim_pose, group=None, dst=0):
+    """local: list of [motion1 [T,C], motion2 [T,C]] for this rank's slice (T may differ between pairs).
+    Returns the full list in pair order on `dst`, None elsewhere.  One collective, after sampling has finished."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    per = (n_pairs + world - 1) // world
+    dev = local[0][0].device if local else torch.device("cpu")
+    t_loc = max([m.shape[0] for pair in local for m in pair], default=0)
+    t_all = torch.tensor([t_loc], device=dev, dtype=torch.long)
+    dist.all_reduce(t_all, op=dist.ReduceOp.MAX, group=group)
+    Tm = int(t_all.item())
+    buf = torch.zeros(per, 2, Tm, dim_pose, device=dev)
+    lens = torch.zeros(per, dtype=torch.long, device=dev)
+    for i, pair in enumerate(local):
+        lens[i] = pair[0].shape[0]
+        for j in (0, 1):
+            buf[i, j, :pair[j].shape[0]] = pair[j]
+    bufs = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    lls = [torch.empty_like(lens) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, bufs, dst=dst, group=group)
+    dist.gather(lens, lls, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = []
+    for r in range(world):
+        lo, hi = shard_pairs(n_pairs, world, r)
+        for i in range(hi - lo):
+            T = int(lls[r][i])
+            out.append([bufs[r][i, 0, :T], bufs[r][i, 1, :T]])
+    return out
+
+
+def generate_sharded(trainer, caption1, caption2, m_lens, dim_pose, batch_size=512, group=None, dst=0):
+    """`DDPMMulTrainer.generate` over all ranks of `group`: every rank samples its contiguous slice of the pairs."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_pairs(len(caption1), world, rank)
+    local = trainer.generate(caption1[lo:hi], caption2[lo:hi], m_lens[lo:hi], dim_pose, batch_size=batch_size) \
+        if hi > lo else []
+    return gather_pairs(local, len(caption1), dim_pose, group=group, dst=dst)

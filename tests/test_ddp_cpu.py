@@ -1,0 +1,154 @@
+"""Host-side logic of the multi-GPU paths on CPU, world_size 2, gloo backend:
+gradient-segment reducer, the trailing 'other parameters' bucket, parameter broadcast, pair sharding and the final
+gather.  The kernels themselves need a GPU (tests/test_train_gpu.py); nothing here launches one."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, fn_name, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        globals()[fn_name](rank, world)
+        ret[rank] = "ok"
+    except Exception as ex:  # noqa
+        import traceback
+        ret[rank] = traceback.format_exc()
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn_name, world=2):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn_name, ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret.get(r) == "ok", ret.get(r)
+
+
+# ------------------------------------------------------------------------------------------------ workers
+def _w_segments(rank, world):
+    import hig_b200  # noqa: F401
+    from hig_b200.ddp import GradReducer
+    red = GradReducer()
+    flat = torch.arange(100, dtype=torch.float32) * (rank + 1)
+    bounds = [(0, 10), (10, 64), (64, 100)]
+    for i, (lo, hi) in enumerate(bounds):     # segments become final one after the other
+        red.segment_ready(i, flat[lo:hi])
+    red.finish()
+    want = torch.arange(100, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+    assert torch.allclose(flat, want)
+    assert red.calls == 3 and red.bytes_reduced == 400
+
+
+def _w_other_bucket_and_broadcast(rank, world):
+    import hig_b200  # noqa: F401
+    from hig_b200.ddp import DataParallel
+    torch.manual_seed(100 + rank)             # different init per rank: construction must broadcast rank 0's
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+    ddp = DataParallel(net)
+    ref = [torch.empty_like(p) for p in net.parameters()]
+    for r, p in zip(ref, net.parameters()):
+        r.copy_(p.data)
+        dist.broadcast(r, src=0)
+        assert torch.equal(r, p.data)
+    assert hasattr(ddp, "module") and ddp.module is net
+    for it in range(2):                       # two iterations: the hook counter must re-arm
+        net.zero_grad()
+        torch.manual_seed(7 + rank + 10 * it)
+        x = torch.randn(4, 5)
+        ddp(x).pow(2).sum().backward()
+        got = [p.grad.clone() for p in net.parameters()]
+        # expected: mean over ranks of the local gradients
+        net.zero_grad()
+        net(x).pow(2).sum().backward()
+        for g, p in zip(got, net.parameters()):
+            loc = p.grad.clone()
+            dist.all_reduce(loc)
+            assert torch.allclose(g, loc / world, atol=1e-6)
+
+
+def _w_sampling_shards(rank, world):
+    import hig_b200  # noqa: F401
+    from hig_b200.ddp import gather_pairs, shard_pairs
+    n = 7
+    cover = []
+    for r in range(world):
+        lo, hi = shard_pairs(n, world, r)
+        cover += list(range(lo, hi))
+    assert cover == list(range(n))
+    lo, hi = shard_pairs(n, world, rank)
+    # pair i has T = 3 + i frames; motion values encode (pair, person)
+    local = [[torch.full((3 + i, 5), float(10 * i)), torch.full((3 + i, 5), float(10 * i + 1))] for i in range(lo, hi)]
+    out = gather_pairs(local, n, 5)
+    if rank == 0:
+        assert len(out) == n
+        for i, (a, b) in enumerate(out):
+            assert a.shape == (3 + i, 5) and b.shape == (3 + i, 5)
+            assert float(a[0, 0]) == 10 * i and float(b[-1, -1]) == 10 * i + 1
+    else:
+        assert out is None
+
+
+# ------------------------------------------------------------------------------------------------ tests
+def test_gradient_segments_are_averaged_world2():
+    _run("_w_segments")
+
+
+def test_other_parameter_bucket_and_broadcast_world2():
+    _run("_w_other_bucket_and_broadcast")
+
+
+def test_sampling_shards_and_gather_world2():
+    _run("_w_sampling_shards")
+
+
+def test_flat_gradient_layout_covers_every_denoiser_parameter():
+    """autograd._Grads: L+2 segments in backward-completion order, adjacent regions where a fused kernel writes several
+    parameters at once (Q|K|V weights, LayerNorm weight|bias, all stylization emb-linears)."""
+    import hig_b200  # noqa: F401
+    from hig_b200.autograd import _Grads, denoiser_param_names
+    from hig_b200.interaction_transformer import MotionInteractionTransformer
+    m = MotionInteractionTransformer(263, num_frames=196, num_layers=2, cap_id=True)
+    segs = denoiser_param_names(m)
+    assert len(segs) == 2 + 2
+    names = [n for s in segs for n in s]
+    assert len(names) == len(set(names))
+    outside = {n for n, _ in m.named_parameters()} - set(names)
+    assert outside == {"cap_embedding", "text_proj.0.weight", "text_proj.0.bias"}
+    gr = _Grads(m, "cpu")
+    assert gr.flat.numel() == sum(p.numel() for n, p in m.named_parameters() if n in set(names))
+    assert gr.seg_bounds[0][0] == 0 and gr.seg_bounds[-1][1] == gr.flat.numel()
+    for (lo, hi), (lo2, _) in zip(gr.seg_bounds, gr.seg_bounds[1:]):
+        assert hi == lo2
+    p = "temporal_decoder_blocks.1.sa_block."
+    r = gr.region(p + "query.weight", 3 * 512 * 512, (1536, 512))
+    r[512:1024].fill_(2.0)
+    assert float(gr.views[p + "key.weight"].min()) == 2.0 and float(gr.views[p + "query.weight"].max()) == 0.0
+    r = gr.region(p + "norm.weight", 1024, (1024,))
+    r[512:].fill_(3.0)
+    assert float(gr.views[p + "norm.bias"].min()) == 3.0
+    first = segs[-1][0]
+    n_styl = 2 * 4
+    r = gr.region(first, n_styl * 1024 * 2048, (n_styl * 1024, 2048))
+    r[1024 * 5:1024 * 6].fill_(5.0)
+    assert float(gr.views["temporal_decoder_blocks.1.ca_block.proj_out.emb_layers.1.weight"].min()) == 5.0

@@ -1,0 +1,107 @@
+"""BASELINE config 4: DDP training step, 128 pairs per GPU (S=256 sequences, T=91 rows as the dataset crops them,
+datasets/mul_dataset.py:186-201), synthetic two-person motion + captions, labelled mode (forward_twice=False).
+    python tools/train_step.py [--pairs 128] [--frames 91] [--iters 10] [--denoiser-only] [--pit]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/train_step.py ...
+Prints one JSON line: ms per iteration (CUDA events, max over ranks), pairs/s over all ranks, phase split."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pairs", type=int, default=128)
+    ap.add_argument("--frames", type=int, default=91)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--denoiser-only", action="store_true", help="cap_id model: no CLIP / text-encoder forward")
+    ap.add_argument("--pit", action="store_true", help="unlabelled (PIT) mode: 4B sequences per iteration")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import hig_b200  # noqa: F401
+    from hig_b200 import _lib
+    from hig_b200.interaction_transformer import MotionInteractionTransformer
+    from hig_b200.mul_ddpm_trainer import DDPMMulTrainer
+    torch.manual_seed(0)
+    m = MotionInteractionTransformer(263, num_frames=196, num_layers=8, latent_dim=512, cap_id=args.denoiser_only)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if not name.startswith("clip.") and p.abs().max() == 0 and "norm.bias" not in name:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    m = m.to(dev)
+    enc = m
+    if world > 1:
+        from hig_b200.ddp import DataParallel
+        enc = DataParallel(m)
+    opt = argparse.Namespace(device=dev, multi=True, label_path=None if args.pit else "labels", cap_id=args.denoiser_only,
+                             diffusion_steps=1000, is_train=True)
+    tr = DDPMMulTrainer(opt, enc)
+    tr.opt_encoder = torch.optim.Adam(m.parameters(), lr=2e-4, fused=True)
+    tr.train_mode()
+    B, T = args.pairs, args.frames
+    rs = np.random.RandomState(rank)
+    if args.denoiser_only:
+        c1, c2 = list(rs.randint(0, 43, B)), list(rs.randint(0, 43, B))
+    else:
+        c1 = [bench.CAPTIONS[(i + rank) % len(bench.CAPTIONS)][0] for i in range(B)]
+        c2 = [bench.CAPTIONS[(i + rank) % len(bench.CAPTIONS)][1] for i in range(B)]
+    batch = (c1, c2, torch.randn(B, T, 263), torch.randn(B, T, 263), torch.from_numpy(rs.randint(20, 200, B)), None)
+
+    def it():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        tr.forward(batch)
+        ev[1].record()
+        logs = tr.update()
+        ev[2].record()
+        return ev, logs
+
+    for _ in range(args.warmup):
+        it()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    evs = [it() for _ in range(args.iters)]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.iters
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    fwd = sum(e[0][0].elapsed_time(e[0][1]) for e in evs) / args.iters
+    bwd = sum(e[0][1].elapsed_time(e[0][2]) for e in evs) / args.iters
+    S = (4 if args.pit else 2) * B
+    fl = bench.flops_per_denoiser_step(S, T) * 3
+    if rank == 0:
+        print(json.dumps({"workload": f"training step, {B} pairs/GPU x {T} frames, {'PIT' if args.pit else 'labelled'}, "
+                                      f"{'denoiser only (cap_id)' if args.denoiser_only else 'with CLIP + text encoder'}",
+                          "n_gpus": world, "ms_per_iter": ms, "pairs_per_s": world * B / ms * 1e3,
+                          "forward_ms": fwd, "backward_plus_adam_ms": bwd, "loss": evs[-1][1]["loss_mot_rec"],
+                          "hig_launches_per_iter": (_lib.launch_count() - l0) / args.iters,
+                          "denoiser_fwd_bwd_tflops": fl / (ms * 1e-3) / 1e12,
+                          "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
