@@ -24,12 +24,16 @@ SIGNATURES = {
     "hig_l2_persist": [c_void_p, c_ull, ctypes.c_float, c_void_p],
     "hig_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                       c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
+    "hig_gemm_bf16_ex": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                         c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
     "hig_gemm_f32": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                      c_void_p, c_int, c_int, c_void_p],
     "hig_ln_film_silu": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                          c_int, c_void_p],
     "hig_eff_attn": [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                      c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "hig_attn_apply_stylize": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+                               c_int, c_void_p],
     "hig_timestep_embed": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_pack_motion": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_ddpm_step": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ull,

@@ -1,0 +1,276 @@
+// hig_attn_apply_stylize: the query half of the efficient attention fused with the StylizationBlock's
+// LayerNorm + FiLM + SiLU, for all 8 heads of a row at once:
+//
+//   Y[t, h*64 : (h+1)*64] = softmax_feat(Q[t, h]) . A[s, h]          (A = softmax_time(K)^T V, 64 x 64 per head,
+//                                                                      produced by hig_eff_attn KV_ONLY)
+//   out[t, :] = SiLU( LayerNorm_512(Y[t, :]) * (1 + scale_s) + shift_s )
+//
+// Reference: the einsum 'bnhd,bhdl->bnhl' + reshape of LinearTemporal{Self,Cross,InteractionCross}Attention.forward
+// (codes/models/interaction_transformer.py:128,162,201) followed by StylizationBlock.forward's norm / FiLM / SiLU
+// (:86-97).  Y never reaches HBM: a CTA owns full 512-wide rows (warp w = head w), so the LayerNorm statistics are
+// exchanged between the 8 warps through shared memory.  Traffic: read Q + A (L2-resident), write out.
+//
+// CTA = 8 warps, one 16-row tile per iteration; Q tiles are prefetched with cp.async into a per-warp double buffer
+// (XOR-swizzled 128-byte rows, conflict-free ldmatrix); A for the 8 heads sits in shared memory (64 KB, swizzled).
+#include "hig_common.cuh"
+#include "hig_internal.h"
+
+namespace hig {
+
+constexpr int AP_THREADS = 256;
+constexpr int AP_HD = 64;
+constexpr int AP_D = 512;
+
+HIG_DEVICE void ap_cp_async16(uint32_t smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(sz) : "memory");
+}
+HIG_DEVICE void ap_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> HIG_DEVICE void ap_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+HIG_DEVICE void ap_ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+HIG_DEVICE void ap_ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+HIG_DEVICE void ap_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// byte offset of 16-byte chunk `c` of row `r` in a [rows][128 B] tile whose chunks are XOR-swizzled with r & 7
+HIG_DEVICE uint32_t ap_swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+constexpr int AP_SMEM_A = 8 * AP_HD * 128;          // 64 KB: A[h][d][l]
+constexpr int AP_SMEM_Q = 8 * 2 * 16 * 128;         // 32 KB: per warp, 2 buffers of 16 rows x 128 B
+constexpr int AP_SMEM_GB = 2 * AP_D * 4;            // gamma', beta'
+constexpr int AP_SMEM_RED = 2 * 16 * 8 * 4;         // row partial sums / centred squares [16 rows][8 warps]
+constexpr int AP_SMEM = AP_SMEM_A + AP_SMEM_Q + AP_SMEM_GB + AP_SMEM_RED;
+
+__global__ void __launch_bounds__(AP_THREADS, 2)
+attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ a_in,
+                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                          const float* __restrict__ scale_shift, int ss_stride, int apply_silu,
+                          __nv_bfloat16* __restrict__ out, int T, int tiles_per_cta) {
+  extern __shared__ __align__(128) uint8_t ap_smem[];
+  const uint32_t sA = smem_u32(ap_smem);
+  const uint32_t sQ = sA + AP_SMEM_A;
+  float* sG = reinterpret_cast<float*>(ap_smem + AP_SMEM_A + AP_SMEM_Q);
+  float* sB = sG + AP_D;
+  float* sR1 = sB + AP_D;            // [16][8]
+  float* sR2 = sR1 + 16 * 8;         // [16][8]
+
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int s = blockIdx.y;
+  const int n_tiles = (T + 15) >> 4;
+  const int tile0 = blockIdx.x * tiles_per_cta;
+  const int tile1 = min(n_tiles, tile0 + tiles_per_cta);
+  if (tile0 >= tile1) return;
+
+  // ---- A of the 8 heads: 8 * 64 rows * 8 chunks of 16 B
+  {
+    const __nv_bfloat16* ag = a_in + (size_t)s * 8 * AP_HD * AP_HD;
+    for (int i = tid; i < 8 * AP_HD * 8; i += AP_THREADS) {
+      const int row = i >> 3, c = i & 7;  // row = h*64 + d
+      ap_cp_async16(sA + ap_swz(row, c), ag + (size_t)row * AP_HD + c * 8, true);
+    }
+  }
+  ap_commit();
+  // ---- this warp's Q tiles: 16 rows x 8 chunks = 128 x 16 B per tile, 4 per lane
+  const uint32_t sQw = sQ + w * (2 * 16 * 128);
+  const __nv_bfloat16* qg = q + (size_t)s * T * ldq + w * AP_HD;
+  auto prefetch = [&](int tile, int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 32 + lane;
+      const int r = idx >> 3, c = idx & 7;
+      const int t = tile * 16 + r;
+      ap_cp_async16(sQw + buf * 2048 + ap_swz(r, c), qg + (size_t)min(t, T - 1) * ldq + c * 8, t < T);
+    }
+  };
+  prefetch(tile0, 0);
+  ap_commit();
+  // ---- folded FiLM affine: out = n_hat * G + B,  G = gamma (1 + scale),  B = beta (1 + scale) + shift
+  for (int i = tid; i < AP_D; i += AP_THREADS) {
+    float g = gamma[i], b = beta[i];
+    if (scale_shift) {
+      const float m1 = 1.0f + scale_shift[(size_t)s * ss_stride + i];
+      g *= m1;
+      b = fmaf(b, m1, scale_shift[(size_t)s * ss_stride + AP_D + i]);
+    }
+    sG[i] = g;
+    sB[i] = b;
+  }
+  ap_wait<1>();      // A landed (this thread's part)
+  __syncthreads();   // ... everyone's, and sG / sB
+
+  const int g = lane >> 2, tg = lane & 3;
+  const uint32_t sAw = sA + w * (AP_HD * 128);
+  int buf = 0;
+  for (int tile = tile0; tile < tile1; ++tile, buf ^= 1) {
+    if (tile + 1 < tile1) prefetch(tile + 1, buf ^ 1);
+    ap_commit();
+    ap_wait<1>();
+    __syncwarp();
+    const uint32_t sQt = sQw + buf * 2048;
+    uint32_t af[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int c = kk * 2 + ((lane >> 4) & 1);
+      ap_ldsm_x4(sQt + ap_swz(row, c), af[kk][0], af[kk][1], af[kk][2], af[kk][3]);
+    }
+    // feature softmax on the fragments: row g <- regs {0,2}, row g+8 <- regs {1,3} of every k-step
+    float x0[16], x1[16];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      float2 f;
+      f = unpack_bf16x2(af[kk][0]); x0[4 * kk + 0] = f.x; x0[4 * kk + 1] = f.y;
+      f = unpack_bf16x2(af[kk][2]); x0[4 * kk + 2] = f.x; x0[4 * kk + 3] = f.y;
+      f = unpack_bf16x2(af[kk][1]); x1[4 * kk + 0] = f.x; x1[4 * kk + 1] = f.y;
+      f = unpack_bf16x2(af[kk][3]); x1[4 * kk + 2] = f.x; x1[4 * kk + 3] = f.y;
+    }
+    float m0 = x0[0], m1 = x1[0];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) { m0 = fmaxf(m0, x0[j]); m1 = fmaxf(m1, x1[j]); }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      x0[j] = __expf(x0[j] - m0); s0 += x0[j];
+      x1[j] = __expf(x1[j] - m1); s1 += x1[j];
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      af[kk][0] = pack_bf16x2(x0[4 * kk + 0] * i0, x0[4 * kk + 1] * i0);
+      af[kk][2] = pack_bf16x2(x0[4 * kk + 2] * i0, x0[4 * kk + 3] * i0);
+      af[kk][1] = pack_bf16x2(x1[4 * kk + 0] * i1, x1[4 * kk + 1] * i1);
+      af[kk][3] = pack_bf16x2(x1[4 * kk + 2] * i1, x1[4 * kk + 3] * i1);
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b0, b1, b2, b3;
+        const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = np * 2 + ((lane >> 4) & 1);
+        ap_ldsm_x4_t(sAw + ap_swz(row, c), b0, b1, b2, b3);
+        ap_mma(acc[2 * np], af[kk], b0, b1);
+        ap_mma(acc[2 * np + 1], af[kk], b2, b3);
+      }
+    }
+    // ---- LayerNorm over the 512 columns of a row = 8 warps x 64 columns: two-pass statistics through smem
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { r0 += acc[nt][0] + acc[nt][1]; r1 += acc[nt][2] + acc[nt][3]; }
+    r0 += __shfl_xor_sync(0xffffffffu, r0, 1); r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, 1); r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+    if (tg == 0) { sR1[g * 8 + w] = r0; sR1[(g + 8) * 8 + w] = r1; }
+    __syncthreads();
+    float mean0, mean1;
+    {
+      const float4 a = *reinterpret_cast<const float4*>(sR1 + g * 8), b = *reinterpret_cast<const float4*>(sR1 + g * 8 + 4);
+      const float4 c = *reinterpret_cast<const float4*>(sR1 + (g + 8) * 8), d = *reinterpret_cast<const float4*>(sR1 + (g + 8) * 8 + 4);
+      mean0 = ((a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w)) * (1.0f / AP_D);
+      mean1 = ((c.x + c.y) + (c.z + c.w) + (d.x + d.y) + (d.z + d.w)) * (1.0f / AP_D);
+    }
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      acc[nt][0] -= mean0; acc[nt][1] -= mean0; acc[nt][2] -= mean1; acc[nt][3] -= mean1;
+      q0 = fmaf(acc[nt][0], acc[nt][0], q0); q0 = fmaf(acc[nt][1], acc[nt][1], q0);
+      q1 = fmaf(acc[nt][2], acc[nt][2], q1); q1 = fmaf(acc[nt][3], acc[nt][3], q1);
+    }
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+    if (tg == 0) { sR2[g * 8 + w] = q0; sR2[(g + 8) * 8 + w] = q1; }
+    __syncthreads();
+    float rstd0, rstd1;
+    {
+      const float4 a = *reinterpret_cast<const float4*>(sR2 + g * 8), b = *reinterpret_cast<const float4*>(sR2 + g * 8 + 4);
+      const float4 c = *reinterpret_cast<const float4*>(sR2 + (g + 8) * 8), d = *reinterpret_cast<const float4*>(sR2 + (g + 8) * 8 + 4);
+      rstd0 = rsqrtf(((a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w)) * (1.0f / AP_D) + 1e-5f);
+      rstd1 = rsqrtf(((c.x + c.y) + (c.z + c.w) + (d.x + d.y) + (d.z + d.w)) * (1.0f / AP_D) + 1e-5f);
+    }
+    // ---- affine + SiLU, staged through this warp's consumed Q buffer, then 16-byte row stores
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int col = w * AP_HD + nt * 8 + 2 * tg;
+      const float2 G2 = *reinterpret_cast<const float2*>(sG + col), B2 = *reinterpret_cast<const float2*>(sB + col);
+      float o[4];
+      o[0] = fmaf(acc[nt][0] * rstd0, G2.x, B2.x);
+      o[1] = fmaf(acc[nt][1] * rstd0, G2.y, B2.y);
+      o[2] = fmaf(acc[nt][2] * rstd1, G2.x, B2.x);
+      o[3] = fmaf(acc[nt][3] * rstd1, G2.y, B2.y);
+      if (apply_silu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = o[j] * fmaf(tanh_approx_f(0.5f * o[j]), 0.5f, 0.5f);
+      }
+      // element (row, nt*8 + 2tg) -> chunk nt, byte offset 4*tg inside the chunk
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQt + ap_swz(g, nt) + 4 * tg), "r"(pack_bf16x2(o[0], o[1])) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQt + ap_swz(g + 8, nt) + 4 * tg), "r"(pack_bf16x2(o[2], o[3])) : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 32 + lane;
+      const int r = idx >> 3, c = idx & 7;
+      const int t = tile * 16 + r;
+      if (t < T) {
+        uint4 val;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                     : "r"(sQt + ap_swz(r, c)) : "memory");
+        *reinterpret_cast<uint4*>(out + ((size_t)s * T + t) * AP_D + w * AP_HD + c * 8) = val;
+      }
+    }
+    __syncwarp();
+  }
+  ap_wait<0>();
+}
+
+int attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
+                       const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
+                       cudaStream_t stream) {
+  if (!q || !a_in || !gamma || !beta || !out || S <= 0 || T <= 0)
+    return set_error(HIG_ERR_INVALID, "attn_apply_stylize: bad arguments");
+  if (H != 8) return set_error(HIG_ERR_UNSUPPORTED, "attn_apply_stylize: built for 8 heads x 64 (latent_dim 512)");
+  if (ldq % 8) return set_error(HIG_ERR_INVALID, "attn_apply_stylize: ldq must be a multiple of 8");
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(a_in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return set_error(HIG_ERR_INVALID, "attn_apply_stylize: pointers must be 16-byte aligned");
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_apply_stylize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM);
+    if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_apply_stylize attr: ") + cudaGetErrorString(e));
+    attr = true;
+  }
+  const int n_tiles = (T + 15) / 16;
+  // ~2 CTAs per SM resident at once: split a sequence's tiles over `chunks` CTAs so that S * chunks >= 296
+  int chunks = (2 * 148 + S - 1) / S;
+  if (chunks > n_tiles) chunks = n_tiles;
+  if (chunks < 1) chunks = 1;
+  const int tiles_per_cta = (n_tiles + chunks - 1) / chunks;
+  chunks = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+  dim3 grid(chunks, S);
+  attn_apply_stylize_kernel<<<grid, AP_THREADS, AP_SMEM, stream>>>(
+      (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)a_in, gamma, beta, scale_shift, ss_stride, apply_silu,
+      (__nv_bfloat16*)out, T, tiles_per_cta);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_apply_stylize launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+}  // namespace hig

@@ -68,6 +68,13 @@ int hig_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, 
                         ldo_bf16, act, static_cast<cudaStream_t>(stream));
 }
 
+int hig_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                     const void* residual, int res_dtype, int ldr, int res_row_mod, void* out, int out_dtype, int ldo,
+                     void* out_bf16, int ldo_bf16, int act, void* stream) {
+  return hig::gemm_bf16_ex(A, lda, W, ldw, M, N, K, bias, residual, res_dtype, ldr, res_row_mod, out, out_dtype, ldo,
+                           out_bf16, ldo_bf16, act, static_cast<cudaStream_t>(stream));
+}
+
 int hig_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const float* bias,
                  const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, int act, void* stream) {
   return hig::gemm_f32(A, lda, W, ldw, M, N, K, bias, residual, ldr, res_row_mod, out_f32, ldo_f32, act,
@@ -107,6 +114,13 @@ int hig_ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, co
 int hig_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
                  const float* sqrt_1mac, int S, int TC, float* out, void* stream) {
   return hig::q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, S, TC, out, static_cast<cudaStream_t>(stream));
+}
+
+int hig_attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
+                           const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
+                           void* stream) {
+  return hig::attn_apply_stylize(q, ldq, a_in, gamma, beta, scale_shift, ss_stride, apply_silu, out, S, T, H,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------- training path

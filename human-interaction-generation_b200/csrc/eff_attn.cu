@@ -73,20 +73,23 @@ eff_attn_bf16_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, con
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int TP = (T + 15) & ~15;
   // Q_ONLY (text apply) only stages Q and A: a third of the shared memory, so five CTAs fit per SM instead of two
+  // KV_ONLY stages K and V only (three CTAs per SM)
   const int kv_rows = (mode == 3) ? 0 : TP;
+  const int q_rows = (mode == 2) ? 0 : TP;
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
   __nv_bfloat16* sV = sK + kv_rows * ATT_STRIDE;
   __nv_bfloat16* sQ = sV + kv_rows * ATT_STRIDE;
-  __nv_bfloat16* sA = sQ + TP * ATT_STRIDE;
+  __nv_bfloat16* sA = sQ + q_rows * ATT_STRIDE;
   float* sred = reinterpret_cast<float*>(sA + HD * ATT_STRIDE);  // [ATT_WARPS][64] partials, then [64] inverse sums
   float* sinv = sred + ATT_WARPS * 64;
 
   const int h = blockIdx.x, s = blockIdx.y, H = gridDim.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool do_kv = (mode != 3), do_q = (mode != 2);
-  const int s_kv = (mode == 1) ? (s + pair_shift) % S : s;
+  // INTER, and KV_ONLY with a pair shift (the K/V half of the inter-person attention): partner's K,V, own length
+  const int s_kv = (mode == 1 || mode == 2) ? (s + pair_shift) % S : s;
   int len = T;
-  if (length && mode != 2 && mode != 3) {
+  if (length && mode != 3) {
     len = length[s];
     len = len < 0 ? 0 : (len > T ? T : len);
   }
@@ -300,9 +303,9 @@ eff_attn_f32_kernel(int mode, const float* __restrict__ q, int ldq, const float*
   const int h = blockIdx.x, s = blockIdx.y, H = gridDim.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool do_kv = (mode != 3), do_q = (mode != 2);
-  const int s_kv = (mode == 1) ? (s + pair_shift) % S : s;
+  const int s_kv = (mode == 1 || mode == 2) ? (s + pair_shift) % S : s;
   int len = T;
-  if (length && mode != 2 && mode != 3) {
+  if (length && mode != 3) {
     len = length[s];
     len = len < 0 ? 0 : (len > T ? T : len);
   }
@@ -402,7 +405,7 @@ int eff_attn(int mode, const void* q, int ldq, const void* k, const void* v, int
     if ((do_q && ((ldq % 8) || (ldy % 8))) || (do_kv && (ldkv % 8)))
       return set_error(HIG_ERR_INVALID, "eff_attn: bf16 leading dimensions must be multiples of 8");
     const int TP = (T + 15) & ~15;
-    const size_t smem = (size_t)((mode == 3 ? 1 : 3) * TP + HD) * ATT_STRIDE * 2 + (ATT_WARPS + 1) * 64 * sizeof(float);
+    const size_t smem = (size_t)((mode == 3 ? 1 : (mode == 2 ? 2 : 3)) * TP + HD) * ATT_STRIDE * 2 + (ATT_WARPS + 1) * 64 * sizeof(float);
     static size_t configured = 0;
     if (smem > configured) {
       e = cudaFuncSetAttribute(eff_attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

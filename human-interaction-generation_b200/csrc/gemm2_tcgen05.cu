@@ -216,6 +216,8 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int 
     case EPI_BF16_GELU: return launch_2cta_kind<EPI_BF16_GELU>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
     case EPI_RES_F32: return launch_2cta_kind<EPI_RES_F32>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
     case EPI_RES_F32_BF16: return launch_2cta_kind<EPI_RES_F32_BF16>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
+    case EPI_RES_H: return launch_2cta_kind<EPI_RES_H>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
+    case EPI_RES_H_BF16: return launch_2cta_kind<EPI_RES_H_BF16>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
     default: return launch_2cta_kind<EPI_GENERIC>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
   }
 }

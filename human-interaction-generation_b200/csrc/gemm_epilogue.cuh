@@ -1,5 +1,6 @@
 // Shared epilogue of the tcgen05 GEMM kernels: TMEM -> registers -> swizzled smem slab -> coalesced global I/O.
 #pragma once
+#include <cuda_fp16.h>
 #include "hig_common.cuh"
 
 namespace hig {
@@ -15,7 +16,22 @@ struct GemmEpilogue {
   int ldo_bf16;
   int act;                // 0 none, 1 GELU(erf), 2 SiLU
   int atomic;             // 1: split-K partial -> atomicAdd into out_f32 (generic kind only; no bias/act)
+  // fp16 residual stream (product path): residual16 / out16 replace residual / out_f32 when set
+  const __half* residual16;
+  int ldr16;
+  __half* out16;
+  int ldo16;
 };
+
+// two fp32 -> packed fp16x2 with saturation to +-65504 (no inf in the fp16 residual stream)
+HIG_DEVICE uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+HIG_DEVICE float2 unpack_f16x2(uint32_t u) {
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
 
 HIG_DEVICE void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -48,11 +64,16 @@ static __device__ __noinline__ void epilogue_chunk_scalar(uint32_t slab, GemmEpi
         float x = ld_shared_f1(slab + rl * 128 + ((cg ^ (rl & 7)) << 4) + j * 4);
         if (ep.bias) x += __ldg(ep.bias + col);
         if (ep.residual) x += __ldg(ep.residual + (size_t)rr * ep.ldr + col);
+        if (ep.residual16) x += __half2float(ep.residual16[(size_t)rr * ep.ldr16 + col]);
         if (ep.act == 1) x = gelu_fast_f(x);
         else if (ep.act == 2) x = silu_f(x);
         if (ep.out_f32) {
           if (ep.atomic) atomicAdd(ep.out_f32 + (size_t)row * ep.ldo_f32 + col, x);
           else ep.out_f32[(size_t)row * ep.ldo_f32 + col] = x;
+        }
+        if (ep.out16) {
+          const uint32_t h2 = pack_f16x2_sat(x, 0.f);
+          ep.out16[(size_t)row * ep.ldo16 + col] = *reinterpret_cast<const __half*>(&h2);
         }
         if (ep.out_bf16) ep.out_bf16[(size_t)row * ep.ldo_bf16 + col] = __float2bfloat16(x);
       }
@@ -67,7 +88,9 @@ enum EpiKind : int {
   EPI_BF16 = 1,         // bias -> bf16                       (QKV / Q / FFN linear2 / text KV)
   EPI_BF16_GELU = 2,    // bias -> GELU -> bf16               (FFN linear1)
   EPI_RES_F32 = 3,      // bias + fp32 residual -> fp32       (block output projection, in place on the stream)
-  EPI_RES_F32_BF16 = 4  // ... and a bf16 copy of the stream  (feeds the FFN / output heads)
+  EPI_RES_F32_BF16 = 4, // ... and a bf16 copy of the stream  (feeds the FFN / output heads)
+  EPI_RES_H = 5,        // bias + fp16 residual -> fp16       (product path: the residual stream is stored in fp16)
+  EPI_RES_H_BF16 = 6    // ... and a bf16 copy of the stream
 };
 
 // Epilogue of one 32-row x 32-column fp32 chunk owned by one warp.
@@ -86,6 +109,8 @@ struct EpiLane {
   float* o32;          // element (row_first, cg*4) of each tensor; null when unused
   __nv_bfloat16* o16;
   const float* res;
+  __half* oh;
+  const __half* resh;
 };
 
 HIG_DEVICE void epi_setup(EpiLane& L, uint32_t slab, const GemmEpilogue& ep, int row0, int M, int lane) {
@@ -103,6 +128,8 @@ HIG_DEVICE void epi_setup(EpiLane& L, uint32_t slab, const GemmEpilogue& ep, int
   L.o32 = ep.out_f32 ? ep.out_f32 + r * ep.ldo_f32 + L.cg * 4 : nullptr;
   L.o16 = ep.out_bf16 ? ep.out_bf16 + r * ep.ldo_bf16 + L.cg * 4 : nullptr;
   L.res = ep.residual ? ep.residual + r * ep.ldr + L.cg * 4 : nullptr;
+  L.oh = ep.out16 ? ep.out16 + r * ep.ldo16 + L.cg * 4 : nullptr;
+  L.resh = ep.residual16 ? ep.residual16 + r * ep.ldr16 + L.cg * 4 : nullptr;
 }
 
 template <int KIND>
@@ -145,6 +172,16 @@ HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const EpiLane& L, uint32
 #pragma unroll
       for (int i = 0; i < 8; ++i) { v[i].x += rs[i].x; v[i].y += rs[i].y; v[i].z += rs[i].z; v[i].w += rs[i].w; }
     }
+    if (KIND == EPI_GENERIC && L.resh) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if ((L.row_ok >> i) & 1u) {
+          const uint2 h = __ldg(reinterpret_cast<const uint2*>(L.resh + (size_t)(4 * i) * ep.ldr16 + col0));
+          const float2 a = unpack_f16x2(h.x), b = unpack_f16x2(h.y);
+          v[i].x += a.x; v[i].y += a.y; v[i].z += b.x; v[i].w += b.y;
+        }
+      }
+    }
     const int act = (KIND == EPI_GENERIC) ? ep.act : (KIND == EPI_BF16_GELU ? 1 : 0);
     if (act == 1) {
 #pragma unroll
@@ -162,6 +199,9 @@ HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const EpiLane& L, uint32
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if ((L.row_ok >> i) & 1u) {
+        if (KIND == EPI_GENERIC && L.oh)
+          *reinterpret_cast<uint2*>(L.oh + (size_t)(4 * i) * ep.ldo16 + col0) =
+              make_uint2(pack_f16x2_sat(v[i].x, v[i].y), pack_f16x2_sat(v[i].z, v[i].w));
         if (w32) {
           float* o = L.o32 + (size_t)(4 * i) * ep.ldo_f32 + col0;
           if (KIND == EPI_GENERIC && ep.atomic) {
@@ -184,18 +224,27 @@ HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const EpiLane& L, uint32
 // ---- split form used by the specialised kinds: global loads one chunk ahead of the accumulator ----------------
 struct EpiPre {
   float4 bias4;
-  float4 rs[8];
+  float4 rs[8];   // fp32 residual kinds; the fp16 kinds keep the raw 8-byte loads in rs[i].x / .y
 };
 
 template <int KIND>
 HIG_DEVICE void epi_prefetch(EpiPre& P, const EpiLane& L, const GemmEpilogue& ep, int col0) {
   P.bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + L.cg * 4));
-  if (KIND >= EPI_RES_F32) {
+  if (KIND == EPI_RES_F32 || KIND == EPI_RES_F32_BF16) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       P.rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if ((L.row_ok >> i) & 1u)
         P.rs[i] = __ldg(reinterpret_cast<const float4*>(L.res + (size_t)(4 * i) * ep.ldr + col0));
+    }
+  }
+  if (KIND == EPI_RES_H || KIND == EPI_RES_H_BF16) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint2 h = make_uint2(0u, 0u);
+      if ((L.row_ok >> i) & 1u) h = __ldg(reinterpret_cast<const uint2*>(L.resh + (size_t)(4 * i) * ep.ldr16 + col0));
+      P.rs[i].x = __uint_as_float(h.x);
+      P.rs[i].y = __uint_as_float(h.y);
     }
   }
 }
@@ -213,7 +262,13 @@ HIG_DEVICE void epi_finish(const uint32_t (&r)[32], const EpiPre& P, const EpiLa
   for (int i = 0; i < 8; ++i) {
     v[i] = ld_shared_f4(L.slab_ld[i & 1] + i * 512);
     v[i].x += P.bias4.x; v[i].y += P.bias4.y; v[i].z += P.bias4.z; v[i].w += P.bias4.w;
-    if (KIND >= EPI_RES_F32) { v[i].x += P.rs[i].x; v[i].y += P.rs[i].y; v[i].z += P.rs[i].z; v[i].w += P.rs[i].w; }
+    if (KIND == EPI_RES_F32 || KIND == EPI_RES_F32_BF16) {
+      v[i].x += P.rs[i].x; v[i].y += P.rs[i].y; v[i].z += P.rs[i].z; v[i].w += P.rs[i].w;
+    }
+    if (KIND == EPI_RES_H || KIND == EPI_RES_H_BF16) {
+      const float2 a = unpack_f16x2(__float_as_uint(P.rs[i].x)), b = unpack_f16x2(__float_as_uint(P.rs[i].y));
+      v[i].x += a.x; v[i].y += a.y; v[i].z += b.x; v[i].w += b.y;
+    }
     if (KIND == EPI_BF16_GELU) {
       v[i].x = gelu_fast_f(v[i].x); v[i].y = gelu_fast_f(v[i].y); v[i].z = gelu_fast_f(v[i].z); v[i].w = gelu_fast_f(v[i].w);
     }
@@ -221,8 +276,12 @@ HIG_DEVICE void epi_finish(const uint32_t (&r)[32], const EpiPre& P, const EpiLa
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     if ((L.row_ok >> i) & 1u) {
-      if (KIND >= EPI_RES_F32) *reinterpret_cast<float4*>(L.o32 + (size_t)(4 * i) * ep.ldo_f32 + col0) = v[i];
-      if (KIND != EPI_RES_F32)
+      if (KIND == EPI_RES_F32 || KIND == EPI_RES_F32_BF16)
+        *reinterpret_cast<float4*>(L.o32 + (size_t)(4 * i) * ep.ldo_f32 + col0) = v[i];
+      if (KIND == EPI_RES_H || KIND == EPI_RES_H_BF16)
+        *reinterpret_cast<uint2*>(L.oh + (size_t)(4 * i) * ep.ldo16 + col0) =
+            make_uint2(pack_f16x2_sat(v[i].x, v[i].y), pack_f16x2_sat(v[i].z, v[i].w));
+      if (KIND != EPI_RES_F32 && KIND != EPI_RES_H)
         *reinterpret_cast<uint2*>(L.o16 + (size_t)(4 * i) * ep.ldo_bf16 + col0) =
             make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
     }
@@ -233,6 +292,11 @@ HIG_DEVICE void epi_finish(const uint32_t (&r)[32], const EpiPre& P, const EpiLa
 // classify a runtime epilogue into the specialised kinds (host side)
 inline int classify_epilogue(const GemmEpilogue& ep, int vec_ok, int N) {
   if (!vec_ok || (N % 32) != 0 || !ep.bias || ep.res_row_mod > 0 || ep.atomic) return EPI_GENERIC;
+  if (ep.residual16 || ep.out16) {
+    if (ep.residual16 && ep.out16 && !ep.residual && !ep.out_f32 && ep.act == 0)
+      return ep.out_bf16 ? EPI_RES_H_BF16 : EPI_RES_H;
+    return EPI_GENERIC;
+  }
   if (!ep.residual && !ep.out_f32 && ep.out_bf16) {
     if (ep.act == 0) return EPI_BF16;
     if (ep.act == 1) return EPI_BF16_GELU;

@@ -290,9 +290,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
 // GEMMs, whose output is a handful of tiles while K = tokens is long.  split_k > 0 forces that many slices.
 static int gemm_bf16_impl(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                           const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, void* out_bf16,
-                          int ldo_bf16, int act, int split_k, cudaStream_t stream) {
+                          int ldo_bf16, int act, int split_k, cudaStream_t stream, const void* residual16 = nullptr,
+                          int ldr16 = 0, void* out16 = nullptr, int ldo16 = 0) {
   if (!A || !W || M <= 0 || N <= 0 || K <= 0) return set_error(HIG_ERR_INVALID, "gemm: null operand or empty shape");
-  if (!out_f32 && !out_bf16) return set_error(HIG_ERR_INVALID, "gemm: no output");
+  if (!out_f32 && !out_bf16 && !out16) return set_error(HIG_ERR_INVALID, "gemm: no output");
   if ((lda % 8) || (ldw % 8)) return set_error(HIG_ERR_INVALID, "gemm: lda/ldw must be multiples of 8 (TMA 16B rule)");
   if (split_k && (bias || residual || out_bf16 || act != 0 || !out_f32))
     return set_error(HIG_ERR_INVALID, "gemm: split-K accumulates raw products into out_f32 only");
@@ -306,12 +307,16 @@ static int gemm_bf16_impl(const void* A, int lda, const void* W, int ldw, int M,
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); ep.ldo_bf16 = ldo_bf16;
   ep.act = act;
   ep.atomic = split_k ? 1 : 0;
+  ep.residual16 = reinterpret_cast<const __half*>(residual16); ep.ldr16 = ldr16;
+  ep.out16 = reinterpret_cast<__half*>(out16); ep.ldo16 = ldo16;
 
   int vec_ok = 1;
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) vec_ok = 0;
   if (residual && ((reinterpret_cast<uintptr_t>(residual) & 15) || (ldr % 4))) vec_ok = 0;
   if (out_f32 && ((reinterpret_cast<uintptr_t>(out_f32) & 15) || (ldo_f32 % 4))) vec_ok = 0;
   if (out_bf16 && ((reinterpret_cast<uintptr_t>(out_bf16) & 7) || (ldo_bf16 % 4))) vec_ok = 0;
+  if (residual16 && ((reinterpret_cast<uintptr_t>(residual16) & 7) || (ldr16 % 4))) vec_ok = 0;
+  if (out16 && ((reinterpret_cast<uintptr_t>(out16) & 7) || (ldo16 % 4))) vec_ok = 0;
 
   CUtensorMap tmA, tmB;
   // CTA-pair kernel (256 x 256 tiles, cta_group::2) for the large projections; HIG_GEMM_2CTA=0 disables it
@@ -349,6 +354,19 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
               int ldo_bf16, int act, cudaStream_t stream) {
   return gemm_bf16_impl(A, lda, W, ldw, M, N, K, bias, residual, ldr, res_row_mod, out_f32, ldo_f32, out_bf16, ldo_bf16,
                         act, 0, stream);
+}
+
+// fp16 residual-stream variant: residual / out may each be fp32 (dtype HIG_F32) or fp16 (HIG_F16)
+int gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                 const void* residual, int res_dtype, int ldr, int res_row_mod, void* out, int out_dtype, int ldo,
+                 void* out_bf16, int ldo_bf16, int act, cudaStream_t stream) {
+  const bool r16 = residual && res_dtype == HIG_F16, o16 = out && out_dtype == HIG_F16;
+  if (residual && res_dtype != HIG_F16 && res_dtype != HIG_F32) return set_error(HIG_ERR_INVALID, "gemm: residual dtype");
+  if (out && out_dtype != HIG_F16 && out_dtype != HIG_F32) return set_error(HIG_ERR_INVALID, "gemm: out dtype");
+  if (r16 && res_row_mod > 0) return set_error(HIG_ERR_UNSUPPORTED, "gemm: row-modulo residual tables are fp32");
+  return gemm_bf16_impl(A, lda, W, ldw, M, N, K, bias, r16 ? nullptr : static_cast<const float*>(residual), ldr,
+                        res_row_mod, o16 ? nullptr : static_cast<float*>(out), ldo, out_bf16, ldo_bf16, act, 0, stream,
+                        r16 ? residual : nullptr, ldr, o16 ? out : nullptr, ldo);
 }
 
 int gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32, int ldo_f32,

@@ -15,6 +15,10 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
               const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, void* out_bf16,
               int ldo_bf16, int act, cudaStream_t stream);
 
+int gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                 const void* residual, int res_dtype, int ldr, int res_row_mod, void* out, int out_dtype, int ldo,
+                 void* out_bf16, int ldo_bf16, int act, cudaStream_t stream);
+
 int gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const float* bias,
              const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, int act,
              cudaStream_t stream);
@@ -38,6 +42,10 @@ int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const 
 
 int q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac, const float* sqrt_1mac,
              int S, int TC, float* out, cudaStream_t stream);
+
+int attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
+                       const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
+                       cudaStream_t stream);
 
 // ---- training path (bwd_ops.cu, eff_attn_bwd.cu, gemm_tcgen05.cu) ----
 int gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32, int ldo_f32,

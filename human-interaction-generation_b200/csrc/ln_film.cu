@@ -9,6 +9,7 @@
 // contiguous elements per 256-wide chunk, so loads are 2x float4 (fp32 in) or 1x uint4 (bf16 in), stores 16 B.
 // Statistics are two-pass in registers (mean, then centred variance) in fp32, eps = 1e-5, biased variance —
 // the same arithmetic as ATen's native_layer_norm.
+#include <cuda_fp16.h>
 #include "hig_common.cuh"
 #include "hig_internal.h"
 
@@ -24,6 +25,18 @@ template <> struct Io<float> {
   static HIG_DEVICE void store8(float* p, const float (&v)[8]) {
     reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
     reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Io<__half> {
+  static HIG_DEVICE void load8(const __half* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
   }
 };
 template <> struct Io<__nv_bfloat16> {
@@ -184,6 +197,7 @@ int ln_film_silu(const void* x, int x_dtype, int rows, int width, int rows_per_s
   launch_ln<W, TI, TO>(x, rows, rows_per_seq, gamma, beta, scale_shift, ss_stride, apply_silu, out, stream)
   if (width == 512) {
     if (x_dtype == HIG_F32 && out_dtype == HIG_BF16) HIG_LN_CASE(512, float, bf);
+    else if (x_dtype == HIG_F16 && out_dtype == HIG_BF16) HIG_LN_CASE(512, __half, bf);
     else if (x_dtype == HIG_BF16 && out_dtype == HIG_BF16) HIG_LN_CASE(512, bf, bf);
     else if (x_dtype == HIG_F32 && out_dtype == HIG_F32) HIG_LN_CASE(512, float, float);
     else return set_error(HIG_ERR_UNSUPPORTED, "ln_film_silu: dtype combination");

@@ -7,11 +7,13 @@ the path: torch only allocates the buffers.  The whole schedule is capturable in
 no host sync, tensor maps are kernel parameters) — gaussian_diffusion.p_sample_loop does exactly that.
 
 HBM layout for S sequences x T frames (tok = S*T rows, D = 512):
-  xres  fp32 [tok, 512]   residual stream (kept fp32: 32 residual adds per step would cost ~0.6% in bf16)
+  xres  fp16 [tok, 512]   residual stream (fp16: half the out-proj epilogue traffic of fp32; bf16 would cost 8e-3
+                          relative error per step over its 32 rounded adds, fp16 costs 1e-3; fp32 in fp32 mode)
   xb    act  [tok, 512]   copy of the residual stream in the GEMM operand type (FFN / output heads read it)
   n     act  [tok, 512]   LayerNorm output feeding the Q/K/V projections
   qkv   act  [tok, 1536]  projections (Q | K | V), also reused as [tok, 512] for the text-CA query
-  y     act  [tok, 512]   attention / FFN branch output
+  y     act  [tok, 512]   FFN branch output (fp32 mode: also the attention output)
+  a_blk act  [S, 8, 64, 64] softmax_time(K)^T V of the current attention block (8 MB: L2-resident hand-off)
   sact  act  [tok, 512]   SiLU(FiLM(LN(y))) feeding the block's output projection
   g     act  [tok, 1024]  GELU(linear1)
   ss    fp32 [S, 4L*1024] (scale | shift) of every StylizationBlock, one GEMM per step
@@ -35,6 +37,9 @@ class DenoiserEngine:
         self.m = module
         self.precision = precision
         self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        # residual stream storage: fp16 on the product path (saturating stores; 1e-3 relative per step (CPU experiment),
+        # against 8e-3 for bf16 — the stream takes 32 rounded adds per step), fp32 in fp32 mode
+        self.res_dtype = torch.float16 if precision == "bf16" else torch.float32
         self.D = module.latent_dim
         self.F = module.ff_size
         self.E = module.time_embed_dim
@@ -149,12 +154,13 @@ class DenoiserEngine:
         e = lambda *shape, dtype=dt: torch.empty(*shape, device=dev, dtype=dtype)
         ws = {
             "xa": torch.zeros(tok, self.CP, device=dev, dtype=dt),
-            "xres": e(tok, D, dtype=torch.float32), "xb": e(tok, D), "n": e(tok, D), "qkv": e(tok, 3 * D),
+            "xres": e(tok, D, dtype=self.res_dtype), "xb": e(tok, D), "n": e(tok, D), "qkv": e(tok, 3 * D),
             "y": e(tok, D), "sact": e(tok, D), "g": e(tok, self.F),
             "temb": e(S, D), "te_h": e(S, self.E), "semb": e(S, self.E),
             "ss": e(S, n_styl * 2 * D, dtype=torch.float32),
             "eps": e(tok, self.LD_EPS, dtype=torch.float32),
             "len": torch.empty(S, device=dev, dtype=torch.int32),
+            "a_blk": e(S, self.H, HEAD_DIM, HEAD_DIM),
         }
         if self.precision == "fp32":
             ws["xb"] = ws["xres"]            # fp32 mode: the operand copy IS the residual stream
@@ -217,17 +223,45 @@ class DenoiserEngine:
         self._gemm(ws["te_h"], W["te2.w"], W["te2.b"], out=ws["semb"], residual=xf_proj, act=ops.ACT_SILU)
         self._gemm(ws["semb"], W["emb.w"], W["emb.b"], out_f32=ws["ss"])
 
-    def _stylize_and_project(self, ws, W, p, T, write_xb):
-        D = self.D
-        i = W[p + ".ss"]
-        ss = ws["ss"][:, i * 2 * D:(i + 1) * 2 * D]
-        ops.ln_film_silu(ws["y"], W[p + ".po.ln.w"], W[p + ".po.ln.b"], ws["sact"], rows_per_seq=T, scale_shift=ss,
-                         silu=True)
+    def _project(self, ws, W, p, write_xb):
+        """x += out_layers(sact)  (StylizationBlock's Linear, :92-97, and the block's residual add)."""
         self._gemm(ws["sact"], W[p + ".po.w"], W[p + ".po.b"], residual=ws["xres"], out_f32=ws["xres"],
                    out=ws["xb"] if write_xb else None)
 
+    def _ss(self, ws, W, p):
+        i = W[p + ".ss"]
+        return ws["ss"][:, i * 2 * self.D:(i + 1) * 2 * self.D]
+
+    def _stylize_and_project(self, ws, W, p, T, write_xb):
+        ops.ln_film_silu(ws["y"], W[p + ".po.ln.w"], W[p + ".po.ln.b"], ws["sact"], rows_per_seq=T,
+                         scale_shift=self._ss(ws, W, p), silu=True)
+        self._project(ws, W, p, write_xb)
+
+    def _attend(self, ws, W, p, S, T, q, k=None, v=None, a_in=None, pair_shift=0, mask_v=True):
+        """Attention output -> SiLU(FiLM(LN(.))) in ws['sact'].
+        bf16: K/V half (A = softmax_time(K)^T V, 8 MB, stays in L2) then the fused query half + stylization front end:
+        the attention output never reaches HBM.  fp32 mode: the unfused validation kernels."""
+        H = self.H
+        if self.precision == "bf16":
+            if a_in is None:
+                a_in = ws["a_blk"]
+                ops.eff_attn(ops.ATTN_KV_ONLY, S, T, H, k=k, v=v, a_out=a_in, length=ws["len"], pair_shift=pair_shift,
+                             mask_v=mask_v)
+            ops.attn_apply_stylize(q, a_in, W[p + ".po.ln.w"], W[p + ".po.ln.b"], ws["sact"], S, T, H,
+                                   scale_shift=self._ss(ws, W, p), silu=True)
+            return
+        if a_in is not None:
+            ops.eff_attn(ops.ATTN_Q_ONLY, S, T, H, q=q, a_in=a_in, y=ws["y"])
+        elif pair_shift:
+            ops.eff_attn(ops.ATTN_INTER, S, T, H, q=q, k=k, v=v, y=ws["y"], length=ws["len"], pair_shift=pair_shift,
+                         mask_v=False)
+        else:
+            ops.eff_attn(ops.ATTN_SELF, S, T, H, q=q, k=k, v=v, y=ws["y"], length=ws["len"], mask_v=True)
+        ops.ln_film_silu(ws["y"], W[p + ".po.ln.w"], W[p + ".po.ln.b"], ws["sact"], rows_per_seq=T,
+                         scale_shift=self._ss(ws, W, p), silu=True)
+
     def layers(self, ws, a_text, S, T):
-        W, D, H = self.packed(), self.D, self.H
+        W, D = self.packed(), self.D
         qkv = ws["qkv"]
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         tok = S * T
@@ -237,20 +271,19 @@ class DenoiserEngine:
             # --- self attention (:112-130)
             ops.ln_film_silu(ws["xres"], W[p + "sa.ln.w"], W[p + "sa.ln.b"], ws["n"])
             self._gemm(ws["n"], W[p + "sa.qkv.w"], W[p + "sa.qkv.b"], out=qkv)
-            ops.eff_attn(ops.ATTN_SELF, S, T, H, q=q, k=k, v=v, y=ws["y"], length=ws["len"], mask_v=True)
-            self._stylize_and_project(ws, W, p + "sa", T, False)
+            self._attend(ws, W, p + "sa", S, T, q, k, v, mask_v=True)
+            self._project(ws, W, p + "sa", False)
             # --- text cross attention (:145-165), K/V side precomputed in text_state()
             ops.ln_film_silu(ws["xres"], W[p + "ca.ln.w"], W[p + "ca.ln.b"], ws["n"])
             self._gemm(ws["n"], W[p + "ca.q.w"], W[p + "ca.q.b"], out=q_ca)
-            ops.eff_attn(ops.ATTN_Q_ONLY, S, T, H, q=q_ca, a_in=a_text[li], y=ws["y"])
-            self._stylize_and_project(ws, W, p + "ca", T, not self.has_ic)
+            self._attend(ws, W, p + "ca", S, T, q_ca, a_in=a_text[li])
+            self._project(ws, W, p + "ca", not self.has_ic)
             # --- inter-person cross attention (:181-207): K,V of the partner, mask of the query side
             if self.has_ic:
                 ops.ln_film_silu(ws["xres"], W[p + "ic.ln.w"], W[p + "ic.ln.b"], ws["n"])
                 self._gemm(ws["n"], W[p + "ic.qkv.w"], W[p + "ic.qkv.b"], out=qkv)
-                ops.eff_attn(ops.ATTN_INTER, S, T, H, q=q, k=k, v=v, y=ws["y"], length=ws["len"],
-                             pair_shift=S // 2, mask_v=False)
-                self._stylize_and_project(ws, W, p + "ic", T, True)
+                self._attend(ws, W, p + "ic", S, T, q, k, v, pair_shift=S // 2, mask_v=False)
+                self._project(ws, W, p + "ic", True)
             # --- FFN (:261-264): no pre-norm, exact GELU fused in the linear1 epilogue
             self._gemm(ws["xb"], W[p + "ffn.w1"], W[p + "ffn.b1"], out=ws["g"], act=ops.ACT_GELU)
             self._gemm(ws["g"], W[p + "ffn.w2"], W[p + "ffn.b2"], out=ws["y"])

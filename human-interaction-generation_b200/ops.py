@@ -6,7 +6,7 @@ import torch
 
 from . import _lib
 
-BF16, F32 = 0, 1
+BF16, F32, F16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
 ATTN_SELF, ATTN_INTER, ATTN_KV_ONLY, ATTN_Q_ONLY = 0, 1, 2, 3
 
@@ -16,6 +16,8 @@ def _dt(t):
         return BF16
     if t.dtype == torch.float32:
         return F32
+    if t.dtype == torch.float16:
+        return F16
     raise TypeError(f"hig_b200: unsupported dtype {t.dtype}")
 
 
@@ -46,10 +48,23 @@ def gemm(a, w, bias=None, residual=None, res_row_mod=0, out_f32=None, out_bf16=N
     if w.shape[1] != K:
         raise ValueError("hig_b200.gemm: K mismatch")
     ldr = _rowmajor(residual, "residual") if residual is not None else 0
-    if residual is not None and residual.dtype != torch.float32:
-        raise TypeError("hig_b200.gemm: residual must be fp32")
     if bias is not None and bias.dtype != torch.float32:
         raise TypeError("hig_b200.gemm: bias must be fp32")
+    half = (residual is not None and residual.dtype == torch.float16) or \
+        (out_f32 is not None and out_f32.dtype == torch.float16)
+    if half:
+        # fp16 residual stream (product path): `out_f32` carries the main (stream) output whatever its dtype
+        if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+            raise TypeError("hig_b200.gemm: the fp16 residual stream belongs to the bf16 path")
+        rc = lib.hig_gemm_bf16_ex(_ptr(a), lda, _ptr(w), ldw, M, N, K, _ptr(bias), _ptr(residual),
+                                  _dt(residual) if residual is not None else F32, ldr, res_row_mod, _ptr(out_f32),
+                                  _dt(out_f32) if out_f32 is not None else F32,
+                                  _rowmajor(out_f32, "out") if out_f32 is not None else 0, _ptr(out_bf16),
+                                  _rowmajor(out_bf16, "out_bf16") if out_bf16 is not None else 0, act, _stream())
+        _lib.check(rc, "hig_gemm_bf16_ex")
+        return out_f32 if out_bf16 is None else (out_bf16 if out_f32 is None else (out_f32, out_bf16))
+    if residual is not None and residual.dtype != torch.float32:
+        raise TypeError("hig_b200.gemm: residual must be fp32 or fp16")
     if a.dtype == torch.bfloat16:
         if w.dtype != torch.bfloat16:
             raise TypeError("hig_b200.gemm: A/W dtype mismatch")
@@ -107,6 +122,24 @@ def eff_attn(mode, S, T, H, q=None, k=None, v=None, a_in=None, a_out=None, y=Non
                           _ptr(length), S, T, H, pair_shift, 1 if mask_v else 0, dt, _stream())
     _lib.check(rc, "hig_eff_attn")
     return y if y is not None else a_out
+
+
+def attn_apply_stylize(q, a_in, gamma, beta, out, S, T, H, scale_shift=None, silu=True):
+    """out = [SiLU](LN(concat_h softmax_feat(q_h) @ a_in[s,h]) * (1 + scale) + shift), bf16; q is a [S*T, ld] view."""
+    lib = _lib.load()
+    if q.dtype != torch.bfloat16 or a_in.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        raise TypeError("hig_b200.attn_apply_stylize: bf16 storage only (fp32 mode uses eff_attn + ln_film_silu)")
+    if not out.is_contiguous() or not a_in.is_contiguous():
+        raise ValueError("hig_b200.attn_apply_stylize: contiguous out / a_in required")
+    ss_stride = 0
+    if scale_shift is not None:
+        if scale_shift.dtype != torch.float32 or scale_shift.stride(1) != 1:
+            raise ValueError("hig_b200.attn_apply_stylize: scale_shift must be fp32 with unit inner stride")
+        ss_stride = scale_shift.stride(0)
+    rc = lib.hig_attn_apply_stylize(_ptr(q), q.stride(0), _ptr(a_in), _ptr(gamma), _ptr(beta), _ptr(scale_shift),
+                                    ss_stride, 1 if silu else 0, _ptr(out), S, T, H, _stream())
+    _lib.check(rc, "hig_attn_apply_stylize")
+    return out
 
 
 def timestep_embed(t, freqs, out):

@@ -23,6 +23,7 @@ extern "C" {
 
 #define HIG_BF16 0
 #define HIG_F32 1
+#define HIG_F16 2 /* residual-stream storage of the product path (11-bit mantissa; saturating stores) */
 
 #define HIG_ACT_NONE 0
 #define HIG_ACT_GELU 1 /* exact erf GELU, nn.GELU() */
@@ -53,6 +54,13 @@ int hig_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, 
                   const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, void* out_bf16,
                   int ldo_bf16, int act, void* stream);
 
+/* hig_gemm_bf16 with typed residual / main output: each HIG_F32 or HIG_F16.  The product path keeps the residual
+ * stream `x = x + proj_out(...)` (:129,164,203,263) in fp16 — half the epilogue traffic of fp32 at 8x the
+ * precision of bf16 (measured: fp16 storage costs 1e-3 relative error per denoiser step, bf16 8e-3). */
+int hig_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                     const void* residual, int res_dtype, int ldr, int res_row_mod, void* out, int out_dtype, int ldo,
+                     void* out_bf16, int ldo_bf16, int act, void* stream);
+
 /* the same contract in fp32 storage and fp32 FFMA arithmetic ("fp32 mode", parity <= 1e-5) */
 int hig_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const float* bias,
                  const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, int act, void* stream);
@@ -72,6 +80,15 @@ int hig_ln_film_silu(const void* x, int x_dtype, int rows, int width, int rows_p
 int hig_eff_attn(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
                  void* a_out, void* y, int ldy, const int* length, int S, int T, int H, int pair_shift, int mask_v,
                  int dtype, void* stream);
+
+/* Query half of the efficient attention fused with the block's StylizationBlock front end, bf16 storage:
+ *   out[t,:] = SiLU( LN_512( concat_h softmax_feat(Q[t,h]) . A[s,h] ) * (1 + scale_s) + shift_s )
+ * (einsum + reshape at models/interaction_transformer.py:128,162,201, then StylizationBlock.forward :86-97 up to its
+ * SiLU).  q [S*T, ldq] at head 0, a_in [S,8,64,64] from hig_eff_attn KV_ONLY (which honours `length` and
+ * `pair_shift`: the K/V half of the self / inter-person attention), scale_shift as in hig_ln_film_silu, out [S*T,512]. */
+int hig_attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
+                           const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
+                           void* stream);
 
 /* out[s] = [cos(t_s f) | sin(t_s f)] — timestep_embedding (models/interaction_transformer.py:26-43);
  * freqs = fp32 [half] table computed once on the host exactly as the reference does. */

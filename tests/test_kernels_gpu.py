@@ -217,6 +217,48 @@ def test_eff_attn_pad_garbage_invariance(cuda):
     assert torch.equal(y1, y2)
 
 
+@pytest.mark.parametrize("S,T", [(4, 196), (6, 33), (2, 16), (2, 1), (128, 91)])
+@pytest.mark.parametrize("mode", ["self", "inter"])
+def test_attn_kv_then_fused_apply_stylize(cuda, S, T, mode):
+    """Product (bf16) attention path: KV_ONLY with length mask / pair shift -> A, then the fused query half +
+    LayerNorm + FiLM + SiLU, against the fp32 reference formulation of the whole chain (:112-130 / :181-207, :86-97)."""
+    ops = _ops()
+    H, D = 8, 512
+    g = torch.Generator(device=cuda).manual_seed(S * 1000 + T)
+    qkv = (torch.randn(S * T, 3 * D, device=cuda, generator=g) * 1.5).bfloat16()
+    lens = torch.randint(1, T + 1, (S,), device=cuda, generator=g, dtype=torch.int32)
+    lens[0] = T
+    mask = (torch.arange(T, device=cuda)[None] < lens[:, None]).float()
+    gamma = 1 + 0.1 * torch.randn(D, device=cuda, generator=g)
+    beta = 0.1 * torch.randn(D, device=cuda, generator=g)
+    ss_all = 0.5 * torch.randn(S, 4 * 2 * D, device=cuda, generator=g)
+    ss = ss_all[:, 2 * D:4 * D]          # a slab of a wider (scale | shift) buffer, as in the engine
+    q, k, v = [qkv[:, i * D:(i + 1) * D].float().view(S, T, H, 64) for i in range(3)]
+    B = S // 2
+    if mode == "inter":
+        perm = torch.cat([torch.arange(B, S), torch.arange(0, B)]).to(cuda)
+        y_ref, a_ref = _attn_ref(q, k[perm], v[perm], mask, torch.ones_like(mask))
+    else:
+        y_ref, a_ref = _attn_ref(q, k, v, mask, mask)
+    h = F.layer_norm(y_ref.reshape(S, T, D), (D,), gamma, beta, 1e-5)
+    ref = F.silu(h * (1 + ss[:, None, :D]) + ss[:, None, D:]).reshape(S * T, D)
+    a = torch.empty(S, H, 64, 64, device=cuda, dtype=torch.bfloat16)
+    ops.eff_attn(ops.ATTN_KV_ONLY, S, T, H, k=qkv[:, D:2 * D], v=qkv[:, 2 * D:], a_out=a, length=lens,
+                 pair_shift=B if mode == "inter" else 0, mask_v=(mode == "self"))
+    assert _rel(a.float(), a_ref) < 1e-2
+    out = torch.full((S * T, D), float("nan"), device=cuda, dtype=torch.bfloat16)
+    ops.attn_apply_stylize(qkv[:, :D], a, gamma, beta, out, S, T, H, scale_shift=ss, silu=True)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out.float(), ref) < 1.5e-2
+    # the unfused kernels compute the same thing: the two product paths agree to bf16 rounding
+    y = torch.empty(S * T, D, device=cuda, dtype=torch.bfloat16)
+    ops.eff_attn(ops.ATTN_INTER if mode == "inter" else ops.ATTN_SELF, S, T, H, q=qkv[:, :D], k=qkv[:, D:2 * D],
+                 v=qkv[:, 2 * D:], y=y, length=lens, pair_shift=B if mode == "inter" else 0, mask_v=(mode == "self"))
+    o2 = torch.empty_like(out)
+    ops.ln_film_silu(y, gamma, beta, o2, rows_per_seq=T, scale_shift=ss, silu=True)
+    assert _rel(out.float(), o2.float()) < 1.5e-2
+
+
 # ------------------------------------------------------------------------------------------------ diffusion ops
 def test_timestep_embed_and_pack(cuda):
     ops = _ops()

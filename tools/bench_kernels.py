@@ -90,6 +90,12 @@ def main():
     qb = qkv[:, :D].contiguous()
     t = timeit(lambda: ops.eff_attn(ops.ATTN_Q_ONLY, S, T, 8, q=qb, a_in=a_t, y=y))
     res["attn_text_apply"] = {"us": t * 1e6, "gbs": (tok * D * 4 + a_t.numel() * 2) / t / 1e9}
+    a_blk = torch.empty(S, 8, 64, 64, device=dev, dtype=torch.bfloat16)
+    t = timeit(lambda: ops.eff_attn(ops.ATTN_KV_ONLY, S, T, 8, k=qkv[:, D:2 * D], v=qkv[:, 2 * D:], a_out=a_blk,
+                                    length=lens))
+    res["attn_kv_only"] = {"us": t * 1e6, "gbs": (tok * D * 4 + a_blk.numel() * 2) / t / 1e9}
+    t = timeit(lambda: ops.attn_apply_stylize(qkv[:, :D], a_blk, g, b, ob, S, T, 8, scale_shift=ss, silu=True))
+    res["attn_apply_stylize"] = {"us": t * 1e6, "gbs": (tok * D * 4 + a_blk.numel() * 2) / t / 1e9}
     print(json.dumps(res, indent=1))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/bench_kernels.json", "w"), indent=1)
