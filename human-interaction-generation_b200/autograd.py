@@ -254,6 +254,7 @@ class _Bwd:
         self.dt = st.eng.act_dtype
         self.dev = st.eps.device
         self.bf16 = st.eng.precision == "bf16"
+        self._zero_bias = st.eng.__dict__.setdefault("_zero_bias", {})
 
     def new(self, *shape, dtype=None):
         return torch.empty(*shape, device=self.dev, dtype=dtype or self.dt)
@@ -267,8 +268,13 @@ class _Bwd:
         return (xt[:, :M] if want_t else None), cp
 
     def dgrad(self, dy, wT, out=None, out_f32=None, accumulate=False):
-        """dx[M,K] (+)= dy[M,N] . W[N,K]   (wT = W^T [K,N] packed in the operand dtype)."""
-        self.eng._gemm(dy, wT, None, out=out, out_f32=out_f32, residual=out_f32 if accumulate else None)
+        """dx[M,K] (+)= dy[M,N] . W[N,K]   (wT = W^T [K,N] packed in the operand dtype).  A zero bias vector keeps the
+        GEMM on its specialised coalesced epilogues."""
+        n = wT.shape[0]
+        zb = self._zero_bias.get(n)
+        if zb is None:
+            zb = self._zero_bias[n] = torch.zeros(n, device=self.dev, dtype=torch.float32)
+        self.eng._gemm(dy, wT, zb, out=out, out_f32=out_f32, residual=out_f32 if accumulate else None)
 
     def wgrad(self, dyT, xT, w_grad):
         """w_grad[N,K] += dy^T[N,M] . x[M,K]  with dyT [N,M], xT [K,M] (views with 16-byte-aligned leading dims)."""

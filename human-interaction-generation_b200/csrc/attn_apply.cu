@@ -12,6 +12,7 @@
 //
 // CTA = 8 warps, one 16-row tile per iteration; Q tiles are prefetched with cp.async into a per-warp double buffer
 // (XOR-swizzled 128-byte rows, conflict-free ldmatrix); A for the 8 heads sits in shared memory (64 KB, swizzled).
+#include <cstdlib>
 #include "hig_common.cuh"
 #include "hig_internal.h"
 
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(AP_THREADS, 2)
 attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ a_in,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           const float* __restrict__ scale_shift, int ss_stride, int apply_silu,
-                          __nv_bfloat16* __restrict__ out, int T, int tiles_per_cta) {
+                          __nv_bfloat16* __restrict__ out, int S, int T) {
   extern __shared__ __align__(128) uint8_t ap_smem[];
   const uint32_t sA = smem_u32(ap_smem);
   const uint32_t sQ = sA + AP_SMEM_A;
@@ -64,54 +65,59 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
   float* sR2 = sR1 + 16 * 8;         // [16][8]
 
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int s = blockIdx.y;
   const int n_tiles = (T + 15) >> 4;
-  const int tile0 = blockIdx.x * tiles_per_cta;
-  const int tile1 = min(n_tiles, tile0 + tiles_per_cta);
-  if (tile0 >= tile1) return;
+  // balanced static schedule: the S * n_tiles row tiles are cut into gridDim.x contiguous ranges (sizes differ by at
+  // most one tile); a range touches at most two sequences when gridDim.x >= S, so A is (re)loaded at most twice
+  const long long G = (long long)S * n_tiles;
+  const int g_lo = (int)(G * blockIdx.x / gridDim.x), g_hi = (int)(G * (blockIdx.x + 1) / gridDim.x);
+  if (g_lo >= g_hi) return;
 
-  // ---- A of the 8 heads: 8 * 64 rows * 8 chunks of 16 B
-  {
-    const __nv_bfloat16* ag = a_in + (size_t)s * 8 * AP_HD * AP_HD;
-    for (int i = tid; i < 8 * AP_HD * 8; i += AP_THREADS) {
-      const int row = i >> 3, c = i & 7;  // row = h*64 + d
-      ap_cp_async16(sA + ap_swz(row, c), ag + (size_t)row * AP_HD + c * 8, true);
-    }
-  }
-  ap_commit();
-  // ---- this warp's Q tiles: 16 rows x 8 chunks = 128 x 16 B per tile, 4 per lane
   const uint32_t sQw = sQ + w * (2 * 16 * 128);
-  const __nv_bfloat16* qg = q + (size_t)s * T * ldq + w * AP_HD;
-  auto prefetch = [&](int tile, int buf) {
+  // this warp's Q tile of global tile index gi: 16 rows x 8 chunks = 128 x 16 B, 4 per lane
+  auto prefetch = [&](int gi, int buf) {
+    const int ps = gi / n_tiles, ptile = gi - ps * n_tiles;
+    const __nv_bfloat16* qg = q + (size_t)ps * T * ldq + w * AP_HD;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = i * 32 + lane;
       const int r = idx >> 3, c = idx & 7;
-      const int t = tile * 16 + r;
+      const int t = ptile * 16 + r;
       ap_cp_async16(sQw + buf * 2048 + ap_swz(r, c), qg + (size_t)min(t, T - 1) * ldq + c * 8, t < T);
     }
   };
-  prefetch(tile0, 0);
+  prefetch(g_lo, 0);
   ap_commit();
-  // ---- folded FiLM affine: out = n_hat * G + B,  G = gamma (1 + scale),  B = beta (1 + scale) + shift
-  for (int i = tid; i < AP_D; i += AP_THREADS) {
-    float g = gamma[i], b = beta[i];
-    if (scale_shift) {
-      const float m1 = 1.0f + scale_shift[(size_t)s * ss_stride + i];
-      g *= m1;
-      b = fmaf(b, m1, scale_shift[(size_t)s * ss_stride + AP_D + i]);
-    }
-    sG[i] = g;
-    sB[i] = b;
-  }
-  ap_wait<1>();      // A landed (this thread's part)
-  __syncthreads();   // ... everyone's, and sG / sB
 
   const int g = lane >> 2, tg = lane & 3;
   const uint32_t sAw = sA + w * (AP_HD * 128);
-  int buf = 0;
-  for (int tile = tile0; tile < tile1; ++tile, buf ^= 1) {
-    if (tile + 1 < tile1) prefetch(tile + 1, buf ^ 1);
+  int buf = 0, cur_s = -1;
+  for (int gi = g_lo; gi < g_hi; ++gi, buf ^= 1) {
+    const int s = gi / n_tiles, tile = gi - s * n_tiles;
+    if (s != cur_s) {
+      // ---- new sequence: A of its 8 heads (8 * 64 rows * 8 chunks of 16 B) and the folded FiLM affine
+      //      out = n_hat * G + B,  G = gamma (1 + scale),  B = beta (1 + scale) + shift
+      __syncthreads();   // every warp is done with the previous sequence's A / sG / sB
+      const __nv_bfloat16* ag = a_in + (size_t)s * 8 * AP_HD * AP_HD;
+      for (int i = tid; i < 8 * AP_HD * 8; i += AP_THREADS) {
+        const int row = i >> 3, c = i & 7;  // row = h*64 + d
+        ap_cp_async16(sA + ap_swz(row, c), ag + (size_t)row * AP_HD + c * 8, true);
+      }
+      ap_commit();
+      for (int i = tid; i < AP_D; i += AP_THREADS) {
+        float gg = gamma[i], bb = beta[i];
+        if (scale_shift) {
+          const float m1 = 1.0f + scale_shift[(size_t)s * ss_stride + i];
+          gg *= m1;
+          bb = fmaf(bb, m1, scale_shift[(size_t)s * ss_stride + AP_D + i]);
+        }
+        sG[i] = gg;
+        sB[i] = bb;
+      }
+      ap_wait<0>();
+      __syncthreads();
+      cur_s = s;
+    }
+    if (gi + 1 < g_hi) prefetch(gi + 1, buf ^ 1);
     ap_commit();
     ap_wait<1>();
     __syncwarp();
@@ -241,6 +247,146 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
   ap_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// attn_kv_kernel: the K/V half,  A[s,h] = softmax_time(K_masked)^T . (V * mask)   -> bf16 [S,H,64,64]
+// (LinearTemporal*Attention.forward, :121-127 / :155-161 / :194-200).  One CTA per (sequence, head); K and V
+// [T,64] staged with cp.async into unpadded XOR-swizzled shared memory (50 KB at T=196 -> 4 CTAs per SM), the time
+// softmax runs column-wise in fp32 (lane = column pair, warp strides rows), the contraction on mma.sync.  K/V of
+// sequence (s + pair_shift) % S, rows >= length[s] masked (the inter-person block's query-side mask quirk, :194).
+// ------------------------------------------------------------------------------------------------
+constexpr int KV_THREADS = 256;
+constexpr int KV_WARPS = 8;
+
+__global__ void __launch_bounds__(KV_THREADS, 4)
+attn_kv_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int ldkv,
+               __nv_bfloat16* __restrict__ a_out, const int* __restrict__ length, int S, int T, int pair_shift) {
+  extern __shared__ __align__(128) uint8_t kv_smem[];
+  const int TP = (T + 15) & ~15;
+  const uint32_t sK = smem_u32(kv_smem);
+  const uint32_t sV = sK + TP * 128;
+  float* sred = reinterpret_cast<float*>(kv_smem + 2 * TP * 128);  // [KV_WARPS][64]
+  float* sinv = sred + KV_WARPS * 64;                               // [64]
+  const int h = blockIdx.x, s = blockIdx.y, H = gridDim.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s_kv = (s + pair_shift) % S;
+  int len = T;
+  if (length) {
+    len = length[s];
+    len = len < 0 ? 0 : (len > T ? T : len);
+  }
+  const __nv_bfloat16* kg = k + (size_t)s_kv * T * ldkv + h * AP_HD;
+  const __nv_bfloat16* vg = v + (size_t)s_kv * T * ldkv + h * AP_HD;
+  // rows >= len are zero-filled: Ks is forced to 0 there and V*mask == 0 (unmasked V rows meet Ks == 0: same A)
+  for (int i = tid; i < TP * 8; i += KV_THREADS) {
+    const int r = i >> 3, c = i & 7;
+    const bool ok = r < len;
+    const size_t off = (size_t)min(r, T - 1) * ldkv + c * 8;
+    ap_cp_async16(sK + ap_swz(r, c), kg + off, ok);
+    ap_cp_async16(sV + ap_swz(r, c), vg + off, ok);
+  }
+  ap_commit();
+  ap_wait<0>();
+  __syncthreads();
+
+  // ---- time softmax of K: lane owns the 4-byte word `lane` of every row (columns 2*lane, 2*lane+1)
+  auto kword = [&](int t) { return sK + t * 128 + (((lane >> 2) ^ (t & 7)) << 4) + (lane & 3) * 4; };
+  float m0 = -INFINITY, m1 = -INFINITY;
+  for (int t = warp; t < len; t += KV_WARPS) {
+    uint32_t u;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(kword(t)));
+    const float2 f = unpack_bf16x2(u);
+    m0 = fmaxf(m0, f.x);
+    m1 = fmaxf(m1, f.y);
+  }
+  sred[warp * 64 + 2 * lane] = m0;
+  sred[warp * 64 + 2 * lane + 1] = m1;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < KV_WARPS; ++w) {
+    m0 = fmaxf(m0, sred[w * 64 + 2 * lane]);
+    m1 = fmaxf(m1, sred[w * 64 + 2 * lane + 1]);
+  }
+  __syncthreads();
+  float s0 = 0.f, s1 = 0.f;
+  for (int t = warp; t < len; t += KV_WARPS) {
+    uint32_t u;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(kword(t)));
+    const float2 f = unpack_bf16x2(u);
+    // sum what the MMA will see (the bf16-rounded weights) so the normalisation is exact
+    const __nv_bfloat162 e2 = __floats2bfloat162_rn(__expf(f.x - m0), __expf(f.y - m1));
+    const float2 ef = __bfloat1622float2(e2);
+    s0 += ef.x;
+    s1 += ef.y;
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(kword(t)), "r"(*reinterpret_cast<const uint32_t*>(&e2)) : "memory");
+  }
+  sred[warp * 64 + 2 * lane] = s0;
+  sred[warp * 64 + 2 * lane + 1] = s1;
+  __syncthreads();
+  if (tid < 64) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < KV_WARPS; ++w) tot += sred[w * 64 + tid];
+    sinv[tid] = tot > 0.f ? 1.0f / tot : 0.f;
+  }
+  __syncthreads();
+
+  // ---- A[d,l] = sum_t e[t,d] V[t,l] / sum_t e[t,d]: warp -> d in [16*(w&3), +16), l in [32*(w>>2), +32)
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int dw = (warp & 3) * 16, lw = (warp >> 2) * 32;
+  const int kend = (len + 15) & ~15;
+  for (int kt = 0; kt < kend; kt += 16) {
+    uint32_t a[4];
+    {
+      const int row = kt + (lane & 7) + ((lane >> 4) & 1) * 8;
+      const int c = (dw >> 3) + ((lane >> 3) & 1);
+      ap_ldsm_x4_t(sK + ap_swz(row, c), a[0], a[1], a[2], a[3]);
+    }
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b0, b1, b2, b3;
+      const int row = kt + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int c = (lw >> 3) + np * 2 + ((lane >> 4) & 1);
+      ap_ldsm_x4_t(sV + ap_swz(row, c), b0, b1, b2, b3);
+      ap_mma(acc[2 * np], a, b0, b1);
+      ap_mma(acc[2 * np + 1], a, b2, b3);
+    }
+  }
+  const int g = lane >> 2, tg = lane & 3;
+  const float i0 = sinv[dw + g], i1 = sinv[dw + g + 8];
+  __nv_bfloat16* dst = a_out + ((size_t)s * H + h) * AP_HD * AP_HD;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int col = lw + nt * 8 + 2 * tg;
+    *reinterpret_cast<uint32_t*>(dst + (dw + g) * AP_HD + col) = pack_bf16x2(acc[nt][0] * i0, acc[nt][1] * i0);
+    *reinterpret_cast<uint32_t*>(dst + (dw + g + 8) * AP_HD + col) = pack_bf16x2(acc[nt][2] * i1, acc[nt][3] * i1);
+  }
+}
+
+int attn_kv(const void* k, const void* v, int ldkv, void* a_out, const int* length, int S, int T, int H,
+            int pair_shift, cudaStream_t stream) {
+  if (!k || !v || !a_out || S <= 0 || T <= 0 || H <= 0) return set_error(HIG_ERR_INVALID, "attn_kv: bad arguments");
+  if (T > 256) return set_error(HIG_ERR_UNSUPPORTED, "attn_kv: T > 256 not supported");
+  if (ldkv % 8) return set_error(HIG_ERR_INVALID, "attn_kv: ldkv must be a multiple of 8");
+  const int TP = (T + 15) & ~15;
+  const size_t smem = (size_t)2 * TP * 128 + (KV_WARPS + 1) * 64 * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_kv attr: ") + cudaGetErrorString(e));
+    configured = smem;
+  }
+  attn_kv_kernel<<<dim3(H, S), KV_THREADS, smem, stream>>>((const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv,
+                                                          (__nv_bfloat16*)a_out, length, S, T, pair_shift);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_kv launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
 int attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
                        const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
                        cudaStream_t stream) {
@@ -257,16 +403,13 @@ int attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* ga
     attr = true;
   }
   const int n_tiles = (T + 15) / 16;
-  // ~2 CTAs per SM resident at once: split a sequence's tiles over `chunks` CTAs so that S * chunks >= 296
-  int chunks = (2 * 148 + S - 1) / S;
-  if (chunks > n_tiles) chunks = n_tiles;
-  if (chunks < 1) chunks = 1;
-  const int tiles_per_cta = (n_tiles + chunks - 1) / chunks;
-  chunks = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
-  dim3 grid(chunks, S);
-  attn_apply_stylize_kernel<<<grid, AP_THREADS, AP_SMEM, stream>>>(
+  // two resident CTAs per SM, every CTA gets the same number of row tiles (+-1)
+  static const int n_sm = []() { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
+  long long ctas = 2LL * n_sm;
+  if (ctas > (long long)S * n_tiles) ctas = (long long)S * n_tiles;
+  attn_apply_stylize_kernel<<<(int)ctas, AP_THREADS, AP_SMEM, stream>>>(
       (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)a_in, gamma, beta, scale_shift, ss_stride, apply_silu,
-      (__nv_bfloat16*)out, T, tiles_per_cta);
+      (__nv_bfloat16*)out, S, T);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_apply_stylize launch: ") + cudaGetErrorString(e));
   count_launch();

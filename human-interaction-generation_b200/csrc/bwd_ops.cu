@@ -20,6 +20,40 @@ template <typename T> HIG_DEVICE void st_from_f(T* p, float v);
 template <> HIG_DEVICE void st_from_f<float>(float* p, float v) { *p = v; }
 template <> HIG_DEVICE void st_from_f<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
+// 8 contiguous elements <-> fp32 registers with 16-byte (bf16) / 2 x 16-byte (fp32) accesses
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  static HIG_DEVICE void load(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static HIG_DEVICE void load_rw(const float* p, float (&v)[8]) {  // coherent load (buffer also written by this kernel)
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static HIG_DEVICE void store(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  static HIG_DEVICE void unpack(const uint4 u, float (&v)[8]) {
+    float2 f;
+    f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+    f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+    f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+    f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+  }
+  static HIG_DEVICE void load(const __nv_bfloat16* p, float (&v)[8]) { unpack(__ldg(reinterpret_cast<const uint4*>(p)), v); }
+  static HIG_DEVICE void load_rw(const __nv_bfloat16* p, float (&v)[8]) { unpack(*reinterpret_cast<const uint4*>(p), v); }
+  static HIG_DEVICE void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // transpose: in [M,N] (ld_in) -> outT [N,M] (ld_t), optional straight copy in the output type (ld_c) and optional
 // column sums (fp32, atomically accumulated: the caller zeroes them).  64x64 tiles through padded shared memory,
@@ -232,12 +266,15 @@ ln_film_silu_bwd_kernel(const TX* __restrict__ x, int rows, int rows_per_seq, in
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     const int col = c * 256 + lane * 8;
+    Vec8<float>::load(gamma + col, G[c]);
+    Vec8<float>::load(beta + col, Bt[c]);
+    if (scale_shift) {
+      Vec8<float>::load(scale_shift + (size_t)seq * ss_stride + col, SC[c]);
+      Vec8<float>::load(scale_shift + (size_t)seq * ss_stride + WIDTH + col, SH[c]);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      G[c][j] = gamma[col + j];
-      Bt[c][j] = beta[col + j];
-      SC[c][j] = scale_shift ? scale_shift[(size_t)seq * ss_stride + col + j] : 0.f;
-      SH[c][j] = scale_shift ? scale_shift[(size_t)seq * ss_stride + WIDTH + col + j] : 0.f;
+      if (!scale_shift) { SC[c][j] = 0.f; SH[c][j] = 0.f; }
       a_sc[c][j] = a_sh[c][j] = a_g[c][j] = a_b[c][j] = 0.f;
     }
   }
@@ -247,14 +284,13 @@ ln_film_silu_bwd_kernel(const TX* __restrict__ x, int rows, int rows_per_seq, in
     float v[CH][8], g[CH][8];
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < CH; ++c)
+    for (int c = 0; c < CH; ++c) {
+      const size_t idx = (size_t)r * WIDTH + c * 256 + lane * 8;
+      Vec8<TX>::load(x + idx, v[c]);
+      Vec8<TG>::load(dout + idx, g[c]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const size_t idx = (size_t)r * WIDTH + c * 256 + lane * 8 + j;
-        v[c][j] = ld_as_f(x + idx);
-        g[c][j] = ld_as_f(dout + idx);
-        s += v[c][j];
-      }
+      for (int j = 0; j < 8; ++j) s += v[c][j];
+    }
     const float mean = warp_sum(s) * (1.0f / WIDTH);
     float ssq = 0.f;
 #pragma unroll
@@ -292,14 +328,17 @@ ln_film_silu_bwd_kernel(const TX* __restrict__ x, int rows, int rows_per_seq, in
     m1 = warp_sum(m1) * (1.0f / WIDTH);
     m2 = warp_sum(m2) * (1.0f / WIDTH);
 #pragma unroll
-    for (int c = 0; c < CH; ++c)
+    for (int c = 0; c < CH; ++c) {
+      const size_t idx = (size_t)r * WIDTH + c * 256 + lane * 8;
+      float d[8], prev[8];
+      if (dx_accumulate) Vec8<TDX>::load_rw(dx + idx, prev);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const size_t idx = (size_t)r * WIDTH + c * 256 + lane * 8 + j;
-        float d = rstd * (g[c][j] - m1 - v[c][j] * m2);
-        if (dx_accumulate) d += ld_as_f(dx + idx);
-        st_from_f(dx + idx, d);
+        d[j] = rstd * (g[c][j] - m1 - v[c][j] * m2);
+        if (dx_accumulate) d[j] += prev[j];
       }
+      Vec8<TDX>::store(dx + idx, d);
+    }
   }
 #pragma unroll
   for (int c = 0; c < CH; ++c)
@@ -331,6 +370,8 @@ int ln_film_silu_bwd(const void* x, int x_dtype, int rows, int width, int rows_p
   if (!x || !dout || !dx || !gamma || !beta || rows <= 0 || rows_per_seq <= 0)
     return set_error(HIG_ERR_INVALID, "ln_film_silu_bwd: bad arguments");
   if (width != 512 && width != 256) return set_error(HIG_ERR_UNSUPPORTED, "ln_film_silu_bwd: width must be 256 or 512");
+  if (scale_shift && ((ss_stride % 4) || (reinterpret_cast<uintptr_t>(scale_shift) & 15)))
+    return set_error(HIG_ERR_INVALID, "ln_film_silu_bwd: scale_shift must be 16-byte aligned with ss_stride % 4 == 0");
   const int n_seq = (rows + rows_per_seq - 1) / rows_per_seq;
   // enough CTAs to fill the machine: split a sequence's rows over `slices` CTAs when there are few sequences
   int slices = (148 * 2 + n_seq - 1) / n_seq;

@@ -120,20 +120,21 @@ ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, int ld_ep
       if (base + j < total) z[j] = noise[base + j];
   } else {
     // counter = (element-group index, timestep of the first element's sequence), key = seed
-    const int s0 = (int)(base / per_seq);
+    const int s0 = (int)((unsigned)base / (unsigned)per_seq);
     const long long ts = t[s0];
     const uint4 ctr = make_uint4((uint32_t)(base >> 2), (uint32_t)((base >> 2) >> 32), (uint32_t)ts, 0x48494742u);
     const uint4 rnd = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     const float2 n0 = box_muller(rnd.x, rnd.y), n1 = box_muller(rnd.z, rnd.w);
     z[0] = n0.x; z[1] = n0.y; z[2] = n1.x; z[3] = n1.y;
   }
+  // decompose the first element once (32-bit arithmetic: the host guarantees total < 2^31), then step
+  int s = (int)((unsigned)base / (unsigned)per_seq);
+  int rem = (int)((unsigned)base - (unsigned)s * (unsigned)per_seq);
+  int tt = rem / C, c = rem - tt * C;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const long long idx = base + j;
     if (idx >= total) break;
-    const int s = (int)(idx / per_seq);
-    const int rem = (int)(idx - (long long)s * per_seq);
-    const int tt = rem / C, c = rem - tt * C;
     long long ts = t[s];
     ts = ts < 0 ? 0 : (ts >= n_steps ? n_steps - 1 : ts);
     const float r = coef[ts], m = coef[n_steps + ts], c1 = coef[2 * n_steps + ts], c2 = coef[3 * n_steps + ts];
@@ -148,6 +149,10 @@ ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, int ld_ep
       TPack* prow = packed + ((size_t)s * T + tt) * ld_packed;
       if (tt > 0) prow[c] = static_cast<TPack>(xn);
       else if (c < 4) prow[C + c] = static_cast<TPack>(xn);
+    }
+    if (++c == C) {
+      c = 0;
+      if (++tt == T) { tt = 0; ++s; }
     }
   }
 }
@@ -164,6 +169,7 @@ int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const 
     return set_error(HIG_ERR_INVALID, "ddpm_step: bad arguments");
   if (packed && ld_packed < C + 4) return set_error(HIG_ERR_INVALID, "ddpm_step: ld_packed < C+4");
   const long long total = (long long)S * T * C;
+  if (total >= (1LL << 31)) return set_error(HIG_ERR_UNSUPPORTED, "ddpm_step: more than 2^31 elements");
   const int blocks = (int)(((total + 3) / 4 + 255) / 256);
   if (packed && packed_dtype == HIG_BF16)
     ddpm_step_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(x, eps, ld_eps, noise, t, coef, n_steps, S, T, C, seed,

@@ -43,6 +43,9 @@ int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const 
 int q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac, const float* sqrt_1mac,
              int S, int TC, float* out, cudaStream_t stream);
 
+int attn_kv(const void* k, const void* v, int ldkv, void* a_out, const int* length, int S, int T, int H,
+            int pair_shift, cudaStream_t stream);
+
 int attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
                        const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
                        cudaStream_t stream);

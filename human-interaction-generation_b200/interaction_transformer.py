@@ -131,19 +131,56 @@ class MotionInteractionTransformer(nn.Module):
 
     # ------------------------------------------------------------------------------------------ text side (PyTorch)
     def encode_text(self, text, device):
-        """:533-559 — CLIP text transformer -> text_pre_proj -> 4-layer encoder -> text_ln; xf_proj from the EOT token."""
+        """:533-559 — CLIP text transformer -> text_pre_proj -> 4-layer encoder -> text_ln; xf_proj from the EOT token.
+
+        Same values as the reference, less work: every distinct caption is encoded once per call and
+        the result is indexed back to the batch (NTU RGB+D has 43 distinct captions, a training batch 256-512), and
+        the FROZEN CLIP features of a caption are cached across calls (invalidated when a CLIP parameter changes)."""
+        text = list(text)
+        uniq = list(dict.fromkeys(text))
+        feats = self._clip_features(uniq, device)               # [77, U, 512]
+        x = self.text_pre_proj(feats)
+        xf_out = self.text_ln(self.textTransEncoder(x))
+        eot = self._eot_index(uniq, device)
+        xf_proj = self.text_proj(xf_out[eot, torch.arange(xf_out.shape[1], device=device)])
+        xf_out = xf_out.permute(1, 0, 2)
+        if len(uniq) != len(text):
+            where = {c: i for i, c in enumerate(uniq)}
+            idx = torch.tensor([where[c] for c in text], device=device, dtype=torch.long)
+            xf_proj, xf_out = xf_proj.index_select(0, idx), xf_out.index_select(0, idx)
+        return xf_proj, xf_out
+
+    def _eot_index(self, captions, device):
+        return self._tokenize(captions, truncate=True).to(device).argmax(dim=-1)
+
+    def _clip_features(self, captions, device):
+        """clip.ln_final(clip.transformer(token_embedding + positional_embedding)) per caption, LND layout (:536-550)."""
         clip = self.clip
-        ctx = torch.enable_grad() if self.no_clip else torch.no_grad()
-        tokens = self._tokenize(text, truncate=True).to(device)
-        with ctx:
+
+        def run(caps):
+            tokens = self._tokenize(caps, truncate=True).to(device)
             x = clip.token_embedding(tokens).type(clip.dtype)
             x = x + clip.positional_embedding.type(clip.dtype)
             x = clip.transformer(x.permute(1, 0, 2))
-            x = clip.ln_final(x).type(clip.dtype)
-        x = self.text_pre_proj(x)
-        xf_out = self.text_ln(self.textTransEncoder(x))
-        xf_proj = self.text_proj(xf_out[tokens.argmax(dim=-1), torch.arange(xf_out.shape[1])])
-        return xf_proj, xf_out.permute(1, 0, 2)
+            return clip.ln_final(x).type(clip.dtype)
+
+        if self.no_clip:                  # trainable CLIP-shaped encoder: nothing can be cached
+            with torch.enable_grad():
+                return run(captions)
+        key = (str(device), sum(p._version for p in clip.parameters()))
+        if getattr(self, "_clip_cache_key", None) != key:
+            self._clip_cache_key, self._clip_cache = key, {}
+        cache = self._clip_cache
+        missing = [c for c in captions if c not in cache]
+        if missing:
+            with torch.no_grad():
+                f = run(missing)
+            for i, c in enumerate(missing):
+                cache[c] = f[:, i].clone()
+            if len(cache) > 8192:
+                for c in list(cache)[:len(cache) - 8192]:
+                    del cache[c]
+        return torch.stack([cache[c] for c in captions], dim=1)
 
     def get_class_embedding(self, text):
         """:561-566 — text = [LongTensor of person-1 caption ids, LongTensor of person-2 caption ids]."""
