@@ -85,6 +85,8 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
       ap_cp_async16(sQw + buf * 2048 + ap_swz(r, c), qg + (size_t)min(t, T - 1) * ldq + c * 8, t < T);
     }
   };
+  pdl_wait();      // q and a_in are outputs of the previous kernels
+  pdl_trigger();
   prefetch(g_lo, 0);
   ap_commit();
 
@@ -276,6 +278,8 @@ attn_kv_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restr
   }
   const __nv_bfloat16* kg = k + (size_t)s_kv * T * ldkv + h * AP_HD;
   const __nv_bfloat16* vg = v + (size_t)s_kv * T * ldkv + h * AP_HD;
+  pdl_wait();      // K, V are outputs of the previous kernel (length[] is older)
+  pdl_trigger();
   // rows >= len are zero-filled: Ks is forced to 0 there and V*mask == 0 (unmasked V rows meet Ks == 0: same A)
   for (int i = tid; i < TP * 8; i += KV_THREADS) {
     const int r = i >> 3, c = i & 7;
@@ -379,9 +383,9 @@ int attn_kv(const void* k, const void* v, int ldkv, void* a_out, const int* leng
     if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_kv attr: ") + cudaGetErrorString(e));
     configured = smem;
   }
-  attn_kv_kernel<<<dim3(H, S), KV_THREADS, smem, stream>>>((const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv,
-                                                          (__nv_bfloat16*)a_out, length, S, T, pair_shift);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(attn_kv_kernel, dim3(H, S), dim3(KV_THREADS), smem, stream, (const __nv_bfloat16*)k,
+                             (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)a_out, length, S, T, pair_shift);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_kv launch: ") + cudaGetErrorString(e));
   count_launch();
   return HIG_OK;
@@ -407,10 +411,10 @@ int attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* ga
   static const int n_sm = []() { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
   long long ctas = 2LL * n_sm;
   if (ctas > (long long)S * n_tiles) ctas = (long long)S * n_tiles;
-  attn_apply_stylize_kernel<<<(int)ctas, AP_THREADS, AP_SMEM, stream>>>(
-      (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)a_in, gamma, beta, scale_shift, ss_stride, apply_silu,
-      (__nv_bfloat16*)out, S, T);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(attn_apply_stylize_kernel, dim3((int)ctas), dim3(AP_THREADS), AP_SMEM, stream,
+                             (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)a_in, gamma, beta, scale_shift, ss_stride,
+                             apply_silu, (__nv_bfloat16*)out, S, T);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_apply_stylize launch: ") + cudaGetErrorString(e));
   count_launch();
   return HIG_OK;

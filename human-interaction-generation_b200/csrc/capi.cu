@@ -1,5 +1,6 @@
 // extern "C" boundary of libhig_b200.so — see include/hig_b200.h for the contract of every entry point.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -16,6 +17,10 @@ int set_error(int code, const std::string& msg) {
   return code;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = []() { const char* e = getenv("HIG_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 }  // namespace hig
 
 extern "C" {

@@ -112,6 +112,8 @@ ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, int ld_ep
   const long long per_seq = (long long)T * C;
   const long long total = (long long)S * per_seq;
   const long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  pdl_wait();      // eps is the output of the previous kernel
+  pdl_trigger();
   if (base >= total) return;
   float z[4] = {0.f, 0.f, 0.f, 0.f};
   if (noise) {
@@ -172,8 +174,8 @@ int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const 
   if (total >= (1LL << 31)) return set_error(HIG_ERR_UNSUPPORTED, "ddpm_step: more than 2^31 elements");
   const int blocks = (int)(((total + 3) / 4 + 255) / 256);
   if (packed && packed_dtype == HIG_BF16)
-    ddpm_step_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(x, eps, ld_eps, noise, t, coef, n_steps, S, T, C, seed,
-                                                               (__nv_bfloat16*)packed, ld_packed);
+    launch_pdl(ddpm_step_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, x, eps, ld_eps, noise, t, coef,
+               n_steps, S, T, C, seed, (__nv_bfloat16*)packed, ld_packed);
   else
     ddpm_step_kernel<float><<<blocks, 256, 0, stream>>>(x, eps, ld_eps, noise, t, coef, n_steps, S, T, C, seed,
                                                         (float*)packed, ld_packed);

@@ -77,6 +77,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail;
+  // its outputs (our operands / residual) are visible after the wait.  Dependents are released only after the wait,
+  // so a kernel's pre-wait code may rely on everything but its immediate predecessor's outputs.
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
@@ -201,8 +206,8 @@ static int launch_2cta_kind(const CUtensorMap& tmA, const CUtensorMap& tmB, int 
   const int n_tiles = (N + G2_BN - 1) / G2_BN;
   int pairs = m_tiles * n_tiles * k_splits;
   if (pairs > num_sms / 2) pairs = num_sms / 2;
-  kern<<<2 * pairs, G2_THREADS, G2_SMEM, stream>>>(tmA, tmB, M, N, K, ep, vec_ok, k_splits);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, dim3(2 * pairs), dim3(G2_THREADS), G2_SMEM, stream, tmA, tmB, M, N, K, ep, vec_ok, k_splits);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("gemm 2cta launch: ") + cudaGetErrorString(e));
   count_launch();
   return HIG_OK;

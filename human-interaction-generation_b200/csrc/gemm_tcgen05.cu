@@ -83,6 +83,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail;
+  // its outputs (our operands / residual) are visible after the wait.  Dependents are released only after the wait,
+  // so a kernel's pre-wait code may rely on everything but its immediate predecessor's outputs.
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -278,8 +283,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   const int n_tiles = (N + BN - 1) / BN;
   int grid = m_tiles * n_tiles * k_splits;
   if (grid > num_sms()) grid = num_sms();
-  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, M, N, K, ep, vec_ok, k_splits);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, tmA, tmB, M, N, K, ep, vec_ok, k_splits);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(e));
   count_launch();
   return HIG_OK;

@@ -80,6 +80,15 @@ HIG_DEVICE float2 unpack_bf16x2(uint32_t u) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// (prologue: barrier init, TMEM allocation, tensor-map prefetch, parameter staging) while its predecessor drains;
+// pdl_wait() blocks until the predecessor grid has completed and its writes are visible.  Both are no-ops for
+// kernels launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+HIG_DEVICE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+HIG_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 HIG_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {

@@ -4,7 +4,30 @@
 #include <string>
 #include "../../include/hig_b200.h"  // HIG_OK / HIG_ERR_* / HIG_BF16 / HIG_F32
 
+#include <utility>
+
 namespace hig {
+
+// HIG_PDL=0 disables programmatic dependent launch (default on)
+bool pdl_enabled();
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute: consecutive
+// kernels of the denoiser step overlap prologue and tail (also inside CUDA-graph capture: programmatic edges)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // records a message retrievable through hig_last_error() and returns `code`
 int set_error(int code, const std::string& msg);

@@ -86,6 +86,9 @@ ln_film_silu_kernel(const TIn* __restrict__ x, int rows, int rows_per_seq, int r
   // B' = beta (1 + scale) + shift, and use single-MUFU sigmoid (tanh.approx) — the kernel is issue-bound, not
   // HBM-bound, at ~25 instructions per element.  fp32 output (fp32 mode): reference evaluation order, precise expf.
   constexpr bool kFast = sizeof(TOut) == 2;
+  // gamma / beta are parameters (loaded while the previous kernel drains); scale_shift and x are kernel outputs
+  pdl_wait();
+  pdl_trigger();
   float SC[CHUNKS][8], SH[CHUNKS][8];
 #pragma unroll
   for (int c = 0; c < CHUNKS; ++c) {
@@ -179,9 +182,9 @@ static void launch_ln(const void* x, int rows, int rows_per_seq, const float* ga
   const int runs_per_seq = (rows_per_seq + rows_per_warp - 1) / rows_per_warp;
   const long long runs = (long long)n_seq * runs_per_seq;
   const int blocks = (int)((runs + LN_WARPS - 1) / LN_WARPS);
-  ln_film_silu_kernel<WIDTH, TIn, TOut><<<blocks, LN_WARPS * 32, 0, stream>>>(
-      reinterpret_cast<const TIn*>(x), rows, rows_per_seq, rows_per_warp, runs_per_seq, gamma, beta, scale_shift,
-      ss_stride, apply_silu, reinterpret_cast<TOut*>(out));
+  launch_pdl(ln_film_silu_kernel<WIDTH, TIn, TOut>, dim3(blocks), dim3(LN_WARPS * 32), 0, stream,
+             reinterpret_cast<const TIn*>(x), rows, rows_per_seq, rows_per_warp, runs_per_seq, gamma, beta, scale_shift,
+             ss_stride, apply_silu, reinterpret_cast<TOut*>(out));
 }
 
 int ln_film_silu(const void* x, int x_dtype, int rows, int width, int rows_per_seq, const float* gamma,
