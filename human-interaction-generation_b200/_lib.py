@@ -26,6 +26,9 @@ SIGNATURES = {
                       c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
     "hig_gemm_bf16_ex": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                          c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
+    "hig_gemm_stream": [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                        c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "hig_row_stats": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "hig_gemm_f32": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                      c_void_p, c_int, c_int, c_void_p],
     "hig_ln_film_silu": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,

@@ -80,6 +80,17 @@ int hig_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int 
                            out_bf16, ldo_bf16, act, static_cast<cudaStream_t>(stream));
 }
 
+int hig_gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op_dtype, int M, int N, int K,
+                    const float* bias, const float* wsum, const float* stats_in, float* stats_out, int ln_width,
+                    void* out, int ldo, void* stream) {
+  return hig::gemm_stream(kind, A, lda, W, ldw, op_dtype, M, N, K, bias, wsum, stats_in, stats_out, ln_width, out, ldo,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int hig_row_stats(const void* x, int x_dtype, int rows, int width, float* stats, void* stream) {
+  return hig::row_stats(x, x_dtype, rows, width, stats, static_cast<cudaStream_t>(stream));
+}
+
 int hig_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const float* bias,
                  const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, int act, void* stream) {
   return hig::gemm_f32(A, lda, W, ldw, M, N, K, bias, residual, ldr, res_row_mod, out_f32, ldo_f32, act,

@@ -208,9 +208,9 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 struct TmapKey {
-  const void* ptr; int rows, cols, ld, box_rows;
+  const void* ptr; int rows, cols, ld, box_rows, f16;
   bool operator==(const TmapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && f16 == o.f16;
   }
 };
 struct TmapKeyHash {
@@ -219,16 +219,19 @@ struct TmapKeyHash {
     h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (h << 6);
     h ^= (size_t)k.cols * 0xC2B2AE3D27D4EB4Full + (h >> 3);
     h ^= (size_t)k.ld * 0x165667B19E3779F9ull + (h << 9);
-    h ^= (size_t)k.box_rows * 0x27D4EB2F165667C5ull;
+    h ^= (size_t)(k.box_rows * 4 + k.f16) * 0x27D4EB2F165667C5ull;
     return h;
   }
 };
 
-// bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle
-static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+// 2-byte row-major [rows, cols] (bf16, or fp16 when is_f16) with leading dimension ld (elements);
+// box = [box_rows, 64 cols], 128B swizzle (flags bit 1: [box_rows, 32 cols], 64B swizzle); flags bit 0: fp16.
+// Used for operands (box_rows 128/256) and for the TMA-staged epilogues of gemm_stream.cu (box_rows 32).
+int get_tmap_2b(const void* ptr, int rows, int cols, int ld, int box_rows, int flags, CUtensorMap* out) {
+  const int is_f16 = flags & 1, narrow = (flags >> 1) & 1;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   static std::mutex mu;
-  TmapKey key{ptr, rows, cols, ld, box_rows};
+  TmapKey key{ptr, rows, cols, ld, box_rows, flags};
   {
     std::lock_guard<std::mutex> g(mu);
     auto itr = cache.find(key);
@@ -238,11 +241,12 @@ static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, C
   if (!enc) return set_error(HIG_ERR_NO_DRIVER, "cuTensorMapEncodeTiled not available");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(narrow ? 32 : GEMM_BK), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap tm;
-  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = enc(&tm, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, narrow ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(HIG_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
   {
@@ -254,10 +258,16 @@ static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, C
   return HIG_OK;
 }
 
+static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  return get_tmap_2b(ptr, rows, cols, ld, box_rows, 0, out);
+}
+
 int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
                      int vec_ok, int num_sms, int k_splits, cudaStream_t stream);
 
-static int num_sms() {
+int device_num_sms();
+static int num_sms() { return device_num_sms(); }
+int device_num_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;

@@ -42,6 +42,13 @@ int gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int N, i
                  const void* residual, int res_dtype, int ldr, int res_row_mod, void* out, int out_dtype, int ldo,
                  void* out_bf16, int ldo_bf16, int act, cudaStream_t stream);
 
+// kind: 0 bias->bf16, 1 bias->GELU->bf16, 2 fp16 stream in place (+ row statistics), 3 LayerNorm-folded -> bf16
+int gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op_dtype, int M, int N, int K,
+                const float* bias, const float* wsum, const float* stats_in, float* stats_out, int ln_width,
+                void* out, int ldo, cudaStream_t stream);
+
+int row_stats(const void* x, int x_dtype, int rows, int width, float* stats, cudaStream_t stream);
+
 int gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const float* bias,
              const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, int act,
              cudaStream_t stream);

@@ -217,4 +217,41 @@ int ln_film_silu(const void* x, int x_dtype, int rows, int width, int rows_per_s
   return HIG_OK;
 }
 
+// Row statistics of the fp16 residual stream for the LayerNorm-folded projections of gemm_stream.cu: stats[row] =
+// {sum, sum of squares, 0, 0, 0, 0, 0, 0} (the four-partial layout the out-projection epilogue writes; here the whole
+// row goes into partial 0).  Only the motion-embedding output needs it — every later LayerNorm input gets its
+// statistics from the epilogue that produced it.
+__global__ void __launch_bounds__(256) row_stats_kernel(const __half* __restrict__ x, int rows, float* __restrict__ stats) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    float a[8], b[8];
+    Io<__half>::load8(x + (size_t)row * 512 + lane * 8, a);
+    Io<__half>::load8(x + (size_t)row * 512 + 256 + lane * 8, b);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1 += a[i] + b[i]; s2 = fmaf(a[i], a[i], fmaf(b[i], b[i], s2)); }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane < 2) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane == 0) { o.x = s1; o.y = s2; }
+      reinterpret_cast<float4*>(stats + (size_t)row * 8)[lane] = o;
+    }
+  }
+}
+
+int row_stats(const void* x, int x_dtype, int rows, int width, float* stats, cudaStream_t stream) {
+  if (!x || !stats || rows <= 0) return set_error(HIG_ERR_INVALID, "row_stats: bad arguments");
+  if (x_dtype != HIG_F16 || width != 512) return set_error(HIG_ERR_UNSUPPORTED, "row_stats: fp16 rows of width 512");
+  const int blocks = min((rows + 7) / 8, 148 * 8);
+  cudaError_t e = launch_pdl(row_stats_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const __half*>(x), rows, stats);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("row_stats launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
 }  // namespace hig

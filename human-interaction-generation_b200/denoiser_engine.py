@@ -56,6 +56,8 @@ class DenoiserEngine:
         self._packed_key = None
         self._ws = {}
         self._text_cache = None
+        # product path: projections with the TMA-staged epilogue, pre-attention LayerNorms folded into them
+        self.stream = precision == "bf16"
 
     # ------------------------------------------------------------------------------------------ weights
     def _param_key(self):
@@ -96,11 +98,18 @@ class DenoiserEngine:
                         W[p + "ca.q.w"], W[p + "ca.q.b"] = op(a.query.weight), f32(a.query.bias)
                         W[p + "ca.kv.w"] = op(torch.cat([a.key.weight, a.value.weight], 0))
                         W[p + "ca.kv.b"] = f32(torch.cat([a.key.bias, a.value.bias], 0))
+                        if self.stream:
+                            self._fold_ln(W, p + "ca.q", a.norm, a.query.weight, a.query.bias)
                     else:
-                        W[p + name + ".qkv.w"] = op(torch.cat([a.query.weight, a.key.weight, a.value.weight], 0))
-                        W[p + name + ".qkv.b"] = f32(torch.cat([a.query.bias, a.key.bias, a.value.bias], 0))
+                        w_cat = torch.cat([a.query.weight, a.key.weight, a.value.weight], 0)
+                        b_cat = torch.cat([a.query.bias, a.key.bias, a.value.bias], 0)
+                        W[p + name + ".qkv.w"], W[p + name + ".qkv.b"] = op(w_cat), f32(b_cat)
+                        if self.stream:
+                            self._fold_ln(W, p + name + ".qkv", a.norm, w_cat, b_cat)
                 W[p + "ffn.w1"], W[p + "ffn.b1"] = op(blk.ffn.linear1.weight), f32(blk.ffn.linear1.bias)
                 W[p + "ffn.w2"], W[p + "ffn.b2"] = op(blk.ffn.linear2.weight), f32(blk.ffn.linear2.bias)
+                if self.stream:   # linear1 reads the fp16 residual stream directly
+                    W[p + "ffn.w1h"] = blk.ffn.linear1.weight.detach().to(torch.float16).contiguous()
                 for name, a in subs + [("ffn", blk.ffn)]:
                     st = a.proj_out
                     W[p + name + ".po.ln.w"], W[p + name + ".po.ln.b"] = f32(st.norm.weight), f32(st.norm.bias)
@@ -119,6 +128,17 @@ class DenoiserEngine:
         self._packed_T = None
         self._text_cache = None
         return W
+
+    @staticmethod
+    def _fold_ln(W, key, norm, weight, bias):
+        """nn.LayerNorm folded into the Linear that consumes it (hig_gemm_stream, HIG_GS_LN_BF16):
+        LN(x) W^T + b = rstd (x (gamma o W)^T - mu rowsum(gamma o W)) + (b + W beta).  The operand is stored in fp16 (the
+        residual stream's type); rowsum is taken over the ROUNDED operand so the mean term cancels exactly."""
+        w32 = weight.detach().to(torch.float32)
+        wg = (w32 * norm.weight.detach().to(torch.float32)[None, :]).to(torch.float16).contiguous()
+        W[key + ".wg"] = wg
+        W[key + ".wsum"] = wg.to(torch.float32).sum(1).contiguous()
+        W[key + ".bg"] = (bias.detach().to(torch.float32) + w32 @ norm.bias.detach().to(torch.float32)).contiguous()
 
     def packed_T(self):
         """W^T copies in the operand dtype: the B operand of the data-gradient GEMMs dx = dy . W (training only).
@@ -161,6 +181,7 @@ class DenoiserEngine:
             "eps": e(tok, self.LD_EPS, dtype=torch.float32),
             "len": torch.empty(S, device=dev, dtype=torch.int32),
             "a_blk": e(S, self.H, HEAD_DIM, HEAD_DIM),
+            "stats": e(tok, 8, dtype=torch.float32),   # LayerNorm row statistics of the stream (4 partials per row)
         }
         if self.precision == "fp32":
             ws["xb"] = ws["xres"]            # fp32 mode: the operand copy IS the residual stream
@@ -260,7 +281,50 @@ class DenoiserEngine:
         ops.ln_film_silu(ws["y"], W[p + ".po.ln.w"], W[p + ".po.ln.b"], ws["sact"], rows_per_seq=T,
                          scale_shift=self._ss(ws, W, p), silu=True)
 
+    def layers_stream(self, ws, a_text, S, T):
+        """bf16 product schedule.  Per layer: 7 tcgen05 projections (hig_gemm_stream), 2 K/V-half kernels, 3 fused
+        query-half + stylization kernels, 1 LayerNorm+FiLM+SiLU (FFN branch).  The three pre-attention LayerNorms
+        (:119,153,190) are folded into the Q/K/V projections: each out-projection epilogue leaves the row statistics
+        of the stream it has just updated in ws['stats'], the next projection reads the raw fp16 stream."""
+        W, D = self.packed(), self.D
+        gs = ops.gemm_stream
+        qkv, xres, sact, stats = ws["qkv"], ws["xres"], ws["sact"], ws["stats"]
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+        tok = S * T
+        q_ca = qkv.view(-1)[:tok * D].view(tok, D)
+        ops.row_stats(xres, stats)
+        for li in range(self.L):
+            p = f"l{li}."
+            last = li == self.L - 1
+            # --- self attention (:112-130)
+            gs(ops.GS_LN_BF16, xres, W[p + "sa.qkv.wg"], W[p + "sa.qkv.bg"], qkv, wsum=W[p + "sa.qkv.wsum"],
+               stats_in=stats, ln_width=D)
+            self._attend(ws, W, p + "sa", S, T, q, k, v, mask_v=True)
+            gs(ops.GS_RES_H, sact, W[p + "sa.po.w"], W[p + "sa.po.b"], xres, stats_out=stats)
+            # --- text cross attention (:145-165), K/V side precomputed in text_state()
+            gs(ops.GS_LN_BF16, xres, W[p + "ca.q.wg"], W[p + "ca.q.bg"], q_ca, wsum=W[p + "ca.q.wsum"],
+               stats_in=stats, ln_width=D)
+            self._attend(ws, W, p + "ca", S, T, q_ca, a_in=a_text[li])
+            gs(ops.GS_RES_H, sact, W[p + "ca.po.w"], W[p + "ca.po.b"], xres, stats_out=stats if self.has_ic else None)
+            # --- inter-person cross attention (:181-207): K,V of the partner, mask of the query side
+            if self.has_ic:
+                gs(ops.GS_LN_BF16, xres, W[p + "ic.qkv.wg"], W[p + "ic.qkv.bg"], qkv, wsum=W[p + "ic.qkv.wsum"],
+                   stats_in=stats, ln_width=D)
+                self._attend(ws, W, p + "ic", S, T, q, k, v, pair_shift=S // 2, mask_v=False)
+                gs(ops.GS_RES_H, sact, W[p + "ic.po.w"], W[p + "ic.po.b"], xres)
+            # --- FFN (:261-264): no pre-norm, linear1 reads the fp16 stream, GELU fused in its epilogue
+            gs(ops.GS_BF16_GELU, xres, W[p + "ffn.w1h"], W[p + "ffn.b1"], ws["g"])
+            gs(ops.GS_BF16, ws["g"], W[p + "ffn.w2"], W[p + "ffn.b2"], ws["y"])
+            ops.ln_film_silu(ws["y"], W[p + "ffn.po.ln.w"], W[p + "ffn.po.ln.b"], sact, rows_per_seq=T,
+                             scale_shift=self._ss(ws, W, p + "ffn"), silu=True)
+            if last:
+                self._project(ws, W, p + "ffn", True)        # also writes the bf16 copy the output heads read
+            else:
+                gs(ops.GS_RES_H, sact, W[p + "ffn.po.w"], W[p + "ffn.po.b"], xres, stats_out=stats)
+
     def layers(self, ws, a_text, S, T):
+        if self.stream:
+            return self.layers_stream(ws, a_text, S, T)
         W, D = self.packed(), self.D
         qkv = ws["qkv"]
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]

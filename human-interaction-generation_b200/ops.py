@@ -88,6 +88,44 @@ def gemm(a, w, bias=None, residual=None, res_row_mod=0, out_f32=None, out_bf16=N
     raise TypeError(f"hig_b200.gemm: unsupported dtype {a.dtype}")
 
 
+GS_BF16, GS_BF16_GELU, GS_RES_H, GS_LN_BF16 = 0, 1, 2, 3
+
+
+def gemm_stream(kind, a, w, bias, out, wsum=None, stats_in=None, stats_out=None, ln_width=0):
+    """Token-sized projection with the TMA-staged epilogue (csrc/gemm_stream.cu).  a [M,K], w [N,K] both bf16 or both
+    fp16; out bf16 [M,N] (GS_BF16 / GS_BF16_GELU / GS_LN_BF16) or the fp16 residual stream updated in place (GS_RES_H)."""
+    lib = _lib.load()
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K or a.dtype != w.dtype or a.dtype not in (torch.bfloat16, torch.float16):
+        raise TypeError("hig_b200.gemm_stream: A and W must both be bf16 or both fp16, with matching K")
+    want = torch.float16 if kind == GS_RES_H else torch.bfloat16
+    if out.dtype != want or tuple(out.shape) != (M, N):
+        raise TypeError(f"hig_b200.gemm_stream: out must be {want} [{M},{N}]")
+    for t, nm in ((bias, "bias"), (wsum, "wsum"), (stats_in, "stats_in"), (stats_out, "stats_out")):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise TypeError(f"hig_b200.gemm_stream: {nm} must be contiguous fp32")
+    for t, nm in ((stats_in, "stats_in"), (stats_out, "stats_out")):
+        if t is not None and tuple(t.shape) != (M, 8):
+            raise ValueError(f"hig_b200.gemm_stream: {nm} must be [M, 8]")
+    rc = lib.hig_gemm_stream(kind, _ptr(a), _rowmajor(a, "A"), _ptr(w), _rowmajor(w, "W"), _dt(a), M, N, K, _ptr(bias),
+                             _ptr(wsum), _ptr(stats_in), _ptr(stats_out), ln_width, _ptr(out), _rowmajor(out, "out"),
+                             _stream())
+    _lib.check(rc, "hig_gemm_stream")
+    return out
+
+
+def row_stats(x, stats):
+    """stats[row] = (sum, sum of squares, 0 x 6) of the fp16 rows of x [rows, 512] (layout of gemm_stream's partials)."""
+    lib = _lib.load()
+    rows, width = x.shape
+    if not x.is_contiguous() or stats.dtype != torch.float32 or tuple(stats.shape) != (rows, 8) or not stats.is_contiguous():
+        raise ValueError("hig_b200.row_stats: x contiguous [rows, 512], stats contiguous fp32 [rows, 8]")
+    rc = lib.hig_row_stats(_ptr(x), _dt(x), rows, width, _ptr(stats), _stream())
+    _lib.check(rc, "hig_row_stats")
+    return stats
+
+
 def ln_film_silu(x, gamma, beta, out, rows_per_seq=1, scale_shift=None, silu=False):
     """out = [SiLU](LN(x) * (1 + scale) + shift); x [rows, W] (W in {256, 512}); scale_shift fp32 view [S, >=2W]."""
     lib = _lib.load()

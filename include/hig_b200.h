@@ -61,6 +61,31 @@ int hig_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int 
                      const void* residual, int res_dtype, int ldr, int res_row_mod, void* out, int out_dtype, int ldo,
                      void* out_bf16, int ldo_bf16, int act, void* stream);
 
+/* The token-sized projections of the sampling path with a TMA-staged epilogue (csrc/gemm_stream.cu): same CTA-pair
+ * tcgen05 main loop, but the epilogue packs each accumulator row into a 128B-swizzled shared-memory slab and one lane
+ * issues a TMA store (residual tiles arrive by TMA load).  A [M,K], W [N,K] both HIG_BF16 or both HIG_F16 (op_dtype),
+ * N % 64 == 0, bias fp32 [N].
+ *   HIG_GS_BF16      out bf16 [M,ldo] = A.W^T + bias                       (FFN linear2 :263, text-CA query :153)
+ *   HIG_GS_BF16_GELU out bf16 = GELU(A.W^T + bias)                         (FFN linear1 :262)
+ *   HIG_GS_RES_H     out fp16 [M,ldo] += A.W^T + bias, in place: the residual `x + proj_out(...)` (:97,129,164,203,
+ *                    263); stats_out (nullable, N == 512) fp32 [M,8] receives four (sum, sum of squares) partials of
+ *                    every updated row
+ *   HIG_GS_LN_BF16   out bf16 = rstd_m (A.W^T - mu_m wsum) + bias: nn.LayerNorm(ln_width) folded into the projection
+ *                    that consumes it (:119-121,153,190-194).  A is the raw stream, W = gamma o W_lin, wsum[n] =
+ *                    sum_k W[n,k], bias[n] = b[n] + sum_k beta[k] W_lin[n,k]; (mu, rstd) of row m from stats_in[m]
+ *                    (the partials HIG_GS_RES_H or hig_row_stats left), eps = 1e-5. */
+#define HIG_GS_BF16 0
+#define HIG_GS_BF16_GELU 1
+#define HIG_GS_RES_H 2
+#define HIG_GS_LN_BF16 3
+int hig_gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op_dtype, int M, int N, int K,
+                    const float* bias, const float* wsum, const float* stats_in, float* stats_out, int ln_width,
+                    void* out, int ldo, void* stream);
+
+/* stats[row] = {sum, sum of squares, 0 x 6} of fp16 rows of width 512: the LayerNorm statistics of the motion-embedding
+ * output (models/interaction_transformer.py:593-602 feeding :119) in the layout HIG_GS_LN_BF16 reads. */
+int hig_row_stats(const void* x, int x_dtype, int rows, int width, float* stats, void* stream);
+
 /* the same contract in fp32 storage and fp32 FFMA arithmetic ("fp32 mode", parity <= 1e-5) */
 int hig_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const float* bias,
                  const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, int act, void* stream);

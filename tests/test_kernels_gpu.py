@@ -98,6 +98,104 @@ def test_gemm_rejects_bad_input(cuda):
         ops.gemm(torch.randn(4, 8).bfloat16(), torch.randn(4, 8).bfloat16())  # CPU tensors: no fallback
 
 
+# ------------------------------------------------------------------------------------ GEMM with the TMA-staged epilogue
+STREAM_SHAPES = [(256, 512, 512), (25088, 1536, 512), (1000, 512, 512), (392 * 8, 1024, 512), (25088, 512, 1024),
+                 (777, 320, 128), (3000, 64, 72), (100, 512, 512), (7, 64, 8)]
+
+
+@pytest.mark.parametrize("op_dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", STREAM_SHAPES)
+def test_gemm_stream_bf16_and_gelu(cuda, M, N, K, op_dt):
+    """out = [GELU](A W^T + b) -> bf16, ragged M (TMA store clipping), partial column tiles, fp16 and bf16 operands.
+    Tolerance: bf16 output rounding (2^-9 relative per element => < 4e-3 rel-L2); GELU is tanh.approx based."""
+    ops = _ops()
+    g = torch.Generator(device=cuda).manual_seed(M + N + K)
+    a = torch.randn(M, K, device=cuda, generator=g).to(op_dt)
+    w = (torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K)).to(op_dt)
+    bias = torch.randn(N, device=cuda, generator=g)
+    ref = a.float() @ w.float().t() + bias
+    for kind, r in ((ops.GS_BF16, ref), (ops.GS_BF16_GELU, F.gelu(ref))):
+        guard = torch.full((M + 3, N), 7.0, device=cuda, dtype=torch.bfloat16)
+        out = guard[:M]
+        ops.gemm_stream(kind, a, w, bias, out)
+        assert _rel(out.float(), r) < 4e-3, (kind, _rel(out.float(), r))
+        assert (out.float() - r).abs().max().item() < 2e-2 * max(1.0, r.abs().max().item())
+        assert (guard[M:] == 7.0).all()          # rows past M untouched
+
+
+@pytest.mark.parametrize("M", [256, 25088, 1000, 3333, 60])
+def test_gemm_stream_residual_inplace_and_row_stats(cuda, M):
+    """x (fp16) += A W^T + b in place, plus the per-row (sum, sum of squares) partials; hig_row_stats agrees."""
+    ops = _ops()
+    N = K = 512
+    g = torch.Generator(device=cuda).manual_seed(M)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=cuda, generator=g)
+    x0 = (torch.randn(M, N, device=cuda, generator=g) * 2).half()
+    x = x0.clone()
+    stats = torch.full((M, 8), -1.0, device=cuda)
+    ops.gemm_stream(ops.GS_RES_H, a, w, bias, x, stats_out=stats)
+    ref = a.float() @ w.float().t() + bias + x0.float()
+    assert _rel(x.float(), ref) < 5e-4, _rel(x.float(), ref)          # fp16 storage: 2^-11 relative
+    st = stats.view(M, 4, 2).sum(1)
+    assert _rel(st[:, 0], ref.sum(1)) < 1e-3
+    assert _rel(st[:, 1], (ref * ref).sum(1)) < 1e-4
+    # without statistics; and the standalone statistics kernel on the result
+    x2 = x0.clone()
+    ops.gemm_stream(ops.GS_RES_H, a, w, bias, x2)
+    assert torch.equal(x2, x)
+    st2 = torch.empty(M, 8, device=cuda)
+    ops.row_stats(x, st2)
+    assert st2[:, 2:].abs().max().item() == 0.0
+    assert _rel(st2[:, 0], x.float().sum(1)) < 1e-5 and _rel(st2[:, 1], (x.float() ** 2).sum(1)) < 1e-5
+
+
+@pytest.mark.parametrize("M,N", [(25088, 1536), (1000, 512), (256, 1536)])
+def test_gemm_stream_layernorm_folded(cuda, M, N):
+    """LayerNorm folded into the projection: out = LN(x; gamma, beta) W^T + b with x the raw fp16 stream.
+    Reference: F.layer_norm in fp32 then the fp32 product; tolerance = bf16 output rounding + fp16 operand rounding."""
+    ops = _ops()
+    K = 512
+    g = torch.Generator(device=cuda).manual_seed(N + M)
+    x = (torch.randn(M, K, device=cuda, generator=g) * 1.7 + 0.3).half()
+    gamma = 1 + 0.2 * torch.randn(K, device=cuda, generator=g)
+    beta = 0.1 * torch.randn(K, device=cuda, generator=g)
+    w = torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K)
+    b = torch.randn(N, device=cuda, generator=g)
+    wg = (w * gamma).half()
+    wsum = wg.float().sum(1).contiguous()
+    bias = (b + w @ beta).contiguous()
+    stats = torch.empty(M, 8, device=cuda)
+    ops.row_stats(x, stats)
+    out = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm_stream(ops.GS_LN_BF16, x, wg, bias, out, wsum=wsum, stats_in=stats, ln_width=K)
+    ref = F.layer_norm(x.float(), (K,), gamma, beta) @ w.t() + b
+    assert _rel(out.float(), ref) < 4e-3, _rel(out.float(), ref)
+    # statistics split over the four partials (as the out-projection epilogue leaves them) give the same result
+    st4 = torch.zeros(M, 4, 2, device=cuda)
+    xf = x.float().view(M, 4, 128)
+    st4[:, :, 0] = xf.sum(2)
+    st4[:, :, 1] = (xf * xf).sum(2)
+    out4 = torch.empty_like(out)
+    ops.gemm_stream(ops.GS_LN_BF16, x, wg, bias, out4, wsum=wsum, stats_in=st4.view(M, 8).contiguous(), ln_width=K)
+    assert _rel(out4.float(), ref) < 4e-3
+
+
+def test_gemm_stream_rejects_bad_input(cuda):
+    ops = _ops()
+    a = torch.zeros(512, 512, device=cuda, dtype=torch.bfloat16)
+    w = torch.zeros(512, 512, device=cuda, dtype=torch.bfloat16)
+    b = torch.zeros(512, device=cuda)
+    with pytest.raises(TypeError):
+        ops.gemm_stream(ops.GS_BF16, a, w.half(), b, torch.empty(512, 512, device=cuda, dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError):   # N not a multiple of 64
+        ops.gemm_stream(ops.GS_BF16, a, w[:40], b[:40].contiguous(), torch.empty(512, 40, device=cuda, dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError):   # row statistics only from the N = 512 projection
+        ops.gemm_stream(ops.GS_RES_H, a, w[:256], b[:256].contiguous(), torch.empty(512, 256, device=cuda, dtype=torch.float16),
+                        stats_out=torch.empty(512, 8, device=cuda))
+
+
 @pytest.mark.parametrize("M,N,K,act", [(130, 263, 512, 0), (257, 512, 267, 1), (64, 1024, 2048, 2)])
 def test_gemm_f32(cuda, M, N, K, act):
     ops = _ops()
