@@ -48,7 +48,7 @@ HIG_DEVICE uint32_t ap_swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r 
 constexpr int AP_SMEM_A = 8 * AP_HD * 128;          // 64 KB: A[h][d][l]
 constexpr int AP_SMEM_Q = 8 * 2 * 16 * 128;         // 32 KB: per warp, 2 buffers of 16 rows x 128 B
 constexpr int AP_SMEM_GB = 2 * AP_D * 4;            // gamma', beta'
-constexpr int AP_SMEM_RED = 2 * 16 * 8 * 4;         // row partial sums / centred squares [16 rows][8 warps]
+constexpr int AP_SMEM_RED = 2 * 16 * 8 * 8;         // two buffers of row partials (sum, sum of squares) [16 rows][8 warps]
 constexpr int AP_SMEM = AP_SMEM_A + AP_SMEM_Q + AP_SMEM_GB + AP_SMEM_RED;
 
 __global__ void __launch_bounds__(AP_THREADS, 2)
@@ -61,8 +61,7 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
   const uint32_t sQ = sA + AP_SMEM_A;
   float* sG = reinterpret_cast<float*>(ap_smem + AP_SMEM_A + AP_SMEM_Q);
   float* sB = sG + AP_D;
-  float* sR1 = sB + AP_D;            // [16][8]
-  float* sR2 = sR1 + 16 * 8;         // [16][8]
+  float2* sR = reinterpret_cast<float2*>(sB + AP_D);   // [2][16][8]
 
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int n_tiles = (T + 15) >> 4;
@@ -91,6 +90,7 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
   ap_commit();
 
   const int g = lane >> 2, tg = lane & 3;
+  const float hs = apply_silu ? 0.5f : 1.0f;
   const uint32_t sAw = sA + w * (AP_HD * 128);
   int buf = 0, cur_s = -1;
   for (int gi = g_lo; gi < g_hi; ++gi, buf ^= 1) {
@@ -112,8 +112,8 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
           gg *= m1;
           bb = fmaf(bb, m1, scale_shift[(size_t)s * ss_stride + AP_D + i]);
         }
-        sG[i] = gg;
-        sB[i] = bb;
+        sG[i] = gg * hs;
+        sB[i] = bb * hs;
       }
       ap_wait<0>();
       __syncthreads();
@@ -131,36 +131,57 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
       const int c = kk * 2 + ((lane >> 4) & 1);
       ap_ldsm_x4(sQt + ap_swz(row, c), af[kk][0], af[kk][1], af[kk][2], af[kk][3]);
     }
-    // feature softmax on the fragments: row g <- regs {0,2}, row g+8 <- regs {1,3} of every k-step
-    float x0[16], x1[16];
+    // feature softmax on the fragments: row g <- regs {0,2}, row g+8 <- regs {1,3} of every k-step.  Column pairs stay
+    // packed (FFMA2 / FADD2 / FMUL2); exp(x - m) = ex2(x log2e - m log2e) is one packed FMA + one MUFU per element.
+    uint64_t x0[8], x1[8];   // pair j of row g / g+8: columns 16 kk + {0,1} (j = 2kk) and 16 kk + 8 + {0,1} (j = 2kk+1) + 2tg
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      float2 f;
-      f = unpack_bf16x2(af[kk][0]); x0[4 * kk + 0] = f.x; x0[4 * kk + 1] = f.y;
-      f = unpack_bf16x2(af[kk][2]); x0[4 * kk + 2] = f.x; x0[4 * kk + 3] = f.y;
-      f = unpack_bf16x2(af[kk][1]); x1[4 * kk + 0] = f.x; x1[4 * kk + 1] = f.y;
-      f = unpack_bf16x2(af[kk][3]); x1[4 * kk + 2] = f.x; x1[4 * kk + 3] = f.y;
+      x0[2 * kk + 0] = f2_pack_u(af[kk][0] << 16, af[kk][0] & 0xffff0000u);
+      x0[2 * kk + 1] = f2_pack_u(af[kk][2] << 16, af[kk][2] & 0xffff0000u);
+      x1[2 * kk + 0] = f2_pack_u(af[kk][1] << 16, af[kk][1] & 0xffff0000u);
+      x1[2 * kk + 1] = f2_pack_u(af[kk][3] << 16, af[kk][3] & 0xffff0000u);
     }
-    float m0 = x0[0], m1 = x1[0];
+    float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-    for (int j = 1; j < 16; ++j) { m0 = fmaxf(m0, x0[j]); m1 = fmaxf(m1, x1[j]); }
+    for (int j = 0; j < 8; ++j) {
+      float a, b;
+      f2_unpack(x0[j], a, b); m0 = fmaxf(m0, fmaxf(a, b));
+      f2_unpack(x1[j], a, b); m1 = fmaxf(m1, fmaxf(a, b));
+    }
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float s0 = 0.f, s1 = 0.f;
+    {
+      const float kL2E = 1.4426950408889634f;
+      const uint64_t l2e = f2_pack(kL2E, kL2E);
+      const uint64_t nm0 = f2_pack(-m0 * kL2E, -m0 * kL2E), nm1 = f2_pack(-m1 * kL2E, -m1 * kL2E);
+      uint64_t sum0 = 0ull, sum1 = 0ull;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      x0[j] = __expf(x0[j] - m0); s0 += x0[j];
-      x1[j] = __expf(x1[j] - m1); s1 += x1[j];
-    }
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-    const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+      for (int j = 0; j < 8; ++j) {
+        float a, b;
+        f2_unpack(f2_fma(x0[j], l2e, nm0), a, b);
+        x0[j] = f2_pack(ex2_ftz(a), ex2_ftz(b));
+        sum0 = f2_add(sum0, x0[j]);
+        f2_unpack(f2_fma(x1[j], l2e, nm1), a, b);
+        x1[j] = f2_pack(ex2_ftz(a), ex2_ftz(b));
+        sum1 = f2_add(sum1, x1[j]);
+      }
+      float s0, s1, t0, t1;
+      f2_unpack(sum0, s0, t0);
+      f2_unpack(sum1, s1, t1);
+      s0 += t0;
+      s1 += t1;
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+      const uint64_t i02 = f2_pack(i0, i0), i12 = f2_pack(i1, i1);
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      af[kk][0] = pack_bf16x2(x0[4 * kk + 0] * i0, x0[4 * kk + 1] * i0);
-      af[kk][2] = pack_bf16x2(x0[4 * kk + 2] * i0, x0[4 * kk + 3] * i0);
-      af[kk][1] = pack_bf16x2(x1[4 * kk + 0] * i1, x1[4 * kk + 1] * i1);
-      af[kk][3] = pack_bf16x2(x1[4 * kk + 2] * i1, x1[4 * kk + 3] * i1);
+      for (int kk = 0; kk < 4; ++kk) {
+        float a, b;
+        f2_unpack(f2_mul(x0[2 * kk + 0], i02), a, b); af[kk][0] = pack_bf16x2(a, b);
+        f2_unpack(f2_mul(x0[2 * kk + 1], i02), a, b); af[kk][2] = pack_bf16x2(a, b);
+        f2_unpack(f2_mul(x1[2 * kk + 0], i12), a, b); af[kk][1] = pack_bf16x2(a, b);
+        f2_unpack(f2_mul(x1[2 * kk + 1], i12), a, b); af[kk][3] = pack_bf16x2(a, b);
+      }
     }
     float acc[8][4];
 #pragma unroll
@@ -179,57 +200,72 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
         ap_mma(acc[2 * np + 1], af[kk], b2, b3);
       }
     }
-    // ---- LayerNorm over the 512 columns of a row = 8 warps x 64 columns: two-pass statistics through smem
-    float r0 = 0.f, r1 = 0.f;
+    // ---- LayerNorm over the 512 columns of a row = 8 warps x 64 columns: (sum, sum of squares) partials of every warp
+    //      meet in shared memory behind ONE barrier per tile (the partial buffer alternates between tiles)
+    uint64_t y0[8], y1[8];
+    uint64_t ps0 = 0ull, pq0 = 0ull, ps1 = 0ull, pq1 = 0ull;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) { r0 += acc[nt][0] + acc[nt][1]; r1 += acc[nt][2] + acc[nt][3]; }
+    for (int nt = 0; nt < 8; ++nt) {
+      y0[nt] = f2_pack(acc[nt][0], acc[nt][1]);
+      y1[nt] = f2_pack(acc[nt][2], acc[nt][3]);
+      ps0 = f2_add(ps0, y0[nt]); pq0 = f2_fma(y0[nt], y0[nt], pq0);
+      ps1 = f2_add(ps1, y1[nt]); pq1 = f2_fma(y1[nt], y1[nt], pq1);
+    }
+    float r0, r1, q0, q1;
+    {
+      float a, b;
+      f2_unpack(ps0, a, b); r0 = a + b;
+      f2_unpack(pq0, a, b); q0 = a + b;
+      f2_unpack(ps1, a, b); r1 = a + b;
+      f2_unpack(pq1, a, b); q1 = a + b;
+    }
     r0 += __shfl_xor_sync(0xffffffffu, r0, 1); r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
-    r1 += __shfl_xor_sync(0xffffffffu, r1, 1); r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
-    if (tg == 0) { sR1[g * 8 + w] = r0; sR1[(g + 8) * 8 + w] = r1; }
-    __syncthreads();
-    float mean0, mean1;
-    {
-      const float4 a = *reinterpret_cast<const float4*>(sR1 + g * 8), b = *reinterpret_cast<const float4*>(sR1 + g * 8 + 4);
-      const float4 c = *reinterpret_cast<const float4*>(sR1 + (g + 8) * 8), d = *reinterpret_cast<const float4*>(sR1 + (g + 8) * 8 + 4);
-      mean0 = ((a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w)) * (1.0f / AP_D);
-      mean1 = ((c.x + c.y) + (c.z + c.w) + (d.x + d.y) + (d.z + d.w)) * (1.0f / AP_D);
-    }
-    float q0 = 0.f, q1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      acc[nt][0] -= mean0; acc[nt][1] -= mean0; acc[nt][2] -= mean1; acc[nt][3] -= mean1;
-      q0 = fmaf(acc[nt][0], acc[nt][0], q0); q0 = fmaf(acc[nt][1], acc[nt][1], q0);
-      q1 = fmaf(acc[nt][2], acc[nt][2], q1); q1 = fmaf(acc[nt][3], acc[nt][3], q1);
-    }
     q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, 1); r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
     q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
-    if (tg == 0) { sR2[g * 8 + w] = q0; sR2[(g + 8) * 8 + w] = q1; }
+    float2* sRb = sR + (buf ? 16 * 8 : 0);     // [16 rows][8 warps] (sum, sum of squares)
+    if (tg == 0) { sRb[g * 8 + w] = make_float2(r0, q0); sRb[(g + 8) * 8 + w] = make_float2(r1, q1); }
     __syncthreads();
-    float rstd0, rstd1;
+    float mean0, mean1, rstd0, rstd1;
     {
-      const float4 a = *reinterpret_cast<const float4*>(sR2 + g * 8), b = *reinterpret_cast<const float4*>(sR2 + g * 8 + 4);
-      const float4 c = *reinterpret_cast<const float4*>(sR2 + (g + 8) * 8), d = *reinterpret_cast<const float4*>(sR2 + (g + 8) * 8 + 4);
-      rstd0 = rsqrtf(((a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w)) * (1.0f / AP_D) + 1e-5f);
-      rstd1 = rsqrtf(((c.x + c.y) + (c.z + c.w) + (d.x + d.y) + (d.z + d.w)) * (1.0f / AP_D) + 1e-5f);
-    }
-    // ---- affine + SiLU, staged through this warp's consumed Q buffer, then 16-byte row stores
-    __syncwarp();
+      float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int col = w * AP_HD + nt * 8 + 2 * tg;
-      const float2 G2 = *reinterpret_cast<const float2*>(sG + col), B2 = *reinterpret_cast<const float2*>(sB + col);
-      float o[4];
-      o[0] = fmaf(acc[nt][0] * rstd0, G2.x, B2.x);
-      o[1] = fmaf(acc[nt][1] * rstd0, G2.y, B2.y);
-      o[2] = fmaf(acc[nt][2] * rstd1, G2.x, B2.x);
-      o[3] = fmaf(acc[nt][3] * rstd1, G2.y, B2.y);
-      if (apply_silu) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = o[j] * fmaf(tanh_approx_f(0.5f * o[j]), 0.5f, 0.5f);
+      for (int i = 0; i < 4; ++i) {
+        const float4 u = *reinterpret_cast<const float4*>(sRb + g * 8 + 2 * i);
+        const float4 v = *reinterpret_cast<const float4*>(sRb + (g + 8) * 8 + 2 * i);
+        sa += u.x + u.z; qa += u.y + u.w;
+        sb += v.x + v.z; qb += v.y + v.w;
       }
-      // element (row, nt*8 + 2tg) -> chunk nt, byte offset 4*tg inside the chunk
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQt + ap_swz(g, nt) + 4 * tg), "r"(pack_bf16x2(o[0], o[1])) : "memory");
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQt + ap_swz(g + 8, nt) + 4 * tg), "r"(pack_bf16x2(o[2], o[3])) : "memory");
+      mean0 = sa * (1.0f / AP_D);
+      mean1 = sb * (1.0f / AP_D);
+      rstd0 = rsqrtf(fmaxf(fmaf(qa, 1.0f / AP_D, -mean0 * mean0), 0.f) + 1e-5f);
+      rstd1 = rsqrtf(fmaxf(fmaf(qb, 1.0f / AP_D, -mean1 * mean1), 0.f) + 1e-5f);
+    }
+    // ---- affine + SiLU, staged through this warp's consumed Q buffer, then 16-byte row stores.  sG / sB already carry
+    //      the factor 1/2 when SiLU follows:  h = x/2,  SiLU(x) = h + h tanh(h)
+    __syncwarp();
+    {
+      const uint64_t rs0 = f2_pack(rstd0, rstd0), rs1 = f2_pack(rstd1, rstd1);
+      const uint64_t c0 = f2_pack(-mean0 * rstd0, -mean0 * rstd0), c1 = f2_pack(-mean1 * rstd1, -mean1 * rstd1);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = w * AP_HD + nt * 8 + 2 * tg;
+        const uint64_t G2 = *reinterpret_cast<const uint64_t*>(sG + col), B2 = *reinterpret_cast<const uint64_t*>(sB + col);
+        uint64_t h0 = f2_fma(y0[nt], f2_mul(G2, rs0), f2_fma(c0, G2, B2));
+        uint64_t h1 = f2_fma(y1[nt], f2_mul(G2, rs1), f2_fma(c1, G2, B2));
+        float a, b, c, d;
+        if (apply_silu) {
+          f2_unpack(h0, a, b);
+          f2_unpack(h1, c, d);
+          h0 = f2_fma(h0, f2_pack(tanh_approx_f(a), tanh_approx_f(b)), h0);
+          h1 = f2_fma(h1, f2_pack(tanh_approx_f(c), tanh_approx_f(d)), h1);
+        }
+        f2_unpack(h0, a, b);
+        f2_unpack(h1, c, d);
+        // element (row, nt*8 + 2tg) -> chunk nt, byte offset 4*tg inside the chunk
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQt + ap_swz(g, nt) + 4 * tg), "r"(pack_bf16x2(a, b)) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQt + ap_swz(g + 8, nt) + 4 * tg), "r"(pack_bf16x2(c, d)) : "memory");
+      }
     }
     __syncwarp();
 #pragma unroll
@@ -292,39 +328,72 @@ attn_kv_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restr
   ap_wait<0>();
   __syncthreads();
 
-  // ---- time softmax of K: lane owns the 4-byte word `lane` of every row (columns 2*lane, 2*lane+1)
-  auto kword = [&](int t) { return sK + t * 128 + (((lane >> 2) ^ (t & 7)) << 4) + (lane & 3) * 4; };
-  float m0 = -INFINITY, m1 = -INFINITY;
-  for (int t = warp; t < len; t += KV_WARPS) {
-    uint32_t u;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(kword(t)));
-    const float2 f = unpack_bf16x2(u);
-    m0 = fmaxf(m0, f.x);
-    m1 = fmaxf(m1, f.y);
+  // ---- time softmax of K: lane owns the 16-byte chunk (lane & 7) = 8 columns of rows (lane >> 3) + 4 warp + 32 i.
+  //      Maxima stay packed bf16x2 (HMNMX2), exp(k - m) = ex2(k log2e - m log2e) is one packed FMA + one MUFU.
+  const int rr = lane >> 3, cc = lane & 7;
+  auto kchunk = [&](int t) { return sK + t * 128 + ((cc ^ (t & 7)) << 4); };
+  auto hmax2 = [](uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+  };
+  uint32_t mx[4] = {0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u};   // (-inf, -inf)
+  for (int t = warp * 4 + rr; t < len; t += 4 * KV_WARPS) {
+    uint4 u;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(kchunk(t)));
+    mx[0] = hmax2(mx[0], u.x); mx[1] = hmax2(mx[1], u.y); mx[2] = hmax2(mx[2], u.z); mx[3] = hmax2(mx[3], u.w);
   }
-  sred[warp * 64 + 2 * lane] = m0;
-  sred[warp * 64 + 2 * lane + 1] = m1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mx[i] = hmax2(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 8));
+    mx[i] = hmax2(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 16));
+  }
+  uint32_t* sredu = reinterpret_cast<uint32_t*>(sred);   // [KV_WARPS][32 words]
+  if (rr == 0) *reinterpret_cast<uint4*>(sredu + warp * 32 + cc * 4) = make_uint4(mx[0], mx[1], mx[2], mx[3]);
   __syncthreads();
 #pragma unroll
   for (int w = 0; w < KV_WARPS; ++w) {
-    m0 = fmaxf(m0, sred[w * 64 + 2 * lane]);
-    m1 = fmaxf(m1, sred[w * 64 + 2 * lane + 1]);
+    const uint4 o = *reinterpret_cast<const uint4*>(sredu + w * 32 + cc * 4);
+    mx[0] = hmax2(mx[0], o.x); mx[1] = hmax2(mx[1], o.y); mx[2] = hmax2(mx[2], o.z); mx[3] = hmax2(mx[3], o.w);
   }
-  __syncthreads();
-  float s0 = 0.f, s1 = 0.f;
-  for (int t = warp; t < len; t += KV_WARPS) {
-    uint32_t u;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(kword(t)));
-    const float2 f = unpack_bf16x2(u);
-    // sum what the MMA will see (the bf16-rounded weights) so the normalisation is exact
-    const __nv_bfloat162 e2 = __floats2bfloat162_rn(__expf(f.x - m0), __expf(f.y - m1));
-    const float2 ef = __bfloat1622float2(e2);
-    s0 += ef.x;
-    s1 += ef.y;
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(kword(t)), "r"(*reinterpret_cast<const uint32_t*>(&e2)) : "memory");
+  __syncthreads();   // sred is reused for the sums
+  const float kL2E = 1.4426950408889634f;
+  const uint64_t l2e = f2_pack(kL2E, kL2E);
+  uint64_t nm[4], sm[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 m = unpack_bf16x2(mx[i]);
+    nm[i] = f2_pack(-m.x * kL2E, -m.y * kL2E);
+    sm[i] = 0ull;
   }
-  sred[warp * 64 + 2 * lane] = s0;
-  sred[warp * 64 + 2 * lane + 1] = s1;
+  for (int t = warp * 4 + rr; t < len; t += 4 * KV_WARPS) {
+    uint32_t u[4];
+    const uint32_t addr = kchunk(t);
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(addr));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a, b;
+      f2_unpack(f2_fma(f2_pack_u(u[i] << 16, u[i] & 0xffff0000u), l2e, nm[i]), a, b);
+      // sum what the MMA will see (the bf16-rounded weights) so the normalisation is exact
+      u[i] = pack_bf16x2(ex2_ftz(a), ex2_ftz(b));
+      sm[i] = f2_add(sm[i], f2_pack_u(u[i] << 16, u[i] & 0xffff0000u));
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
+  }
+  {
+    float ssum[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f2_unpack(sm[i], ssum[2 * i], ssum[2 * i + 1]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 8);
+      ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 16);
+    }
+    if (rr == 0) {
+      *reinterpret_cast<float4*>(sred + warp * 64 + cc * 8) = make_float4(ssum[0], ssum[1], ssum[2], ssum[3]);
+      *reinterpret_cast<float4*>(sred + warp * 64 + cc * 8 + 4) = make_float4(ssum[4], ssum[5], ssum[6], ssum[7]);
+    }
+  }
   __syncthreads();
   if (tid < 64) {
     float tot = 0.f;

@@ -355,6 +355,336 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// ======================================================================================================================
+// Resident-W variant (gemm_wres_kernel): the same CTA-pair MMA, but the pair keeps its 256 rows of W (all of K <= 512,
+// 128 KB per CTA) in shared memory for a whole run of row tiles and streams only A.
+//
+// Why: the L2 delivers ~6.3 KB/clk chip-wide (B300_MICROARCH.md, "LTS throughput cap"), i.e. ~43 B/clk per SM, while a
+// 256 x 256 tile with both operands streamed needs (256 + 256) x 16 x 2 B per 128-clk MMA = 64 B/clk per SM before the
+// epilogue moves a byte — the streamed kernel above tops out at ~63 % tensor-pipe active on the QKV projection
+// (profiles/r01c_ncu_full_summary.txt).  With W resident the operand stream is 32 B/clk per SM.  Tiles are ordered
+// column-block-major and cut into one contiguous range per pair, so a pair reloads W at most once or twice per launch.
+//
+// Shared memory: W 128 KB + 4 A stages x 16 KB + 8 epilogue warps x 2 sub-slabs x 2 KB (32 rows x 32 columns, 64-byte
+// swizzle) = 224 KB.  The fp16 residual of ST_RES_H does not fit a landing slab any more: each lane reads its own row
+// with 32-byte loads (one full sector per lane per instruction), prefetched half a tile ahead in registers.
+// ======================================================================================================================
+constexpr int WR_STAGES = 4;
+constexpr int WR_KB = 8;                                  // K <= 512
+constexpr int WR_W_BYTES = WR_KB * GS_B_BYTES;            // 128 KB
+constexpr int WR_SUB = 32 * 64;                           // 2 KB sub-slab
+constexpr int WR_EPI_BYTES = GS_EPI_WARPS * 2 * WR_SUB;   // 32 KB
+constexpr int WR_BAR_BYTES = (2 * WR_STAGES + 4 + 2) * 8 + 16;
+constexpr int WR_SMEM = WR_W_BYTES + WR_STAGES * GS_A_BYTES + WR_EPI_BYTES + WR_BAR_BYTES + 1024;
+static_assert(WR_SMEM <= 232448, "shared memory budget");
+
+// tanh-form GELU on a pair (same formula as gelu_fast_f): v (0.5 + 0.5 tanh(v (c0 + c1 v^2)))
+HIG_DEVICE uint64_t f2_gelu(uint64_t v) {
+  const uint64_t c0 = f2_pack(0.7978845608028654f, 0.7978845608028654f);
+  const uint64_t c1 = f2_pack(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f);
+  const uint64_t hf = f2_pack(0.5f, 0.5f);
+  const uint64_t arg = f2_mul(f2_fma(c1, f2_mul(v, v), c0), v);
+  float a0, a1;
+  f2_unpack(arg, a0, a1);
+  const uint64_t th = f2_pack(tanh_approx_f(a0), tanh_approx_f(a1));
+  const uint64_t hv = f2_mul(v, hf);
+  return f2_fma(hv, th, hv);
+}
+
+// 64 fp16 columns of this lane's row of the residual stream -> 32 registers (4 x 32-byte loads, L1 no-allocate)
+HIG_DEVICE void wr_load_res(const __half* p, bool ok, uint32_t (&r)[32]) {
+  if (ok) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(r[8 * i + 0]), "=r"(r[8 * i + 1]), "=r"(r[8 * i + 2]), "=r"(r[8 * i + 3]), "=r"(r[8 * i + 4]),
+                     "=r"(r[8 * i + 5]), "=r"(r[8 * i + 6]), "=r"(r[8 * i + 7])
+                   : "l"(p + 16 * i)
+                   : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = 0u;
+  }
+}
+
+// One 32-column chunk of this lane's accumulator row -> 64 bytes of a sub-slab (16-byte chunks 0..3 of the row,
+// XOR-swizzled with (row >> 1) & 3 as CU_TENSOR_MAP_SWIZZLE_64B expects).  res: 16 registers = the 32 fp16 residuals.
+template <int KIND, int ROFF>
+HIG_DEVICE void wres_chunk(const uint32_t (&r)[32], const uint32_t (&res)[32], uint32_t sub_row, int sw2, const StreamEpi& ep,
+                           int col0, uint64_t rstd2, uint64_t nmr2, uint64_t& s1, uint64_t& s2) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {  // 8 columns -> one 16-byte chunk
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 8 * g));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 8 * g + 4));
+    uint64_t v[4], bb[4];
+    bb[0] = f2_pack(b0.x, b0.y); bb[1] = f2_pack(b0.z, b0.w); bb[2] = f2_pack(b1.x, b1.y); bb[3] = f2_pack(b1.z, b1.w);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = f2_pack_u(r[8 * g + 2 * i], r[8 * g + 2 * i + 1]);
+    if (KIND == ST_LN_BF16) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(ep.wsum + col0 + 8 * g));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(ep.wsum + col0 + 8 * g + 4));
+      const uint64_t ww[4] = {f2_pack(w0.x, w0.y), f2_pack(w0.z, w0.w), f2_pack(w1.x, w1.y), f2_pack(w1.z, w1.w)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = f2_fma(rstd2, v[i], f2_fma(nmr2, ww[i], bb[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = f2_add(v[i], bb[i]);
+    }
+    if (KIND == ST_BF16_GELU) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = f2_gelu(v[i]);
+    }
+    const uint32_t addr = sub_row + ((g ^ sw2) << 4);
+    float lo[4], hi[4];
+    if (KIND == ST_RES_H) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 h = unpack_h2(res[ROFF + 4 * g + i]);
+        v[i] = f2_add(v[i], f2_pack(h.x, h.y));
+        s1 = f2_add(s1, v[i]);
+        s2 = f2_fma(v[i], v[i], s2);
+        f2_unpack(v[i], lo[i], hi[i]);
+      }
+      st_shared_u4(addr, pack_h2_sat(lo[0], hi[0]), pack_h2_sat(lo[1], hi[1]), pack_h2_sat(lo[2], hi[2]), pack_h2_sat(lo[3], hi[3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) f2_unpack(v[i], lo[i], hi[i]);
+      st_shared_u4(addr, pack_bf16x2(lo[0], hi[0]), pack_bf16x2(lo[1], hi[1]), pack_bf16x2(lo[2], hi[2]), pack_bf16x2(lo[3], hi[3]));
+    }
+  }
+}
+
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GS_THREADS, 1)
+gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __half* __restrict__ resid, int ldr, int M, int N, int K,
+                 StreamEpi ep, int f16_ops) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;
+  uint8_t* sA = sW + WR_W_BYTES;
+  uint8_t* sEpi = sA + WR_STAGES * GS_A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + WR_EPI_BYTES);
+  uint64_t* empty_bar = full_bar + WR_STAGES;
+  uint64_t* tfull_bar = empty_bar + WR_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* wfull_bar = tempty_bar + 2;
+  uint64_t* wfree_bar = wfull_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfree_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  const int m_tiles = (M + 2 * GS_BM - 1) / (2 * GS_BM);
+  const int n_tiles = N / GS_BN;                       // N % 256 == 0 (host-checked)
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (K + GS_BK - 1) / GS_BK;        // <= WR_KB (host-checked)
+  // column-block-major order, one contiguous range of tiles per pair (sizes differ by at most one)
+  const int lo = (int)((long long)num_tiles * pair / num_pairs);
+  const int hi = (int)((long long)num_tiles * (pair + 1) / num_pairs);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int s = 0; s < WR_STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + s, 1);
+      mbar_init(tempty_bar + s, 2 * GS_EPI_WARPS);
+    }
+    mbar_init(wfull_bar, 1);
+    mbar_init(wfree_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      auto load_w = [&](int n_blk) {
+        if (rank == 0) mbar_arrive_expect_tx(wfull_bar, 2 * k_blocks * GS_B_BYTES);
+        for (int kb = 0; kb < k_blocks; ++kb)
+          tma_load_2d_2cta(sW + kb * GS_B_BYTES, &tmB, wfull_bar, kb * GS_BK, n_blk * GS_BN + (int)rank * (GS_BN / 2));
+      };
+      int cur_n = -1;
+      uint32_t run = 0;
+      // W does not depend on the previous kernel: the whole resident block is requested BEFORE griddepcontrol.wait
+      if (lo < hi) { cur_n = lo / m_tiles; load_w(cur_n); run = 1; }
+      pdl_wait();
+      pdl_trigger();
+      uint32_t it = 0;
+      for (int tile = lo; tile < hi; ++tile) {
+        const int n_blk = tile / m_tiles;
+        const int m_blk = tile - n_blk * m_tiles;
+        if (n_blk != cur_n) {            // the MMAs that read the old block have completed (commit from the MMA warp)
+          mbar_wait(wfree_bar, (run - 1u) & 1u);
+          load_w(n_blk);
+          cur_n = n_blk;
+          ++run;
+        }
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t stage = it % WR_STAGES;
+          const uint32_t phase = (it / WR_STAGES) & 1u;
+          mbar_wait(empty_bar + stage, phase ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * GS_A_BYTES);
+          tma_load_2d_2cta(sA + stage * GS_A_BYTES, &tmA, full_bar + stage, kb * GS_BK, m_blk * 2 * GS_BM + (int)rank * GS_BM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = umma_idesc_f16kind(2 * GS_BM, GS_BN, f16_ops ? 0u : 1u);
+      uint32_t it = 0, lt = 0, runs = 0;
+      int cur_n = -1;
+      for (int tile = lo; tile < hi; ++tile, ++lt) {
+        const int n_blk = tile / m_tiles;
+        if (n_blk != cur_n) {
+          mbar_wait(wfull_bar, runs & 1u);
+          ++runs;
+          cur_n = n_blk;
+        }
+        const uint32_t as = lt & 1u;
+        const uint32_t aphase = (lt >> 1) & 1u;
+        mbar_wait(tempty_bar + as, aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * GS_BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t stage = it % WR_STAGES;
+          const uint32_t phase = (it / WR_STAGES) & 1u;
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * GS_A_BYTES));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sW + kb * GS_B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GS_BK / 16; ++k)
+            umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta_mc(empty_bar + stage, 0b11);
+        }
+        umma_commit_2cta_mc(tfull_bar + as, 0b11);
+        if (tile + 1 < hi && (tile + 1) / m_tiles != cur_n) umma_commit_2cta_mc(wfree_bar, 0b11);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue warps (2..9, both CTAs) =================
+    const int ew = warp - 2;
+    const int q = warp & 3;          // TMEM lane quarter this warp may read (hardware rule: warp id % 4)
+    const int ch = ew >> 2;          // column half of the tile
+    uint8_t* sub0 = sEpi + ew * 2 * WR_SUB;
+    const int sw2 = (lane >> 1) & 3;
+    const uint32_t row_s0 = smem_u32(sub0) + lane * 64;
+    const uint32_t row_s1 = row_s0 + WR_SUB;
+    pdl_wait();   // statistics / residual we read and the output we overwrite belong to the previous kernels
+    uint32_t res0[32], res1[32];
+    if (KIND == ST_RES_H) {
+      if (lo < hi) {
+        const int n_blk = lo / m_tiles, m_blk = lo - n_blk * m_tiles;
+        const int row = m_blk * 2 * GS_BM + (int)rank * GS_BM + q * 32 + lane;
+        wr_load_res(resid + (size_t)min(row, M - 1) * ldr + n_blk * GS_BN + ch * (GS_BN / 2), row < M, res0);
+      }
+    }
+    uint32_t lt = 0;
+    for (int tile = lo; tile < hi; ++tile, ++lt) {
+      const int n_blk = tile / m_tiles;
+      const int m_blk = tile - n_blk * m_tiles;
+      const uint32_t as = lt & 1u;
+      const uint32_t aphase = (lt >> 1) & 1u;
+      const int row0 = m_blk * 2 * GS_BM + (int)rank * GS_BM + q * 32;
+      const int gc0 = n_blk * GS_BN + ch * (GS_BN / 2);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GS_BN + ch * (GS_BN / 2);
+      float rstd = 0.f, nmr = 0.f;
+      if (KIND == ST_LN_BF16) {
+        const int row = min(row0 + lane, M - 1);
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(ep.stats_in + (size_t)row * 8));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(ep.stats_in + (size_t)row * 8 + 4));
+        const float sum = (p0.x + p0.z) + (p1.x + p1.z);
+        const float ssq = (p0.y + p0.w) + (p1.y + p1.w);
+        const float mu = sum * ep.inv_width;
+        const float var = fmaxf(fmaf(ssq, ep.inv_width, -mu * mu), 0.f);
+        rstd = rsqrtf(var + ep.ln_eps);
+        nmr = -mu * rstd;
+      }
+      const uint64_t rstd2 = f2_pack(rstd, rstd), nmr2 = f2_pack(nmr, nmr);
+      uint64_t s1 = 0ull, s2 = 0ull;
+      if (KIND == ST_RES_H) {   // second half of this tile's residual: in flight while the MMAs finish
+        const int row = row0 + lane;
+        wr_load_res(resid + (size_t)min(row, M - 1) * ldr + gc0 + 64, row < M, res1);
+      }
+
+      mbar_wait(tfull_bar + as, aphase);
+      tc_fence_after();
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(taddr, ra);
+      tmem_ld_32x32(taddr + 32, rb);
+      tmem_ld_wait();
+      // ---- columns 0..31 -> sub-slab 0, 32..63 -> sub-slab 1 (each store group is waited for two chunks later)
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      wres_chunk<KIND, 0>(ra, res0, row_s0, sw2, ep, gc0, rstd2, nmr2, s1, s2);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { tma_store_2d(&tmC, reinterpret_cast<const void*>(sub0), gc0, row0); bulk_commit(); bulk_wait_read<1>(); }
+      __syncwarp();
+      wres_chunk<KIND, 16>(rb, res0, row_s1, sw2, ep, gc0 + 32, rstd2, nmr2, s1, s2);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { tma_store_2d(&tmC, reinterpret_cast<const void*>(sub0 + WR_SUB), gc0 + 32, row0); bulk_commit(); }
+      if (KIND == ST_RES_H) {   // first half of the NEXT tile's residual
+        if (tile + 1 < hi) {
+          const int nn = (tile + 1) / m_tiles, nm = (tile + 1) - nn * m_tiles;
+          const int row = nm * 2 * GS_BM + (int)rank * GS_BM + q * 32 + lane;
+          wr_load_res(resid + (size_t)min(row, M - 1) * ldr + nn * GS_BN + ch * (GS_BN / 2), row < M, res0);
+        }
+      }
+      // ---- columns 64..127; the accumulator buffer goes back to the MMA warp once they are in registers
+      tmem_ld_32x32(taddr + 64, ra);
+      tmem_ld_32x32(taddr + 96, rb);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive_cluster(tempty_bar + as, 0); bulk_wait_read<1>(); }
+      __syncwarp();
+      wres_chunk<KIND, 0>(ra, res1, row_s0, sw2, ep, gc0 + 64, rstd2, nmr2, s1, s2);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { tma_store_2d(&tmC, reinterpret_cast<const void*>(sub0), gc0 + 64, row0); bulk_commit(); bulk_wait_read<1>(); }
+      __syncwarp();
+      wres_chunk<KIND, 16>(rb, res1, row_s1, sw2, ep, gc0 + 96, rstd2, nmr2, s1, s2);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { tma_store_2d(&tmC, reinterpret_cast<const void*>(sub0 + WR_SUB), gc0 + 96, row0); bulk_commit(); }
+      if (KIND == ST_RES_H) {
+        // deterministic row statistics: partial (n_blk, ch) of row (sum, sum of squares) — summed by the consumer
+        if (ep.stats_out != nullptr && row0 + lane < M) {
+          float a0, a1, b0, b1;
+          f2_unpack(s1, a0, a1);
+          f2_unpack(s2, b0, b1);
+          *reinterpret_cast<float2*>(ep.stats_out + (size_t)(row0 + lane) * 8 + (n_blk * 2 + ch) * 2) = make_float2(a0 + a1, b0 + b1);
+        }
+      }
+    }
+    if (lane == 0) bulk_wait<0>();   // all stores of this warp have completed before the CTA may retire
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<512>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 int get_tmap_2b(const void* ptr, int rows, int cols, int ld, int box_rows, int is_f16, CUtensorMap* out);  // gemm_tcgen05.cu
 int device_num_sms();
@@ -380,6 +710,35 @@ static int launch_stream(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("stream gemm launch: ") + cudaGetErrorString(e));
   count_launch();
   return HIG_OK;
+}
+
+template <int KIND>
+static int launch_wres(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const void* resid, int ldr,
+                       int M, int N, int K, const StreamEpi& ep, int f16_ops, cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm_wres_kernel<KIND>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM);
+    if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("cudaFuncSetAttribute(resident-W gemm): ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int m_tiles = (M + 2 * GS_BM - 1) / (2 * GS_BM);
+  int pairs = m_tiles * (N / GS_BN);
+  const int max_pairs = device_num_sms() / 2;
+  if (pairs > max_pairs) pairs = max_pairs;
+  if (const char* pe = getenv("HIG_GS_PAIRS")) { const int v = atoi(pe); if (v > 0 && v < pairs) pairs = v; }  // experiment knob
+  cudaError_t e = launch_pdl(kern, dim3(2 * pairs), dim3(GS_THREADS), WR_SMEM, stream, tmA, tmB, tmC,
+                             static_cast<const __half*>(resid), ldr, M, N, K, ep, f16_ops);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("resident-W gemm launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+// HIG_WRES=0 routes everything through the streamed kernel (A/B timing); default: resident-W wherever it applies
+static bool wres_enabled() {
+  const char* e = getenv("HIG_WRES");
+  return !(e && e[0] == '0');
 }
 
 int gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op_dtype, int M, int N, int K,
@@ -413,6 +772,19 @@ int gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op
   if (rc) return rc;
   rc = get_tmap_2b(W, N, K, ldw, 128, tm_f16, &tmB);
   if (rc) return rc;
+  // resident-W kernel: whole K in shared memory, full 256-column blocks; the residual is read with 32-byte loads
+  const bool wres = wres_enabled() && K <= WR_KB * GS_BK && (N % GS_BN) == 0 &&
+                    (kind != ST_RES_H || (reinterpret_cast<uintptr_t>(out) & 31) == 0);
+  if (wres) {
+    rc = get_tmap_2b(out, M, N, ldo, 32, (kind == ST_RES_H ? 1 : 0) | 2, &tmC);   // 32 x 32 boxes, 64-byte swizzle
+    if (rc) return rc;
+    switch (kind) {
+      case ST_BF16: return launch_wres<ST_BF16>(tmA, tmB, tmC, nullptr, 0, M, N, K, ep, f16, stream);
+      case ST_BF16_GELU: return launch_wres<ST_BF16_GELU>(tmA, tmB, tmC, nullptr, 0, M, N, K, ep, f16, stream);
+      case ST_RES_H: return launch_wres<ST_RES_H>(tmA, tmB, tmC, out, ldo, M, N, K, ep, f16, stream);
+      default: return launch_wres<ST_LN_BF16>(tmA, tmB, tmC, nullptr, 0, M, N, K, ep, f16, stream);
+    }
+  }
   rc = get_tmap_2b(out, M, N, ldo, 32, kind == ST_RES_H, &tmC);
   if (rc) return rc;
   switch (kind) {

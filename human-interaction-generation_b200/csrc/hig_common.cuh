@@ -80,6 +80,42 @@ HIG_DEVICE float2 unpack_bf16x2(uint32_t u) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2) for the instruction-issue-bound epilogues and attention tails
+// ----------------------------------------------------------------------------------------------
+HIG_DEVICE uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+HIG_DEVICE uint64_t f2_pack_u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+HIG_DEVICE void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+HIG_DEVICE uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+HIG_DEVICE uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+HIG_DEVICE uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// 2^x, flush-to-zero: one MUFU, none of the denormal range scaling __expf / exp2f wrap around it
+HIG_DEVICE float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// ----------------------------------------------------------------------------------------------
 // programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
 // (prologue: barrier init, TMEM allocation, tensor-map prefetch, parameter staging) while its predecessor drains;
 // pdl_wait() blocks until the predecessor grid has completed and its writes are visible.  Both are no-ops for
