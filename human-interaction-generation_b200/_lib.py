@@ -40,7 +40,9 @@ SIGNATURES = {
     "hig_timestep_embed": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_pack_motion": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_ddpm_step": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ull,
-                      c_void_p, c_int, c_int, c_void_p, c_void_p],
+                      c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "hig_recover_joints": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                           c_void_p, c_void_p],
     "hig_q_sample": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
     # training path
     "hig_gemm_bf16_splitk": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p],

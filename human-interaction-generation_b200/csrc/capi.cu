@@ -121,10 +121,17 @@ int hig_pack_motion(const float* x, int S, int T, int C, int ld_out, void* out, 
 }
 
 int hig_ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
-                  int n_steps, int S, int T, int C, unsigned long long seed, void* packed, int ld_packed,
-                  int packed_dtype, long long* t_next, void* stream) {
-  return hig::ddpm_step(x, eps, ld_eps, noise, t, coef, n_steps, S, T, C, seed, packed, ld_packed, packed_dtype,
+                  int n_steps, int S, int T, int C, unsigned long long seed, const unsigned long long* seed_dev, void* packed,
+                  int ld_packed, int packed_dtype, long long* t_next, void* stream) {
+  return hig::ddpm_step(x, eps, ld_eps, noise, t, coef, n_steps, S, T, C, seed, seed_dev, packed, ld_packed, packed_dtype,
                         t_next, static_cast<cudaStream_t>(stream));
+}
+
+int hig_recover_joints(const float* x, int S, int T, int C, int init_row, const float* mean, const float* std_,
+                       const float* init_mean, const float* init_std, const int* length, int joints_num, float* joints,
+                       void* stream) {
+  return hig::recover_joints(x, S, T, C, init_row, mean, std_, init_mean, init_std, length, joints_num, joints,
+                             static_cast<cudaStream_t>(stream));
 }
 
 int hig_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,

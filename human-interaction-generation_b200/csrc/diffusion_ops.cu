@@ -108,7 +108,8 @@ template <typename TPack>
 __global__ void __launch_bounds__(256)
 ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, int ld_eps, const float* __restrict__ noise,
                  const long long* __restrict__ t, const float* __restrict__ coef, int n_steps, int S, int T, int C,
-                 unsigned long long seed, TPack* __restrict__ packed, int ld_packed) {
+                 unsigned long long seed, const unsigned long long* __restrict__ seed_dev, TPack* __restrict__ packed,
+                 int ld_packed) {
   const long long per_seq = (long long)T * C;
   const long long total = (long long)S * per_seq;
   const long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -121,7 +122,9 @@ ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, int ld_ep
     for (int j = 0; j < 4; ++j)
       if (base + j < total) z[j] = noise[base + j];
   } else {
-    // counter = (element-group index, timestep of the first element's sequence), key = seed
+    // counter = (element-group index, timestep of the first element's sequence), key = seed; a seed kept in device
+    // memory lets one captured graph serve every sampling call (the host rewrites 8 bytes instead of re-capturing)
+    if (seed_dev != nullptr) seed = *seed_dev;
     const int s0 = (int)((unsigned)base / (unsigned)per_seq);
     const long long ts = t[s0];
     const uint4 ctr = make_uint4((uint32_t)(base >> 2), (uint32_t)((base >> 2) >> 32), (uint32_t)ts, 0x48494742u);
@@ -165,8 +168,8 @@ __global__ void advance_t_kernel(const long long* __restrict__ t, long long* __r
 }
 
 int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
-              int n_steps, int S, int T, int C, unsigned long long seed, void* packed, int ld_packed, int packed_dtype,
-              long long* t_next, cudaStream_t stream) {
+              int n_steps, int S, int T, int C, unsigned long long seed, const unsigned long long* seed_dev, void* packed,
+              int ld_packed, int packed_dtype, long long* t_next, cudaStream_t stream) {
   if (!x || !eps || !t || !coef || S <= 0 || T <= 0 || C <= 0 || n_steps <= 0)
     return set_error(HIG_ERR_INVALID, "ddpm_step: bad arguments");
   if (packed && ld_packed < C + 4) return set_error(HIG_ERR_INVALID, "ddpm_step: ld_packed < C+4");
@@ -175,9 +178,9 @@ int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const 
   const int blocks = (int)(((total + 3) / 4 + 255) / 256);
   if (packed && packed_dtype == HIG_BF16)
     launch_pdl(ddpm_step_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, x, eps, ld_eps, noise, t, coef,
-               n_steps, S, T, C, seed, (__nv_bfloat16*)packed, ld_packed);
+               n_steps, S, T, C, seed, seed_dev, (__nv_bfloat16*)packed, ld_packed);
   else
-    ddpm_step_kernel<float><<<blocks, 256, 0, stream>>>(x, eps, ld_eps, noise, t, coef, n_steps, S, T, C, seed,
+    ddpm_step_kernel<float><<<blocks, 256, 0, stream>>>(x, eps, ld_eps, noise, t, coef, n_steps, S, T, C, seed, seed_dev,
                                                         (float*)packed, ld_packed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("ddpm_step launch: ") + cudaGetErrorString(e));

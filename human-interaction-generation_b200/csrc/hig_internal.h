@@ -67,8 +67,12 @@ int timestep_embed(const long long* t, const float* freqs, int S, int half, void
 int pack_motion(const float* x, int S, int T, int C, int ld_out, void* out, int out_dtype, cudaStream_t stream);
 
 int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
-              int n_steps, int S, int T, int C, unsigned long long seed, void* packed, int ld_packed, int packed_dtype,
-              long long* t_next, cudaStream_t stream);
+              int n_steps, int S, int T, int C, unsigned long long seed, const unsigned long long* seed_dev, void* packed,
+              int ld_packed, int packed_dtype, long long* t_next, cudaStream_t stream);
+
+int recover_joints(const float* x, int S, int T, int C, int init_row, const float* mean, const float* stdv,
+                   const float* init_mean, const float* init_std, const int* length, int joints_num, float* joints,
+                   cudaStream_t stream);
 
 int q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac, const float* sqrt_1mac,
              int S, int TC, float* out, cudaStream_t stream);

@@ -54,6 +54,7 @@ class DenoiserEngine:
         self._packed = None
         self._packed_T = None
         self._packed_key = None
+        self.packed_generation = 0   # bumped whenever the operand copies are rebuilt (captured graphs go stale)
         self._ws = {}
         self._text_cache = None
         # product path: projections with the TMA-staged epilogue, pre-attention LayerNorms folded into them
@@ -125,6 +126,7 @@ class DenoiserEngine:
             half = self.D // 2
             W["freqs"] = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(dev)
         self._packed, self._packed_key = W, key
+        self.packed_generation += 1
         self._packed_T = None
         self._text_cache = None
         return W

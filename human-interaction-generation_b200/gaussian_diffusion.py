@@ -221,7 +221,8 @@ class GaussianDiffusion:
             if st is None or st["ws"] is not ws or st["a_text"].shape != a_text_new.shape:
                 st = {"ws": ws, "x": th.empty(S, T, C, device=device), "t": th.empty(S, device=device, dtype=th.long),
                       "z": th.empty(S, T, C, device=device) if noise_seq is not None else None,
-                      "xfp": th.empty(S, eng.E, device=device), "a_text": th.empty_like(a_text_new), "graph": None}
+                      "xfp": th.empty(S, eng.E, device=device), "a_text": th.empty_like(a_text_new), "graph": None,
+                      "graph_key": None, "seed": th.zeros(1, device=device, dtype=th.long)}
                 if len(self._fast_state) > 4:
                     self._fast_state.clear()
                 self._fast_state[key] = st
@@ -232,17 +233,30 @@ class GaussianDiffusion:
             st["t"].fill_(self.num_timesteps - 1)
             ops.pack_motion(st["x"], ws["xa"])
             coef = self._tables(device)["coef"]
+            # The Philox key lives in device memory, the timestep too (decremented by the posterior kernel), and every
+            # operand is a fixed buffer of `st` / `ws`: ONE captured graph serves every later call of this shape.  (torch's
+            # graph capture costs a gc.collect() + empty_cache() + instantiation — 0.2 s per call, sometimes seconds.)
             seed = self.seed
             self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+            st["seed"].fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
 
             import os as _os
-            persist = _os.environ.get("HIG_L2_PERSIST", "1") != "0"
+            persist = _os.environ.get("HIG_L2_PERSIST", "0") != "0"   # measured: no gain with the 26 MB fp16 stream
 
             def step():
                 if persist:
                     ops.l2_persist(ws["xres"])
                 eps = eng.run_packed(ws, st["t"], st["xfp"], st["a_text"], S, T)
-                ops.ddpm_step(st["x"], eps, st["t"], coef, noise=st["z"], seed=seed, packed=ws["xa"], t_next=st["t"])
+                ops.ddpm_step(st["x"], eps, st["t"], coef, noise=st["z"], seed_dev=st["seed"], packed=ws["xa"],
+                              t_next=st["t"])
+
+            # a cached graph is valid while the packed weights, the schedule tables and the kernel-selection knobs it
+            # was recorded with are the ones in force
+            eng.packed()
+            graph_key = (eng.packed_generation, coef.data_ptr(), self.num_timesteps,
+                         tuple(_os.environ.get(k) for k in ("HIG_WRES", "HIG_L2_PERSIST", "HIG_PDL", "HIG_GS_PAIRS")))
+            if st["graph_key"] != graph_key:
+                st["graph"], st["graph_key"] = None, graph_key
 
             steps = range(self.num_timesteps)
             if progress:
@@ -251,14 +265,12 @@ class GaussianDiffusion:
                     steps = tqdm(steps)
                 except Exception:
                     pass
-            # The Philox seed is a kernel argument frozen into the graph: production runs capture once per call,
-            # injected-noise (parity) runs keep the graph across calls.
-            graph = st["graph"] if noise_seq is not None else None
+            graph = st["graph"] if use_graph else None
             launches, c_prev = 0, _lib.launch_count()
             for k in steps:
                 if noise_seq is not None:
                     st["z"].copy_(noise_seq[k])
-                if k == 0 or not use_graph:
+                if not use_graph or (graph is None and k == 0):
                     step()                      # eager: also performs every lazy initialisation before capture
                     c_now = _lib.launch_count()
                     launches, c_prev = launches + (c_now - c_prev), c_now
@@ -267,8 +279,7 @@ class GaussianDiffusion:
                 if graph is None:
                     graph = self._capture(step)
                     c_prev = _lib.launch_count()   # capture records kernels, it does not run them
-                    if noise_seq is not None:
-                        st["graph"] = graph
+                    st["graph"] = graph
                 graph.replay()
                 launches += st["nodes"]            # one replay launches every recorded kernel node
             # kernels of this library launched on the GPU during this call (eager + graph replays)

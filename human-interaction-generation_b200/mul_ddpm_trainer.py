@@ -97,6 +97,27 @@ class DDPMMulTrainer(object):
             all_output.extend([output[i], output[B + i]] for i in range(B))
         return all_output
 
+    def generate_joints(self, caption1, caption2, m_lens, dim_pose, mean=None, std=None, init_mean=None, init_std=None,
+                        joints_num=22, batch_size=512):
+        """caption -> 3-D joints without leaving the GPU: generate_batch followed by the fused de-normalisation +
+        recover_from_ric2 kernel (what tools/visualization.py:143-155 + plot_t2m2 :54-56 do per sample on the CPU).
+        Returns a list of [joints1, joints2] per pair, each [m_len-1, joints_num, 3]."""
+        from .motion_process import joints_from_samples
+        N = len(caption1)
+        self.encoder.eval()
+        out = []
+        for lo in range(0, N, batch_size):
+            hi = min(lo + batch_size, N)
+            lens = torch.as_tensor(m_lens[lo:hi]).reshape(-1)
+            x = self.generate_batch(caption1[lo:hi], caption2[lo:hi], lens, dim_pose)
+            B, T = hi - lo, x.shape[1]
+            l2 = torch.cat([lens, lens]).clamp(max=T)
+            j = joints_from_samples(x, mean, std, init_mean, init_std, length=l2, joints_num=joints_num)
+            for i in range(B):
+                n = max(int(l2[i]) - 1, 0)
+                out.append([j[i, :n], j[B + i, :n]])
+        return out
+
     # ------------------------------------------------------------------------------------------ training (:91-162, :223-256)
     def forward(self, batch_data, eval_mode=False):
         if not self.multi:

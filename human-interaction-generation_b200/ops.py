@@ -200,8 +200,9 @@ def pack_motion(x, out):
     return out
 
 
-def ddpm_step(x, eps, t, coef, noise=None, seed=0, packed=None, t_next=None):
-    """In-place x <- posterior sample; eps [S*T, ld_eps] fp32 view, coef fp32 [5, n_steps]."""
+def ddpm_step(x, eps, t, coef, noise=None, seed=0, packed=None, t_next=None, seed_dev=None):
+    """In-place x <- posterior sample; eps [S*T, ld_eps] fp32 view, coef fp32 [5, n_steps].  seed_dev: int64 device
+    scalar holding the Philox key (overrides `seed`; lets a captured graph be reused with a fresh seed)."""
     lib = _lib.load()
     S, T, C = x.shape
     if x.dtype != torch.float32 or not x.is_contiguous():
@@ -210,11 +211,34 @@ def ddpm_step(x, eps, t, coef, noise=None, seed=0, packed=None, t_next=None):
         raise ValueError("hig_b200.ddpm_step: noise must be contiguous fp32")
     eps2 = eps.reshape(S * T, -1) if eps.dim() == 3 else eps
     rc = lib.hig_ddpm_step(_ptr(x), _ptr(eps2), eps2.stride(0), _ptr(noise), _ptr(t), _ptr(coef), coef.shape[1],
-                           S, T, C, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(packed),
+                           S, T, C, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(seed_dev), _ptr(packed),
                            packed.stride(0) if packed is not None else 0,
                            _dt(packed) if packed is not None else F32, _ptr(t_next), _stream())
     _lib.check(rc, "hig_ddpm_step")
     return x
+
+
+def recover_joints(x, mean=None, std=None, init_mean=None, init_std=None, length=None, joints_num=22, init_row=0,
+                   out=None):
+    """x fp32 [S,T,C] on CUDA -> joints fp32 [S,T-1,joints_num,3] (hig_recover_joints); init_row 0 or -1 / T-1."""
+    lib = _lib.load()
+    if x.dim() != 3 or x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("hig_b200.recover_joints: x must be contiguous fp32 [S, T, C]")
+    S, T, C = x.shape
+    if init_row < 0:
+        init_row += T
+    f = lambda v, n: None if v is None else torch.as_tensor(v, dtype=torch.float32).to(x.device).contiguous().reshape(n)
+    mean, std, init_mean, init_std = f(mean, C), f(std, C), f(init_mean, 4), f(init_std, 4)
+    if length is not None:
+        length = torch.as_tensor(length).reshape(-1).to(device=x.device, dtype=torch.int32).contiguous()
+        if length.numel() != S:
+            raise ValueError(f"hig_b200.recover_joints: length must have {S} entries")
+    if out is None:
+        out = torch.empty(S, max(T - 1, 0), joints_num, 3, device=x.device, dtype=torch.float32)
+    rc = lib.hig_recover_joints(_ptr(x), S, T, C, init_row, _ptr(mean), _ptr(std), _ptr(init_mean), _ptr(init_std),
+                                _ptr(length), joints_num, _ptr(out), _stream())
+    _lib.check(rc, "hig_recover_joints")
+    return out
 
 
 def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, out=None):

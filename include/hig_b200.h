@@ -127,12 +127,25 @@ int hig_pack_motion(const float* x, int S, int T, int C, int ld_out, void* out, 
 /* one reverse-diffusion update, in place on x: p_sample + p_mean_variance (EPSILON / FIXED_SMALL,
  * clip_denoised=False) — models/gaussian_diffusion.py:606-666,443-537.  coef = fp32 [5][n_steps]
  * {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2,
- * exp(0.5*posterior_log_variance_clipped)}.  noise nullable -> Philox4x32-10(seed, t, index) + Box-Muller.
+ * exp(0.5*posterior_log_variance_clipped)}.  noise nullable -> Philox4x32-10(seed, t, index) + Box-Muller
+ * (replaces th.randn_like, :657); seed_dev nullable: when given, the key is read from device memory instead of `seed`,
+ * so a CUDA graph holding this launch can be replayed for a new sample after an 8-byte update.
  * packed nullable: also writes the next step's pack_motion operand.  t_next nullable: t_next[s] = t[s]-1
  * (may alias t; issued as a trailing launch). */
 int hig_ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
-                  int n_steps, int S, int T, int C, unsigned long long seed, void* packed, int ld_packed,
-                  int packed_dtype, long long* t_next, void* stream);
+                  int n_steps, int S, int T, int C, unsigned long long seed, const unsigned long long* seed_dev, void* packed,
+                  int ld_packed, int packed_dtype, long long* t_next, void* stream);
+
+/* Sampled motion -> 3-D joints in one launch: tools/visualization.py:149-155 (x[1:]*std+mean, x[0,:4]*init_std+init_mean)
+ * followed by utils/motion_process.py recover_from_ric2 (:418-456; recover_root_rot_pos :362-381, qrot/qinv
+ * utils/quaternion.py:16-20,54-73).  x fp32 [S,T,C] contiguous, persons stacked on dim 0 (each sequence is processed on
+ * its own, as the reference does); init_row = 0 (the sampler's layout: init state in row 0) or T-1 (recover_from_ric2's
+ * layout: init state moved to the end); mean/std [C] and init_mean/init_std [4] nullable pairs (NULL = already
+ * de-normalised); length int32 [S] nullable: rows >= length[s] are padding, their joints are written as zeros.
+ * joints fp32 [S, T-1, joints_num, 3].  The two prefix sums accumulate in fp64 like torch's CPU cumsum. */
+int hig_recover_joints(const float* x, int S, int T, int C, int init_row, const float* mean, const float* std_,
+                       const float* init_mean, const float* init_std, const int* length, int joints_num, float* joints,
+                       void* stream);
 
 /* x_t = sqrt(abar_t) x0 + sqrt(1 - abar_t) noise — GaussianDiffusion.q_sample (models/gaussian_diffusion.py:399-417) */
 int hig_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE — generate tests/golden/*.npz by running the REAL reference (imported read-only from
 /root/reference/codes behind oracle/ref_shims.py) on seeded weights/inputs from oracle/weights.py.
 
-Run in the build container only:   python oracle/make_golden.py
+Run in the build container only:   python oracle/make_golden.py [case ...]   (no argument = every case)
 The fixtures are small (inputs are re-derived from seeds at test time; only outputs are stored).
 """
 import os
@@ -27,7 +27,33 @@ CASES = {
                           n_text=77),
     "loop": dict(layers=2, S=2, T=16, seed=14, lengths=[16, 11], mode="text", n_text=5, steps=50),
     "train": dict(layers=2, S=4, T=12, seed=15, lengths=[12, 7, 12, 7], mode="text", n_text=3),
+    # sample -> joints post-processing (tools/visualization.py:149-155 + utils/motion_process.recover_from_ric2)
+    "joints": dict(S=6, T=24, seed=16),
 }
+
+
+def joints_golden(c):
+    """Runs the reference's recover_from_ric2 on seeded 'samples' de-normalised exactly as tools/visualization.py
+    does (:149-155 is inline script code, restated here statement by statement around the imported function)."""
+    import importlib
+    ref_shims.import_reference()
+    mp = importlib.import_module("utils.motion_process")
+    x, mean, std, init_mean, init_std = weights.make_joint_inputs(c["seed"], c["S"], c["T"])
+    B = c["S"] // 2
+    j1, j2 = [], []
+    for i in range(B):
+        motion1, motion2 = x[i].numpy().copy(), x[i + B].numpy().copy()
+        motion1[1:] = motion1[1:] * std + mean
+        motion2[1:] = motion2[1:] * std + mean
+        motion1[0, :4] = motion1[0, :4] * init_std + init_mean
+        motion2[0, :4] = motion2[0, :4] * init_std + init_mean
+        motion1 = np.concatenate([motion1[1:], motion1[0][None, :]], axis=0)
+        motion2 = np.concatenate([motion2[1:], motion2[0][None, :]], axis=0)
+        a, b = mp.recover_from_ric2(torch.from_numpy(motion1).unsqueeze(0).float(),
+                                    torch.from_numpy(motion2).unsqueeze(0).float(), 22)
+        j1.append(a.squeeze(0).numpy())
+        j2.append(b.squeeze(0).numpy())
+    return {"joints": np.stack(j1 + j2)}      # [S, T-1, 22, 3], persons stacked like the sampler's batch
 
 
 def build_reference_model(it, layers, wseed=0):
@@ -50,7 +76,15 @@ def main():
     it, gd = ref_shims.import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
+        if name == "joints":
+            out = {"cfg": np.array(repr(c)), **joints_golden(c)}
+            np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+            print(name, {k: getattr(v, "shape", None) for k, v in out.items()})
+            continue
         m, sd = build_reference_model(it, c["layers"])
         inp = weights.make_inputs(c["seed"], c["S"], c["T"], n_text=c.get("n_text", 1), lengths=c["lengths"],
                                   timesteps=c.get("timesteps"))

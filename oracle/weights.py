@@ -118,3 +118,18 @@ def make_noise(seed, steps, S, T, C=263):
     """[steps+1, S, T, C]: index 0 is x_T, index 1+k the noise drawn at the k-th reverse step."""
     rs = np.random.RandomState(seed)
     return torch.from_numpy(rs.standard_normal((steps + 1, S, T, C)).astype(np.float32))
+
+
+def make_joint_inputs(seed, S, T, C=263):
+    """Seeded stand-ins for a sampled batch and the dataset statistics of tools/visualization.py:103-111 (mean/std of
+    the 263 motion features, init_mean/init_std of the 4 init-state features; the real files are not available
+    offline).  Returns (x [S,T,C] torch fp32, mean [C], std [C], init_mean [4], init_std [4]) — numpy float32."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(S, T, C, generator=g)
+    mean = (torch.randn(C, generator=g) * 0.3).numpy()
+    std = (torch.rand(C, generator=g) * 0.5 + 0.5).numpy()
+    # yaw velocity is small in the data (radians per frame); keep the integrated yaw within a few turns
+    mean[0], std[0] = 0.01, 0.05
+    init_mean = (torch.randn(4, generator=g) * 0.5).numpy()
+    init_std = (torch.rand(4, generator=g) * 0.5 + 0.5).numpy()
+    return x, mean, std, init_mean, init_std

@@ -1,10 +1,14 @@
 """Kernel-level parity on the B200: every C-ABI entry point against a plain PyTorch fp32 statement of the op it
 replaces (tolerances written per test).  Model-level parity against the oracle lives in test_parity_gpu.py."""
 import math
+import os
+import sys
 
 import pytest
 import torch
 import torch.nn.functional as F
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))  # the checker
 
 pytestmark = pytest.mark.gpu
 
@@ -448,6 +452,94 @@ def test_ddpm_step_philox_noise_statistics(cuda):
     x4 = torch.ones_like(x)
     ops.ddpm_step(x4, eps, torch.zeros_like(t), coef, seed=1)  # t == 0: no noise
     assert torch.equal(x4, (coef[2][0] * (coef[0][0] * torch.ones_like(x))) + coef[3][0] * torch.ones_like(x))
+
+
+def test_ddpm_step_device_seed_matches_immediate_seed(cuda):
+    """The Philox key read from device memory (graph-reusable) gives the same draw as the kernel-argument key."""
+    ops = _ops()
+    S, T, C, n = 4, 33, 263, 1000
+    coef, _, _ = _coef_tables(n)
+    coef = coef.to(cuda)
+    eps = torch.zeros(S, T, C, device=cuda)
+    t = torch.full((S,), 321, device=cuda)
+    for seed in (1234, (1 << 63) + 12345, (1 << 64) - 1):
+        a, b = torch.zeros(S, T, C, device=cuda), torch.zeros(S, T, C, device=cuda)
+        ops.ddpm_step(a, eps, t, coef, seed=seed)
+        sd = torch.tensor([seed - (1 << 64) if seed >= (1 << 63) else seed], device=cuda, dtype=torch.long)
+        ops.ddpm_step(b, eps, t, coef, seed=99, seed_dev=sd)
+        assert torch.equal(a, b) and a.abs().sum() > 0
+
+
+# ------------------------------------------------------------------------------------------------ sample -> joints
+def _joint_case(cuda):
+    import ast
+    import os
+    import sys
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import weights
+    d = np.load(os.path.join(root, "tests", "golden", "joints.npz"))
+    cfg = ast.literal_eval(str(d["cfg"]))
+    x, mean, std, im, isd = weights.make_joint_inputs(cfg["seed"], cfg["S"], cfg["T"])
+    return x, mean, std, im, isd, torch.from_numpy(d["joints"])
+
+
+def test_recover_joints_matches_reference_golden(cuda):
+    """hig_recover_joints against the REAL reference's recover_from_ric2 output (tests/golden/joints.npz).  Prefix sums
+    are fp64-accumulated on both sides and qrot is evaluated unfused in the reference order, so the only slack needed is
+    the last ulp of cosf/sinf: 2e-5 absolute on coordinates of magnitude <= 33 (6e-7 relative)."""
+    from hig_b200 import motion_process as mp
+    x, mean, std, im, isd, gold = _joint_case(cuda)
+    j = mp.joints_from_samples(x.to(cuda), mean, std, im, isd)
+    assert j.shape == gold.shape
+    err = (j.cpu() - gold).abs().max().item()
+    print(f"joints vs reference golden: max abs err {err:.2e} (max |coord| {gold.abs().max():.1f}), "
+          f"bit-exact fraction {(j.cpu() == gold).float().mean():.4f}")
+    assert err <= 2e-5
+    assert mp.mpjpe(j.cpu(), gold).item() < 1e-5
+
+
+def test_recover_joints_layouts_lengths_and_errors(cuda):
+    import sys
+    import numpy as np
+    from hig_b200 import motion_process as mp
+    import joints_oracle as JO
+    ops = _ops()
+    x, mean, std, im, isd, gold = _joint_case(cuda)
+    S, T, C = x.shape
+    # recover_from_ric2's own layout (de-normalised, init-state row last), same name and argument meaning
+    data = np.stack([JO.denormalise(s, mean, std, im, isd) for s in x.numpy()])
+    d = torch.from_numpy(data).to(cuda)
+    j1, j2 = mp.recover_from_ric2(d[:S // 2], d[S // 2:], 22)
+    assert (torch.cat([j1, j2]).cpu() - gold).abs().max().item() <= 2e-5
+    o1, o2 = JO.recover_from_ric2(data[:S // 2], data[S // 2:], 22)
+    assert (torch.cat([j1, j2]).cpu() - torch.from_numpy(np.concatenate([o1, o2]))).abs().max().item() <= 2e-5
+    # padded batch: the valid frames are a prefix of the full result (both scans are causal), the padding is zero
+    lens = torch.tensor([T, 9, 2, 1, T, 14])
+    jl = mp.joints_from_samples(x.to(cuda), mean, std, im, isd, length=lens).cpu()
+    jf = mp.joints_from_samples(x.to(cuda), mean, std, im, isd).cpu()
+    for s, n in enumerate(lens.tolist()):
+        assert torch.equal(jl[s, :n - 1], jf[s, :n - 1]) and jl[s, max(n - 1, 0):].abs().sum() == 0
+    # a trimmed sequence gives the same joints as the padded one
+    jt = mp.joints_from_samples(x[1:2, :9].contiguous().to(cuda), mean, std, im, isd).cpu()
+    assert torch.equal(jt[0], jf[1, :8])
+    # BASELINE shape, fewer joints, T = 2 (one frame)
+    g = torch.Generator(device=cuda).manual_seed(4)
+    big = torch.randn(128, 196, 263, device=cuda, generator=g) * 0.3
+    jb = mp.joints_from_samples(big)
+    ob = JO.joints_from_samples(big[:3].cpu().numpy(), np.zeros(263, np.float32), np.ones(263, np.float32),
+                                np.zeros(4, np.float32), np.ones(4, np.float32))
+    assert jb.shape == (128, 195, 22, 3) and (jb[:3].cpu() - torch.from_numpy(ob)).abs().max().item() <= 2e-5
+    assert ops.recover_joints(big[:2, :2].contiguous(), joints_num=5).shape == (2, 1, 5, 3)
+    with pytest.raises(RuntimeError):
+        ops.recover_joints(big[:2, :1].contiguous())                       # no motion frame
+    with pytest.raises(RuntimeError):
+        ops.recover_joints(big[:2, :, :40].contiguous())                   # too few features for 22 joints
+    with pytest.raises(RuntimeError):
+        ops.recover_joints(big[:2], mean=mean)                             # mean without std
+    with pytest.raises(RuntimeError):
+        ops.recover_joints(x)                                              # CPU tensor: no fallback
 
 
 def test_launch_counter(cuda):

@@ -13,7 +13,12 @@ isrc = h.index("Source")
 isamp = h.index("# Samples")
 iexe = h.index("Instructions Executed")
 stalls = [i for i, n in enumerate(h) if n.startswith("stall_") and "Not Issued" not in n]
-data = rows[hi + 1:]
+data = []
+for r in rows[hi + 1:]:
+    if r and r[0] in ("Address", "Line No", "Kernel Name"):
+        break
+    if len(r) > max(isamp, iexe):
+        data.append(r)
 tot = sum(int(r[isamp] or 0) for r in data)
 print("total samples", tot)
 rank = sorted(range(len(data)), key=lambda i: -int(data[i][isamp] or 0))[:top]
