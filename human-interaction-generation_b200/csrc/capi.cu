@@ -127,6 +127,11 @@ int hig_ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, co
                         t_next, static_cast<cudaStream_t>(stream));
 }
 
+int hig_debug_trace(unsigned long long* buf) {
+  hig::set_gemm_trace(buf);
+  return HIG_OK;
+}
+
 int hig_recover_joints(const float* x, int S, int T, int C, int init_row, const float* mean, const float* std_,
                        const float* init_mean, const float* init_std, const int* length, int joints_num, float* joints,
                        void* stream) {

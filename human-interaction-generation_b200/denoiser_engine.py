@@ -165,8 +165,9 @@ class DenoiserEngine:
         return WT
 
     # ------------------------------------------------------------------------------------------ workspaces
-    def workspace(self, S, T):
-        key = (S, T)
+    def workspace(self, S, T, slot=0):
+        """Activation buffers for S sequences x T frames; `slot` distinguishes concurrent branches of the same shape."""
+        key = (S, T, slot)
         ws = self._ws.get(key)
         if ws is not None:
             return ws

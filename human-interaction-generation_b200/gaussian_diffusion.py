@@ -214,41 +214,81 @@ class GaussianDiffusion:
                 xf_proj, xf_out = kw["xf_proj"], kw["xf_out"]
             else:
                 xf_proj, xf_out = net.encode_text(kw["text"], device)
-            key = (S, T, C, eng.precision, noise_seq is not None, str(device))
+            import os as _os
+            # Independent interactions CAN be sampled as `nb` concurrent branches of one CUDA graph (HIG_BRANCHES=nb: one
+            # stream and one set of workspaces each; a pair never straddles branches — both persons of pair i go to branch
+            # i // (B / nb); results are bit-identical to nb = 1 with the noise off).  Measured at the C2 shape on B200
+            # (profiles/r01d_step_ab_branches.txt): 3.21 ms/step at nb = 1, 3.43 at 2, 3.94 at 4 — the persistent GEMM
+            # grids of two branches only steal SMs from each other, so the default is ONE branch.  Parity runs (injected
+            # noise) are always single-branch so the noise indexing is the reference's.
+            B = S // 2
+            nb = int(_os.environ.get("HIG_BRANCHES", "1"))
+            if noise_seq is not None or nb < 1 or S % 2 or B % nb or B // nb < 8:
+                nb = 1
+            Sh = S // nb
+            key = (S, T, C, eng.precision, noise_seq is not None, str(device), nb)
             st = self._fast_state.get(key)
-            ws = eng.workspace(S, T)
+            wss = [eng.workspace(Sh, T, slot=k) for k in range(nb)]
             a_text_new = eng.text_state(xf_out)
-            if st is None or st["ws"] is not ws or st["a_text"].shape != a_text_new.shape:
-                st = {"ws": ws, "x": th.empty(S, T, C, device=device), "t": th.empty(S, device=device, dtype=th.long),
-                      "z": th.empty(S, T, C, device=device) if noise_seq is not None else None,
-                      "xfp": th.empty(S, eng.E, device=device), "a_text": th.empty_like(a_text_new), "graph": None,
-                      "graph_key": None, "seed": th.zeros(1, device=device, dtype=th.long)}
+            if st is None or any(a is not b for a, b in zip(st["ws"], wss)) or st["a_shape"] != tuple(a_text_new.shape):
+                Bh = B // nb
+                idx = [th.cat([th.arange(k * Bh, (k + 1) * Bh), B + th.arange(k * Bh, (k + 1) * Bh)]).to(device)
+                       for k in range(nb)] if nb > 1 else [None]
+                st = {"ws": wss, "idx": idx, "a_shape": tuple(a_text_new.shape), "graph": None, "graph_key": None,
+                      "streams": [th.cuda.Stream(device=device) for _ in range(nb - 1)],
+                      "br": [{"x": th.empty(Sh, T, C, device=device), "t": th.empty(Sh, device=device, dtype=th.long),
+                              "z": th.empty(Sh, T, C, device=device) if noise_seq is not None else None,
+                              "xfp": th.empty(Sh, eng.E, device=device),
+                              "a_text": th.empty(a_text_new.shape[0], Sh, *a_text_new.shape[2:], device=device,
+                                                 dtype=a_text_new.dtype),
+                              "seed": th.zeros(1, device=device, dtype=th.long)} for _ in range(nb)]}
                 if len(self._fast_state) > 4:
                     self._fast_state.clear()
                 self._fast_state[key] = st
-            st["a_text"].copy_(a_text_new)
-            st["xfp"].copy_(xf_proj.detach().float())
-            eng.set_lengths(ws, kw.get("length"), S, T)
-            st["x"].copy_(x_T if x_T is not None else th.randn(S, T, C, device=device))
-            st["t"].fill_(self.num_timesteps - 1)
-            ops.pack_motion(st["x"], ws["xa"])
+            if x_T is None:
+                x_T = th.randn(S, T, C, device=device)
+            length = kw.get("length")
+            if length is not None:
+                length = th.as_tensor(length).reshape(-1)
+                if length.numel() != S:
+                    raise ValueError(f"length must have {S} entries, got {length.numel()}")
+                length = length.to(device)
+            xfp_all = xf_proj.detach().float()
             coef = self._tables(device)["coef"]
             # The Philox key lives in device memory, the timestep too (decremented by the posterior kernel), and every
             # operand is a fixed buffer of `st` / `ws`: ONE captured graph serves every later call of this shape.  (torch's
             # graph capture costs a gc.collect() + empty_cache() + instantiation — 0.2 s per call, sometimes seconds.)
-            seed = self.seed
-            self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
-            st["seed"].fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
+            for k, (br, ws, ix) in enumerate(zip(st["br"], wss, st["idx"])):
+                sel = (lambda a, dim=0: a) if ix is None else (lambda a, dim=0: a.index_select(dim, ix))
+                br["a_text"].copy_(sel(a_text_new, 1))
+                br["xfp"].copy_(sel(xfp_all))
+                eng.set_lengths(ws, None if length is None else sel(length), Sh, T)
+                br["x"].copy_(sel(x_T))
+                br["t"].fill_(self.num_timesteps - 1)
+                ops.pack_motion(br["x"], ws["xa"])
+                seed = self.seed
+                self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+                br["seed"].fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
 
-            import os as _os
-            persist = _os.environ.get("HIG_L2_PERSIST", "0") != "0"   # measured: no gain with the 26 MB fp16 stream
+            persist = nb == 1 and _os.environ.get("HIG_L2_PERSIST", "0") != "0"   # measured: no gain with the fp16 stream
 
-            def step():
+            def branch_step(br, ws):
                 if persist:
                     ops.l2_persist(ws["xres"])
-                eps = eng.run_packed(ws, st["t"], st["xfp"], st["a_text"], S, T)
-                ops.ddpm_step(st["x"], eps, st["t"], coef, noise=st["z"], seed_dev=st["seed"], packed=ws["xa"],
-                              t_next=st["t"])
+                eps = eng.run_packed(ws, br["t"], br["xfp"], br["a_text"], Sh, T)
+                ops.ddpm_step(br["x"], eps, br["t"], coef, noise=br["z"], seed_dev=br["seed"], packed=ws["xa"],
+                              t_next=br["t"])
+
+            def step():
+                cur = th.cuda.current_stream()
+                for sd in st["streams"]:
+                    sd.wait_stream(cur)
+                branch_step(st["br"][0], wss[0])
+                for sd, br, ws in zip(st["streams"], st["br"][1:], wss[1:]):
+                    with th.cuda.stream(sd):
+                        branch_step(br, ws)
+                for sd in st["streams"]:
+                    cur.wait_stream(sd)
 
             # a cached graph is valid while the packed weights, the schedule tables and the kernel-selection knobs it
             # was recorded with are the ones in force
@@ -269,7 +309,7 @@ class GaussianDiffusion:
             launches, c_prev = 0, _lib.launch_count()
             for k in steps:
                 if noise_seq is not None:
-                    st["z"].copy_(noise_seq[k])
+                    st["br"][0]["z"].copy_(noise_seq[k])
                 if not use_graph or (graph is None and k == 0):
                     step()                      # eager: also performs every lazy initialisation before capture
                     c_now = _lib.launch_count()
@@ -284,7 +324,12 @@ class GaussianDiffusion:
                 launches += st["nodes"]            # one replay launches every recorded kernel node
             # kernels of this library launched on the GPU during this call (eager + graph replays)
             self.last_launches = launches
-            return st["x"].clone()
+            if nb == 1:
+                return st["br"][0]["x"].clone()
+            out = th.empty(S, T, C, device=device)
+            for br, ix in zip(st["br"], st["idx"]):
+                out.index_copy_(0, ix, br["x"])
+            return out
 
     @staticmethod
     def _capture(step):

@@ -40,6 +40,10 @@ const char* hig_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long hig_launch_count(void);
 
+/* Debug aid (no reference counterpart): when buf != NULL the resident-W projection kernel writes 32 clock64 / globaltimer
+ * slots per CTA pair into buf (>= 74 * 32 entries) — tile-by-tile timeline read by tools/gemm_trace.py; NULL disables. */
+int hig_debug_trace(unsigned long long* buf);
+
 /* L2 residency hint (no reference counterpart): pins [ptr, ptr+bytes) — the fp32 residual stream — in the 126 MB L2
  * through an access-policy window on `stream`; ptr == NULL clears it. */
 int hig_l2_persist(const void* ptr, unsigned long long bytes, float hit_ratio, void* stream);

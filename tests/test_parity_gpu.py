@@ -158,6 +158,37 @@ def test_sampling_loop_golden_and_graph(cuda, precision):
     assert rel(img, a) < (1e-6 if precision == "fp32" else 1e-6)
 
 
+def test_branched_sampling_matches_single_branch(cuda, monkeypatch):
+    """Production sampling splits the pairs over concurrent graph branches (HIG_BRANCHES, default 2).  With the
+    posterior noise switched off (sigma table zeroed) the chain is deterministic, and because no kernel mixes rows of
+    different sequences except through the pair, every branch count must give the same samples — also with ragged
+    lengths, per-sequence text and a second call that reuses the cached graph with new inputs."""
+    import weights
+    from hig_b200.gaussian_diffusion import (GaussianDiffusion, LossType, ModelMeanType, ModelVarType,
+                                             get_named_beta_schedule)
+    m, _ = build(2, "bf16", cuda)
+    m.cap_id = False
+    S, T, steps = 32, 40, 50
+    lens = [40, 13, 27, 31, 40, 5, 40, 22] * 4
+    res = {}
+    for nb in ("1", "2"):
+        monkeypatch.setenv("HIG_BRANCHES", nb)
+        diff = GaussianDiffusion(betas=get_named_beta_schedule("linear", steps), model_mean_type=ModelMeanType.EPSILON,
+                                 model_var_type=ModelVarType.FIXED_SMALL, loss_type=LossType.MSE)
+        diff._tables(cuda)["coef"][4].zero_()
+        outs = []
+        for seed in (21, 22):
+            inp = weights.make_inputs(seed, S, T, n_text=7, lengths=lens)
+            kw = {"xf_proj": inp["xf_proj"].to(cuda), "xf_out": inp["xf_out"].to(cuda), "length": inp["length"].to(cuda)}
+            outs.append(diff.p_sample_loop(m, (S, T, 263), noise=inp["x"].to(cuda), clip_denoised=False, model_kwargs=kw))
+        res[nb] = outs
+        assert diff.last_launches > 0
+    for a, b in zip(res["1"], res["2"]):
+        assert torch.isfinite(a).all() and not torch.equal(res["1"][0], res["1"][1])
+        print(f"branches 1 vs 2: bit-identical={torch.equal(a, b)} rel={rel(a, b):.2e}")
+        assert rel(a, b) < 1e-6
+
+
 def test_teacher_forced_steps_bf16(cuda):
     """Primary bf16 gate: feed the ORACLE's x_t to the CUDA path at several t and compare eps and x_{t-1}."""
     import denoiser_oracle as DO
