@@ -158,3 +158,80 @@ def generate_sharded(trainer, caption1, caption2, m_lens, dim_pose, batch_size=5
     local = trainer.generate(caption1[lo:hi], caption2[lo:hi], m_lens[lo:hi], dim_pose, batch_size=batch_size) \
         if hi > lo else []
     return gather_pairs(local, len(caption1), dim_pose, group=group, dst=dst)
+
+
+# ---------------------------------------------------------------------------------------------- length-bucketed generation
+def plan_buckets(m_lens, batch_size, world=1, num_frames=196):
+    """Schedule for generating N pairs of very different lengths (the evaluation driver, datasets/evaluator.py:26-127 ->
+    trainer.generate over the whole test split): the reference pads every chunk of 512 to its longest motion, so with
+    shuffled lengths every batch runs at ~196 frames.  Here the pairs are sorted by length, cut into batches of at most
+    `batch_size`, and the batches are dealt to the ranks longest-processing-time-first on cost = T_batch * pairs (the
+    denoiser is linear in tokens).  Deterministic: every rank computes the same plan.
+    Returns per rank a list of (T_batch, [pair indices])."""
+    lens = [max(1, min(int(v), num_frames)) for v in torch.as_tensor(m_lens).reshape(-1).tolist()]
+    order = sorted(range(len(lens)), key=lambda i: (-lens[i], i))
+    batches = [order[i:i + batch_size] for i in range(0, len(order), batch_size)]
+    plan = [[] for _ in range(world)]
+    load = [0] * world
+    for b in sorted(batches, key=lambda b: (-lens[b[0]] * len(b), b[0])):
+        r = min(range(world), key=lambda r: (load[r], r))
+        plan[r].append((lens[b[0]], b))
+        load[r] += lens[b[0]] * len(b)
+    return plan
+
+
+def gather_indexed(local, indices, n_pairs, dim_pose, group=None, dst=0):
+    """local[k] = [motion1 [T_k,C], motion2 [T_k,C]] is pair indices[k]; returns the list of all n_pairs in index order on
+    `dst` (None elsewhere).  One padded gather after sampling has finished; no collective inside the sampling loop."""
+    if not (dist.is_available() and dist.is_initialized()):
+        out = [None] * n_pairs
+        for i, pair in zip(indices, local):
+            out[i] = pair
+        return out
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = local[0][0].device if local else torch.device("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    meta = torch.tensor([len(local), max([m.shape[0] for pair in local for m in pair], default=0)], device=dev)
+    dist.all_reduce(meta, op=dist.ReduceOp.MAX, group=group)
+    per, Tm = int(meta[0]), int(meta[1])
+    buf = torch.zeros(per, 2, Tm, dim_pose, device=dev)
+    info = torch.full((per, 2), -1, dtype=torch.long, device=dev)      # (pair index, rows)
+    for k, (i, pair) in enumerate(zip(indices, local)):
+        info[k, 0], info[k, 1] = i, pair[0].shape[0]
+        for j in (0, 1):
+            buf[k, j, :pair[j].shape[0]] = pair[j]
+    bufs = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    infos = [torch.empty_like(info) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, bufs, dst=dst, group=group)
+    dist.gather(info, infos, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = [None] * n_pairs
+    for r in range(world):
+        for k in range(per):
+            i, T = int(infos[r][k, 0]), int(infos[r][k, 1])
+            if i >= 0:
+                out[i] = [bufs[r][k, 0, :T], bufs[r][k, 1, :T]]
+    return out
+
+
+def generate_bucketed(trainer, caption1, caption2, m_lens, dim_pose, batch_size=512, group=None, dst=0):
+    """Length-bucketed, rank-sharded `DDPMMulTrainer.generate`: same arguments, returns (on `dst`; everywhere when
+    torch.distributed is not initialised) the list of [motion1, motion2] in the callers' order, each trimmed to its own
+    length — what the evaluator keeps anyway (datasets/evaluator.py:94-97)."""
+    on = dist.is_available() and dist.is_initialized()
+    world, rank = (dist.get_world_size(group), dist.get_rank(group)) if on else (1, 0)
+    lens = torch.as_tensor(m_lens).reshape(-1)
+    if not (len(caption1) == len(caption2) == lens.numel()):
+        raise ValueError("caption1, caption2 and m_lens must have one entry per pair")
+    plan = plan_buckets(lens, batch_size, world, trainer._net().num_frames)
+    trainer.encoder.eval()
+    local, indices = [], []
+    for T_b, idx in plan[rank]:
+        ml = lens[idx]
+        out = trainer.generate_batch([caption1[i] for i in idx], [caption2[i] for i in idx], ml, dim_pose)
+        B = len(idx)
+        for k, i in enumerate(idx):
+            n = max(1, min(int(ml[k]), out.shape[1]))
+            local.append([out[k, :n], out[B + k, :n]])
+            indices.append(i)
+    return gather_indexed(local, indices, len(caption1), dim_pose, group=group, dst=dst)

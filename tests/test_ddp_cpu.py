@@ -109,7 +109,86 @@ def _w_sampling_shards(rank, world):
         assert out is None
 
 
+class _FakeNet:
+    num_frames = 196
+
+
+class _FakeTrainer:
+    """Host-logic stand-in for DDPMMulTrainer: generate_batch returns [2B, T, C] with (caption id, person, T) encoded."""
+    encoder = torch.nn.Identity()
+
+    def __init__(self):
+        self.batches = []
+
+    def _net(self):
+        return _FakeNet()
+
+    def generate_batch(self, c1, c2, m_lens, dim_pose):
+        T = int(min(int(torch.as_tensor(m_lens).max()), 196))
+        self.batches.append((T, len(c1)))
+        out = torch.zeros(2 * len(c1), T, dim_pose)
+        for k, (a, b) in enumerate(zip(c1, c2)):
+            out[k, :, 0], out[len(c1) + k, :, 0] = float(a), float(b)
+            out[k, :, 1] = out[len(c1) + k, :, 1] = float(T)
+        return out
+
+
+def _w_bucketed_generation(rank, world):
+    import hig_b200  # noqa: F401
+    from hig_b200.ddp import generate_bucketed, plan_buckets
+    rs = torch.Generator().manual_seed(5)
+    n = 37
+    lens = torch.randint(20, 240, (n, 1), generator=rs)
+    c1, c2 = list(range(n)), [1000 + i for i in range(n)]
+    tr = _FakeTrainer()
+    out = generate_bucketed(tr, c1, c2, lens, 6, batch_size=8)
+    plan = plan_buckets(lens, 8, world)
+    assert [(T, len(ix)) for T, ix in plan[rank]] == tr.batches          # this rank ran exactly its planned batches
+    if rank == 0:
+        assert len(out) == n
+        for i, (a, b) in enumerate(out):
+            want = min(int(lens[i]), 196)
+            assert a.shape == (want, 6) and b.shape == (want, 6)          # trimmed to the pair's own length
+            assert float(a[0, 0]) == i and float(b[0, 0]) == 1000 + i     # caller's order, persons not swapped
+            assert float(a[0, 1]) >= want                                # its batch was long enough
+    else:
+        assert out is None
+
+
 # ------------------------------------------------------------------------------------------------ tests
+def test_plan_buckets_covers_balances_and_saves_frames():
+    import hig_b200  # noqa: F401
+    from hig_b200.ddp import plan_buckets
+    g = torch.Generator().manual_seed(1)
+    lens = torch.randint(20, 200, (1000,), generator=g)
+    for world in (1, 2, 8):
+        plan = plan_buckets(lens, 64, world)
+        seen = sorted(i for r in plan for _, ix in r for i in ix)
+        assert seen == list(range(1000))
+        for r in plan:
+            for T, ix in r:
+                assert len(ix) <= 64 and T == min(int(lens[ix].max()), 196) and T == min(int(lens[ix[0]]), 196)
+        cost = [sum(T * len(ix) for T, ix in r) for r in plan]
+        assert max(cost) - min(cost) <= 196 * 64                          # LPT: within one batch of each other
+        # frames actually sampled vs the reference's chunking in caller order (every chunk padded to its longest)
+        ref = sum(min(int(lens[i:i + 64].max()), 196) * len(lens[i:i + 64]) for i in range(0, 1000, 64))
+        assert sum(cost) < 0.65 * ref
+    assert plan_buckets(torch.tensor([[5], [300]]), 4, 1)[0] == [(196, [1, 0])]   # [N,1] lengths, clamped to num_frames
+
+
+def test_bucketed_generation_single_process():
+    import hig_b200  # noqa: F401
+    from hig_b200.ddp import generate_bucketed
+    tr = _FakeTrainer()
+    out = generate_bucketed(tr, [3, 4, 5], [30, 40, 50], [100, 20, 60], 4, batch_size=2)
+    assert [a.shape[0] for a, _ in out] == [100, 20, 60] and tr.batches == [(100, 2), (20, 1)]
+    assert [float(a[0, 0]) for a, _ in out] == [3, 4, 5] and [float(b[0, 0]) for _, b in out] == [30, 40, 50]
+
+
+def test_bucketed_generation_world2():
+    _run("_w_bucketed_generation")
+
+
 def test_gradient_segments_are_averaged_world2():
     _run("_w_segments")
 

@@ -320,3 +320,23 @@ def test_length_forms_and_errors(cuda):
     with pytest.raises(ValueError):
         with torch.no_grad():
             m(g("x")[:3], g("t")[:3], length=g("length")[:3], xf_proj=g("xf_proj")[:3], xf_out=g("xf_out")[:3])
+
+
+def test_bucketed_generation_and_joints_end_to_end(cuda):
+    """caption ids -> length-bucketed sampling (ddp.generate_bucketed, single process) -> per-pair motions trimmed to
+    their own lengths, in the caller's order; then generate_joints: caption -> joints without leaving the GPU."""
+    import argparse
+    from hig_b200.ddp import generate_bucketed
+    from hig_b200.mul_ddpm_trainer import DDPMMulTrainer
+    m, _ = build(1, "bf16", cuda, cap_id=True)
+    opt = argparse.Namespace(device=cuda, multi=True, label_path=None, cap_id=True, diffusion_steps=8, is_train=False)
+    tr = DDPMMulTrainer(opt, m)
+    lens = torch.tensor([[40], [12], [33], [40], [7]])
+    c1, c2 = [3, 5, 7, 9, 11], [4, 6, 8, 10, 12]
+    out = generate_bucketed(tr, c1, c2, lens, 263, batch_size=2)
+    assert [a.shape for a, _ in out] == [(n, 263) for n in (40, 12, 33, 40, 7)]
+    assert all(a.is_cuda and torch.isfinite(a).all() and torch.isfinite(b).all() for a, b in out)
+    mean, std, im, isd = joint_stats()
+    js = tr.generate_joints(c1, c2, lens.view(-1), 263, mean=mean, std=std, init_mean=im, init_std=isd)
+    assert [j1.shape for j1, _ in js] == [(n - 1, 22, 3) for n in (40, 12, 33, 40, 7)]
+    assert all(torch.isfinite(j1).all() and torch.isfinite(j2).all() for j1, j2 in js)
