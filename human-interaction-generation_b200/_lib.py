@@ -39,6 +39,7 @@ SIGNATURES = {
     "hig_attn_apply_stylize": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                                c_int, c_void_p],
     "hig_timestep_embed": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
+    "hig_time_table_silu": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_pack_motion": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_ddpm_step": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ull,
                       c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],

@@ -127,6 +127,11 @@ int hig_ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, co
                         t_next, static_cast<cudaStream_t>(stream));
 }
 
+int hig_time_table_silu(const float* table, int n_steps, const long long* t, const float* xf_proj, int S, int E, void* out,
+                        int out_dtype, void* stream) {
+  return hig::time_table_silu(table, n_steps, t, xf_proj, S, E, out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
 int hig_debug_trace(unsigned long long* buf) {
   hig::set_gemm_trace(buf);
   return HIG_OK;

@@ -40,6 +40,47 @@ int timestep_embed(const long long* t, const float* freqs, int S, int half, void
 }
 
 // ------------------------------------------------------------------------------------------------
+// time_table_silu: out[s, :] = SiLU(table[t_s, :] + xf_proj[s, :]).  table[n, :] = time_embed(timestep_embedding(n))
+// (:474-478, :591) for every timestep of the schedule, computed once per set of weights with the same GEMM kernels, so
+// the sampling loop replaces the sinusoid kernel and the two M = S GEMMs of the time MLP (8 CTAs each, latency-bound)
+// by this gather.  Same association order as the GEMM epilogue it replaces: (acc + bias) + residual, then SiLU.
+// ------------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void time_table_silu_kernel(const float* __restrict__ table, int n_steps, const long long* __restrict__ t,
+                                       const float* __restrict__ xf_proj, int S, int E, TOut* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();      // t is decremented by the previous step's posterior kernel
+  pdl_trigger();
+  if (idx >= S * (E / 4)) return;
+  const int s = idx / (E / 4), c = (idx - s * (E / 4)) * 4;
+  long long ts = t[s];
+  ts = ts < 0 ? 0 : (ts >= n_steps ? n_steps - 1 : ts);
+  const float4 a = *reinterpret_cast<const float4*>(table + (size_t)ts * E + c);
+  const float4 b = *reinterpret_cast<const float4*>(xf_proj + (size_t)s * E + c);
+  const float v[4] = {silu_f(a.x + b.x), silu_f(a.y + b.y), silu_f(a.z + b.z), silu_f(a.w + b.w)};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[(size_t)s * E + c + j] = static_cast<TOut>(v[j]);
+}
+
+int time_table_silu(const float* table, int n_steps, const long long* t, const float* xf_proj, int S, int E, void* out,
+                    int out_dtype, cudaStream_t stream) {
+  if (!table || !t || !xf_proj || !out || S <= 0 || E <= 0 || (E % 4) || n_steps <= 0)
+    return set_error(HIG_ERR_INVALID, "time_table_silu: bad arguments (E must be a multiple of 4)");
+  const int n = S * (E / 4), blocks = (n + 255) / 256;
+  cudaError_t e;
+  if (out_dtype == HIG_BF16)
+    e = launch_pdl(time_table_silu_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, table, n_steps, t, xf_proj, S, E,
+                   (__nv_bfloat16*)out);
+  else
+    e = launch_pdl(time_table_silu_kernel<float>, dim3(blocks), dim3(256), 0, stream, table, n_steps, t, xf_proj, S, E,
+                   (float*)out);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("time_table_silu launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // pack_motion: x fp32 [S,T,C] -> GEMM operand [S*T, ld] such that ONE projection with the augmented weight
 // [joint_embed.weight | joint_embed2.weight | 0] reproduces embed_motion:
 //   row t>=1 : cols [0,C) = x[s,t,:],     cols [C,ld) = 0

@@ -374,7 +374,7 @@ constexpr int WR_KB = 8;                                  // K <= 512
 constexpr int WR_W_BYTES = WR_KB * GS_B_BYTES;            // 128 KB
 constexpr int WR_SUB = 32 * 64;                           // 2 KB sub-slab
 constexpr int WR_EPI_BYTES = GS_EPI_WARPS * 2 * WR_SUB;   // 32 KB
-constexpr int WR_BAR_BYTES = (2 * WR_STAGES + 4 + WR_KB + 1) * 8 + 16;
+constexpr int WR_BAR_BYTES = (2 * WR_STAGES + 4 + 2) * 8 + 16;
 constexpr int WR_SMEM = WR_W_BYTES + WR_STAGES * GS_A_BYTES + WR_EPI_BYTES + WR_BAR_BYTES + 1024;
 static_assert(WR_SMEM <= 232448, "shared memory budget");
 
@@ -479,8 +479,8 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + WR_STAGES;
   uint64_t* tfull_bar = empty_bar + WR_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* wfull_bar = tempty_bar + 2;            // one per k-block: the first tile starts as soon as W block 0 is in
-  uint64_t* wfree_bar = wfull_bar + WR_KB;
+  uint64_t* wfull_bar = tempty_bar + 2;
+  uint64_t* wfree_bar = wfull_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfree_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -509,7 +509,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(tfull_bar + s, 1);
       mbar_init(tempty_bar + s, 2 * GS_EPI_WARPS);
     }
-    for (int s = 0; s < WR_KB; ++s) mbar_init(wfull_bar + s, 1);
+    mbar_init(wfull_bar, 1);
     mbar_init(wfree_bar, 1);
     fence_mbar_init();
   }
@@ -524,10 +524,11 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================= TMA producer (both CTAs) =================
     if (lane == 0) {
       auto load_w = [&](int n_blk) {
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          if (rank == 0) mbar_arrive_expect_tx(wfull_bar + kb, 2 * GS_B_BYTES);
-          tma_load_2d_2cta(sW + kb * GS_B_BYTES, &tmB, wfull_bar + kb, kb * GS_BK, n_blk * GS_BN + (int)rank * (GS_BN / 2));
-        }
+        // one barrier for the whole block: waiting k-block by k-block was measured and is slower — the first tile then runs
+        // while 7/8 of W still competes with A for the ~44 B/clk an SM gets from L2 (profiles/r01d_gemm_trace.txt)
+        if (rank == 0) mbar_arrive_expect_tx(wfull_bar, 2 * k_blocks * GS_B_BYTES);
+        for (int kb = 0; kb < k_blocks; ++kb)
+          tma_load_2d_2cta(sW + kb * GS_B_BYTES, &tmB, wfull_bar, kb * GS_BK, n_blk * GS_BN + (int)rank * (GS_BN / 2));
       };
       int cur_n = -1;
       uint32_t run = 0;
@@ -535,7 +536,12 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lo < hi) { cur_n = lo / m_tiles; load_w(cur_n); run = 1; }
       pdl_wait();
       pdl_trigger();
-      if (tr != nullptr) tr[2] = clock64();
+      if (tr != nullptr) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        tr[2] = clock64();
+        tr[31] = gt;
+      }
       uint32_t it = 0;
       for (int tile = lo; tile < hi; ++tile) {
         const int n_blk = tile / m_tiles;
@@ -563,8 +569,12 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int cur_n = -1;
       for (int tile = lo; tile < hi; ++tile, ++lt) {
         const int n_blk = tile / m_tiles;
-        const bool new_w = n_blk != cur_n;   // first tile on a freshly requested W block: wait for it k-block by k-block
-        cur_n = n_blk;
+        if (n_blk != cur_n) {
+          mbar_wait(wfull_bar, runs & 1u);
+          if (tr != nullptr && runs == 0) tr[3] = clock64();
+          ++runs;
+          cur_n = n_blk;
+        }
         const uint32_t as = lt & 1u;
         const uint32_t aphase = (lt >> 1) & 1u;
         mbar_wait(tempty_bar + as, aphase ^ 1u);
@@ -573,10 +583,6 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t stage = it % WR_STAGES;
           const uint32_t phase = (it / WR_STAGES) & 1u;
-          if (new_w) {
-            mbar_wait(wfull_bar + kb, runs & 1u);
-            if (tr != nullptr && runs == 0 && kb == k_blocks - 1) tr[3] = clock64();
-          }
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
           const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * GS_A_BYTES));
@@ -587,7 +593,6 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           umma_commit_2cta_mc(empty_bar + stage, 0b11);
         }
         umma_commit_2cta_mc(tfull_bar + as, 0b11);
-        if (new_w) ++runs;
         if (tr != nullptr && lt < 8) tr[4 + lt] = clock64();
         if (tile + 1 < hi && (tile + 1) / m_tiles != cur_n) umma_commit_2cta_mc(wfree_bar, 0b11);
       }
@@ -710,7 +715,9 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-static unsigned long long* g_trace = nullptr;   // debug: set through hig_debug_trace (>= 74 * 32 slots)
+// debug: set through hig_debug_trace; every traced launch takes the next block of 74 * 32 slots (the caller sizes the
+// buffer for the launches it makes before clearing the pointer)
+static unsigned long long* g_trace = nullptr;
 void set_gemm_trace(unsigned long long* buf) { g_trace = buf; }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -757,6 +764,7 @@ static int launch_wres(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   if (const char* pe = getenv("HIG_GS_PAIRS")) { const int v = atoi(pe); if (v > 0 && v < pairs) pairs = v; }  // experiment knob
   cudaError_t e = launch_pdl(kern, dim3(2 * pairs), dim3(GS_THREADS), WR_SMEM, stream, tmA, tmB, tmC,
                              static_cast<const __half*>(resid), ldr, M, N, K, ep, f16_ops, g_trace);
+  if (g_trace != nullptr) g_trace += 74 * 32;
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("resident-W gemm launch: ") + cudaGetErrorString(e));
   count_launch();

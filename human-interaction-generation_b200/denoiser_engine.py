@@ -57,6 +57,7 @@ class DenoiserEngine:
         self.packed_generation = 0   # bumped whenever the operand copies are rebuilt (captured graphs go stale)
         self._ws = {}
         self._text_cache = None
+        self._time_table = None
         # product path: projections with the TMA-staged epilogue, pre-attention LayerNorms folded into them
         self.stream = precision == "bf16"
 
@@ -238,13 +239,37 @@ class DenoiserEngine:
         ws["len"].copy_(ln.to(device=ws["len"].device, dtype=torch.int32, non_blocking=True).clamp(min=0, max=T))
 
     # ------------------------------------------------------------------------------------------ forward
-    def embed(self, ws, t_dev, xf_proj, S):
+    def time_table(self, n_steps):
+        """time_embed(timestep_embedding(n)) for n = 0 .. n_steps-1, fp32 [n_steps, E]: the time MLP depends on nothing
+        but the integer timestep, so the sampling loop reads it from this table (built with the same kernels; a row's
+        value does not depend on how many rows the GEMM has).  Rebuilt when the weights change."""
+        W = self.packed()
+        key = (self.packed_generation, n_steps)
+        if self._time_table is not None and self._time_table[0] == key:
+            return self._time_table[1]
+        dev, dt = W["te0.w"].device, self.act_dtype
+        t_all = torch.arange(n_steps, device=dev, dtype=torch.int64)
+        temb = torch.empty(n_steps, self.D, device=dev, dtype=dt)
+        te_h = torch.empty(n_steps, self.E, device=dev, dtype=dt)
+        table = torch.empty(n_steps, self.E, device=dev, dtype=torch.float32)
+        ops.timestep_embed(t_all, W["freqs"], temb)
+        for lo in range(0, n_steps, 256):   # <= 256 rows per call: the same single-CTA kernel the per-step path (M = S) takes
+            hi = min(lo + 256, n_steps)
+            self._gemm(temb[lo:hi], W["te0.w"], W["te0.b"], out=te_h[lo:hi], act=ops.ACT_SILU)
+            self._gemm(te_h[lo:hi], W["te2.w"], W["te2.b"], out_f32=table[lo:hi])
+        self._time_table = (key, table)
+        return table
+
+    def embed(self, ws, t_dev, xf_proj, S, time_table=None):
         """emb = time_embed(timestep_embedding(t)) + xf_proj (:591), then every block's (scale|shift) in one GEMM."""
         W = self.packed()
-        ops.timestep_embed(t_dev, W["freqs"], ws["temb"])
-        self._gemm(ws["temb"], W["te0.w"], W["te0.b"], out=ws["te_h"], act=ops.ACT_SILU)
-        # StylizationBlock applies SiLU(emb) before its linear (:74-77): fold it into this epilogue
-        self._gemm(ws["te_h"], W["te2.w"], W["te2.b"], out=ws["semb"], residual=xf_proj, act=ops.ACT_SILU)
+        if time_table is not None:
+            ops.time_table_silu(time_table, t_dev, xf_proj, ws["semb"])
+        else:
+            ops.timestep_embed(t_dev, W["freqs"], ws["temb"])
+            self._gemm(ws["temb"], W["te0.w"], W["te0.b"], out=ws["te_h"], act=ops.ACT_SILU)
+            # StylizationBlock applies SiLU(emb) before its linear (:74-77): fold it into this epilogue
+            self._gemm(ws["te_h"], W["te2.w"], W["te2.b"], out=ws["semb"], residual=xf_proj, act=ops.ACT_SILU)
         self._gemm(ws["semb"], W["emb.w"], W["emb.b"], out_f32=ws["ss"])
 
     def _project(self, ws, W, p, write_xb):
@@ -369,9 +394,9 @@ class DenoiserEngine:
         W = self.packed()
         self._gemm(ws["xa"], W["in.w"], None, residual=W["in.pos"], res_row_mod=T, out_f32=ws["xres"])
 
-    def run_packed(self, ws, t_dev, xf_proj, a_text, S, T):
+    def run_packed(self, ws, t_dev, xf_proj, a_text, S, T, time_table=None):
         """Everything after pack_motion: ws['xa'] must hold the packed motion, ws['len'] the lengths."""
-        self.embed(ws, t_dev, xf_proj, S)
+        self.embed(ws, t_dev, xf_proj, S, time_table)
         self.embed_motion(ws, T)
         self.layers(ws, a_text, S, T)
         self.heads(ws, S, T)

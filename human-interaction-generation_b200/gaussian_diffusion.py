@@ -270,12 +270,13 @@ class GaussianDiffusion:
                 self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
                 br["seed"].fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
 
+            ttab = eng.time_table(self.num_timesteps) if _os.environ.get("HIG_TIME_TABLE", "1") != "0" else None
             persist = nb == 1 and _os.environ.get("HIG_L2_PERSIST", "0") != "0"   # measured: no gain with the fp16 stream
 
             def branch_step(br, ws):
                 if persist:
                     ops.l2_persist(ws["xres"])
-                eps = eng.run_packed(ws, br["t"], br["xfp"], br["a_text"], Sh, T)
+                eps = eng.run_packed(ws, br["t"], br["xfp"], br["a_text"], Sh, T, time_table=ttab)
                 ops.ddpm_step(br["x"], eps, br["t"], coef, noise=br["z"], seed_dev=br["seed"], packed=ws["xa"],
                               t_next=br["t"])
 
@@ -294,7 +295,8 @@ class GaussianDiffusion:
             # was recorded with are the ones in force
             eng.packed()
             graph_key = (eng.packed_generation, coef.data_ptr(), self.num_timesteps,
-                         tuple(_os.environ.get(k) for k in ("HIG_WRES", "HIG_L2_PERSIST", "HIG_PDL", "HIG_GS_PAIRS")))
+                         tuple(_os.environ.get(k) for k in ("HIG_WRES", "HIG_L2_PERSIST", "HIG_PDL", "HIG_GS_PAIRS",
+                                                            "HIG_TIME_TABLE")))
             if st["graph_key"] != graph_key:
                 st["graph"], st["graph_key"] = None, graph_key
 

@@ -218,6 +218,19 @@ def ddpm_step(x, eps, t, coef, noise=None, seed=0, packed=None, t_next=None, see
     return x
 
 
+def time_table_silu(table, t, xf_proj, out):
+    """out[s] = SiLU(table[t[s]] + xf_proj[s]); table fp32 [n_steps,E], t int64 [S], xf_proj fp32 [S,E], out bf16/fp32."""
+    lib = _lib.load()
+    S, E = xf_proj.shape
+    if table.dtype != torch.float32 or xf_proj.dtype != torch.float32 or t.dtype != torch.int64:
+        raise ValueError("hig_b200.time_table_silu: table / xf_proj fp32, t int64")
+    if not (table.is_contiguous() and xf_proj.is_contiguous() and out.is_contiguous()) or table.shape[1] != E:
+        raise ValueError("hig_b200.time_table_silu: contiguous [*, E] operands required")
+    rc = lib.hig_time_table_silu(_ptr(table), table.shape[0], _ptr(t), _ptr(xf_proj), S, E, _ptr(out), _dt(out), _stream())
+    _lib.check(rc, "hig_time_table_silu")
+    return out
+
+
 def recover_joints(x, mean=None, std=None, init_mean=None, init_std=None, length=None, joints_num=22, init_row=0,
                    out=None):
     """x fp32 [S,T,C] on CUDA -> joints fp32 [S,T-1,joints_num,3] (hig_recover_joints); init_row 0 or -1 / T-1."""

@@ -41,7 +41,8 @@ const char* hig_last_error(void);
 unsigned long long hig_launch_count(void);
 
 /* Debug aid (no reference counterpart): when buf != NULL the resident-W projection kernel writes 32 clock64 / globaltimer
- * slots per CTA pair into buf (>= 74 * 32 entries) — tile-by-tile timeline read by tools/gemm_trace.py; NULL disables. */
+ * slots per CTA pair into buf, each launch taking the next block of 74 * 32 entries (size buf for the launches made
+ * before clearing it) — tile-by-tile timeline read by tools/gemm_trace.py; NULL disables. */
 int hig_debug_trace(unsigned long long* buf);
 
 /* L2 residency hint (no reference counterpart): pins [ptr, ptr+bytes) — the fp32 residual stream — in the 126 MB L2
@@ -139,6 +140,14 @@ int hig_pack_motion(const float* x, int S, int T, int C, int ld_out, void* out, 
 int hig_ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
                   int n_steps, int S, int T, int C, unsigned long long seed, const unsigned long long* seed_dev, void* packed,
                   int ld_packed, int packed_dtype, long long* t_next, void* stream);
+
+/* out[s,:] = SiLU(table[t[s],:] + xf_proj[s,:]) — the input of every StylizationBlock's emb linear (SiLU folded in,
+ * models/interaction_transformer.py:74-77) when emb = time_embed(timestep_embedding(t)) + xf_proj (:591) is read from a
+ * table of the time MLP over the whole schedule (table fp32 [n_steps,E], built once per set of weights with hig_gemm_bf16)
+ * instead of being recomputed every sampling step.  t int64 [S] (clamped to the table), xf_proj fp32 [S,E],
+ * out HIG_BF16 or HIG_F32 [S,E]. */
+int hig_time_table_silu(const float* table, int n_steps, const long long* t, const float* xf_proj, int S, int E, void* out,
+                        int out_dtype, void* stream);
 
 /* Sampled motion -> 3-D joints in one launch: tools/visualization.py:149-155 (x[1:]*std+mean, x[0,:4]*init_std+init_mean)
  * followed by utils/motion_process.py recover_from_ric2 (:418-456; recover_root_rot_pos :362-381, qrot/qinv

@@ -470,6 +470,31 @@ def test_ddpm_step_device_seed_matches_immediate_seed(cuda):
         assert torch.equal(a, b) and a.abs().sum() > 0
 
 
+def test_time_table_silu_matches_gemm_epilogue_path(cuda):
+    """SiLU(table[t] + xf_proj) must be bit-identical to the te2 GEMM epilogue it replaces (bias, residual, SiLU)."""
+    ops = _ops()
+    S, E, n = 6, 2048, 50
+    g = torch.Generator(device=cuda).manual_seed(3)
+    h = torch.randn(n, E, device=cuda, generator=g).bfloat16()
+    w = (torch.randn(E, E, device=cuda, generator=g) / 45).bfloat16()
+    b = torch.randn(E, device=cuda, generator=g)
+    xf = torch.randn(S, E, device=cuda, generator=g)
+    t = torch.tensor([49, 0, 7, 7, 31, 120], device=cuda)          # 120: clamped to the last row
+    table = torch.empty(n, E, device=cuda)
+    ops.gemm(h, w, bias=b, out_f32=table)
+    rows = t.clamp(max=n - 1)
+    want = torch.empty(S, E, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(h[rows].contiguous(), w, bias=b, residual=xf, out_bf16=want, act=ops.ACT_SILU)
+    got = torch.empty_like(want)
+    ops.time_table_silu(table, t, xf, got)
+    assert torch.equal(got, want)
+    got32 = torch.empty(S, E, device=cuda)
+    ops.time_table_silu(table, t, xf, got32)
+    assert _rel(got32, F.silu(table[rows] + xf)) < 1e-6
+    with pytest.raises(ValueError):
+        ops.time_table_silu(table, t.int(), xf, got)
+
+
 # ------------------------------------------------------------------------------------------------ sample -> joints
 def _joint_case(cuda):
     import ast

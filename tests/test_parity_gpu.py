@@ -329,7 +329,7 @@ def test_bucketed_generation_and_joints_end_to_end(cuda):
     from hig_b200.ddp import generate_bucketed
     from hig_b200.mul_ddpm_trainer import DDPMMulTrainer
     m, _ = build(1, "bf16", cuda, cap_id=True)
-    opt = argparse.Namespace(device=cuda, multi=True, label_path=None, cap_id=True, diffusion_steps=8, is_train=False)
+    opt = argparse.Namespace(device=cuda, multi=True, label_path=None, cap_id=True, diffusion_steps=50, is_train=False)
     tr = DDPMMulTrainer(opt, m)
     lens = torch.tensor([[40], [12], [33], [40], [7]])
     c1, c2 = [3, 5, 7, 9, 11], [4, 6, 8, 10, 12]

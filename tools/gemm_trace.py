@@ -36,7 +36,8 @@ for name, kind, N, K in CASES:
         else:
             ops.gemm_stream(kind, A, w, b, O)
 
-    buf = torch.zeros(74 * 32, device=dev, dtype=torch.long)
+    NL = 6
+    buf = torch.zeros(NL * 74 * 32, device=dev, dtype=torch.long)
     for _ in range(5):
         run()
     torch.cuda.synchronize()
@@ -47,11 +48,27 @@ for name, kind, N, K in CASES:
     e1.record()
     torch.cuda.synchronize()
     lib.hig_debug_trace(buf.data_ptr())
-    for _ in range(4):
+    for _ in range(NL):
         run()
     torch.cuda.synchronize()
     lib.hig_debug_trace(None)
-    t = buf.view(74, 32).cpu().double()
+    allt = buf.view(NL, 74, 32).cpu().double()
+    # kernel boundary on the global timer: last CTA exit of launch n -> dependents of launch n+1 released (griddepcontrol.wait
+    # returns), and -> first / mean CTA entry of launch n+1
+    for n in range(2, NL - 1):
+        end_n = allt[n, :, 30].max().item()
+        nxt = allt[n + 1]
+        print(f"   boundary {n}->{n + 1}: last exit -> gate open {(nxt[:, 31].min().item() - end_n) / 1e3:6.2f} us | "
+              f"mean exit -> mean entry {(nxt[:, 29].mean().item() - allt[n, :, 30].mean().item()) / 1e3:6.2f} us | "
+              f"entry spread {(nxt[:, 29].max().item() - nxt[:, 29].min().item()) / 1e3:5.2f} us | "
+              f"exit spread {(allt[n, :, 30].max().item() - allt[n, :, 30].min().item()) / 1e3:5.2f} us")
+    t = allt[NL - 1]
+    if os.environ.get("TRACE_PER_PAIR"):
+        # gate -> exit per pair (us) for two consecutive launches: the spread is the tile quantisation (2 vs 3 tiles at N = 512)
+        for n in (NL - 2, NL - 1):
+            a = allt[n]
+            d = (a[:, 30] - a[:, 31]) / 1e3
+            print(f"   launch {n}: gate->exit per pair: " + " ".join(f"{d[p]:.1f}" for p in range(74)))
     rel = t[:, :29] - t[:, :1]
     mean = rel.mean(0)
     ntile = [(t[:, 4 + i] > 0).sum().item() for i in range(8)]
