@@ -40,6 +40,7 @@ SIGNATURES = {
                                c_int, c_void_p],
     "hig_timestep_embed": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_time_table_silu": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
+    "hig_tile_rows": [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p],
     "hig_pack_motion": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_ddpm_step": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ull,
                       c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],

@@ -132,6 +132,10 @@ int hig_time_table_silu(const float* table, int n_steps, const long long* t, con
   return hig::time_table_silu(table, n_steps, t, xf_proj, S, E, out, out_dtype, static_cast<cudaStream_t>(stream));
 }
 
+int hig_tile_rows(const float* table, int period, int width, long long rows, void* out_f16, void* stream) {
+  return hig::tile_rows(table, period, width, rows, out_f16, static_cast<cudaStream_t>(stream));
+}
+
 int hig_debug_trace(unsigned long long* buf) {
   hig::set_gemm_trace(buf);
   return HIG_OK;

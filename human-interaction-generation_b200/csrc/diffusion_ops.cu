@@ -40,6 +40,37 @@ int timestep_embed(const long long* t, const float* freqs, int S, int half, void
 }
 
 // ------------------------------------------------------------------------------------------------
+// tile_rows: out[r, :] = fp16(table[r % period, :]) — seeds the fp16 residual stream with the positional rows
+// (sequence_embedding + joint_embed bias, :593-602) so that the motion embedding becomes an in-place
+// `stream += A.W^T` projection that also leaves the LayerNorm row statistics behind.
+// ------------------------------------------------------------------------------------------------
+__global__ void tile_rows_kernel(const float* __restrict__ table, int period, int width, long long rows, __half* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 8-column group
+  const int gpr = width >> 3;
+  pdl_wait();      // the stream is still read by the previous step's last kernels
+  pdl_trigger();
+  if (idx >= rows * gpr) return;
+  const long long r = idx / gpr;
+  const int c = (int)(idx - r * gpr) * 8;
+  const float* src = table + (size_t)(r % period) * width + c;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+  __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+  *reinterpret_cast<uint4*>(out + (size_t)r * width + c) = *reinterpret_cast<uint4*>(h);
+}
+
+int tile_rows(const float* table, int period, int width, long long rows, void* out_f16, cudaStream_t stream) {
+  if (!table || !out_f16 || period <= 0 || width <= 0 || (width % 8) || rows <= 0)
+    return set_error(HIG_ERR_INVALID, "tile_rows: bad arguments (width must be a multiple of 8)");
+  const long long n = rows * (width / 8);
+  cudaError_t e = launch_pdl(tile_rows_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, table, period, width, rows,
+                             (__half*)out_f16);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("tile_rows launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // time_table_silu: out[s, :] = SiLU(table[t_s, :] + xf_proj[s, :]).  table[n, :] = time_embed(timestep_embedding(n))
 // (:474-478, :591) for every timestep of the schedule, computed once per set of weights with the same GEMM kernels, so
 // the sampling loop replaces the sinusoid kernel and the two M = S GEMMs of the time MLP (8 CTAs each, latency-bound)

@@ -69,6 +69,8 @@ int timestep_embed(const long long* t, const float* freqs, int S, int half, void
 int time_table_silu(const float* table, int n_steps, const long long* t, const float* xf_proj, int S, int E, void* out,
                     int out_dtype, cudaStream_t stream);
 
+int tile_rows(const float* table, int period, int width, long long rows, void* out_f16, cudaStream_t stream);
+
 int pack_motion(const float* x, int S, int T, int C, int ld_out, void* out, int out_dtype, cudaStream_t stream);
 
 int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,

@@ -22,6 +22,7 @@ HBM layout for S sequences x T frames (tok = S*T rows, D = 512):
 Reference: MotionInteractionTransformer.forward, codes/models/interaction_transformer.py:577-616.
 """
 import math
+import os
 
 import torch
 
@@ -85,6 +86,7 @@ class DenoiserEngine:
             pos[0] = m.joint_embed2.bias
             pos[1:] = m.joint_embed.bias[None] + m.sequence_embedding[:m.num_frames - 1]
             W["in.pos"] = pos.contiguous()
+            W["zero.b"] = torch.zeros(self.D, device=dev, dtype=torch.float32)
             W["te0.w"], W["te0.b"] = op(m.time_embed[0].weight), f32(m.time_embed[0].bias)
             W["te2.w"], W["te2.b"] = op(m.time_embed[2].weight), f32(m.time_embed[2].bias)
             emb_w, emb_b = [], []
@@ -320,7 +322,6 @@ class DenoiserEngine:
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         tok = S * T
         q_ca = qkv.view(-1)[:tok * D].view(tok, D)
-        ops.row_stats(xres, stats)
         for li in range(self.L):
             p = f"l{li}."
             last = li == self.L - 1
@@ -392,7 +393,15 @@ class DenoiserEngine:
 
     def embed_motion(self, ws, T):
         W = self.packed()
+        if self.stream and os.environ.get("HIG_EMBED_STREAM", "1") != "0":
+            # stream <- positional rows, then stream += xa . W_in^T on the resident-W kernel, which also leaves the row
+            # statistics the first LayerNorm-folded projection needs (no separate row_stats pass)
+            ops.tile_rows(W["in.pos"], T, ws["xres"])
+            ops.gemm_stream(ops.GS_RES_H, ws["xa"], W["in.w"], W["zero.b"], ws["xres"], stats_out=ws["stats"])
+            return
         self._gemm(ws["xa"], W["in.w"], None, residual=W["in.pos"], res_row_mod=T, out_f32=ws["xres"])
+        if self.stream:
+            ops.row_stats(ws["xres"], ws["stats"])
 
     def run_packed(self, ws, t_dev, xf_proj, a_text, S, T, time_table=None):
         """Everything after pack_motion: ws['xa'] must hold the packed motion, ws['len'] the lengths."""

@@ -231,6 +231,17 @@ def time_table_silu(table, t, xf_proj, out):
     return out
 
 
+def tile_rows(table, period, out):
+    """out[r] = fp16(table[r % period]); table fp32 [>= period, W], out fp16 [rows, W]."""
+    lib = _lib.load()
+    if table.dtype != torch.float32 or out.dtype != torch.float16 or not table.is_contiguous() or not out.is_contiguous() \
+            or table.shape[1] != out.shape[1] or not 0 < period <= table.shape[0]:
+        raise ValueError("hig_b200.tile_rows: table contiguous fp32 [>= period, W], out contiguous fp16 [rows, W]")
+    rc = lib.hig_tile_rows(_ptr(table), period, table.shape[1], out.shape[0], _ptr(out), _stream())
+    _lib.check(rc, "hig_tile_rows")
+    return out
+
+
 def recover_joints(x, mean=None, std=None, init_mean=None, init_std=None, length=None, joints_num=22, init_row=0,
                    out=None):
     """x fp32 [S,T,C] on CUDA -> joints fp32 [S,T-1,joints_num,3] (hig_recover_joints); init_row 0 or -1 / T-1."""

@@ -149,6 +149,11 @@ int hig_ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, co
 int hig_time_table_silu(const float* table, int n_steps, const long long* t, const float* xf_proj, int S, int E, void* out,
                         int out_dtype, void* stream);
 
+/* out[r,:] = fp16(table[r % period,:]), table fp32 [period,width], out fp16 [rows,width], width % 8 == 0: seeds the fp16
+ * residual stream with sequence_embedding + the joint_embed biases (models/interaction_transformer.py:593-602), after
+ * which embed_motion is the in-place projection hig_gemm_stream(HIG_GS_RES_H) on the packed motion operand. */
+int hig_tile_rows(const float* table, int period, int width, long long rows, void* out_f16, void* stream);
+
 /* Sampled motion -> 3-D joints in one launch: tools/visualization.py:149-155 (x[1:]*std+mean, x[0,:4]*init_std+init_mean)
  * followed by utils/motion_process.py recover_from_ric2 (:418-456; recover_root_rot_pos :362-381, qrot/qinv
  * utils/quaternion.py:16-20,54-73).  x fp32 [S,T,C] contiguous, persons stacked on dim 0 (each sequence is processed on
