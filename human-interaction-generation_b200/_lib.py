@@ -42,7 +42,7 @@ SIGNATURES = {
     "hig_time_table_silu": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_tile_rows": [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p],
     "hig_pack_motion": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
-    "hig_ddpm_step": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ull,
+    "hig_ddpm_step": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ull,
                       c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "hig_recover_joints": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                            c_void_p, c_void_p],

@@ -120,10 +120,10 @@ int hig_pack_motion(const float* x, int S, int T, int C, int ld_out, void* out, 
   return hig::pack_motion(x, S, T, C, ld_out, out, out_dtype, static_cast<cudaStream_t>(stream));
 }
 
-int hig_ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
+int hig_ddpm_step(float* x, const void* eps, int ld_eps, int eps_dtype, const float* noise, const long long* t, const float* coef,
                   int n_steps, int S, int T, int C, unsigned long long seed, const unsigned long long* seed_dev, void* packed,
                   int ld_packed, int packed_dtype, long long* t_next, void* stream) {
-  return hig::ddpm_step(x, eps, ld_eps, noise, t, coef, n_steps, S, T, C, seed, seed_dev, packed, ld_packed, packed_dtype,
+  return hig::ddpm_step(x, eps, ld_eps, eps_dtype, noise, t, coef, n_steps, S, T, C, seed, seed_dev, packed, ld_packed, packed_dtype,
                         t_next, static_cast<cudaStream_t>(stream));
 }
 

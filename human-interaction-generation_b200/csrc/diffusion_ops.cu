@@ -176,9 +176,9 @@ HIG_DEVICE float2 box_muller(uint32_t a, uint32_t b) {
 // contraction) and, in the same pass, the packed GEMM operand of the next denoiser call.
 // coef = [5][n_steps] fp32: r = sqrt(1/abar), m = sqrt(1/abar - 1), c1, c2, sigma = exp(0.5*logvar_clipped)
 // ------------------------------------------------------------------------------------------------
-template <typename TPack>
+template <typename TPack, typename TEps>
 __global__ void __launch_bounds__(256)
-ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, int ld_eps, const float* __restrict__ noise,
+ddpm_step_kernel(float* __restrict__ x, const TEps* __restrict__ eps, int ld_eps, const float* __restrict__ noise,
                  const long long* __restrict__ t, const float* __restrict__ coef, int n_steps, int S, int T, int C,
                  unsigned long long seed, const unsigned long long* __restrict__ seed_dev, TPack* __restrict__ packed,
                  int ld_packed) {
@@ -217,7 +217,7 @@ ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, int ld_ep
     const float r = coef[ts], m = coef[n_steps + ts], c1 = coef[2 * n_steps + ts], c2 = coef[3 * n_steps + ts];
     const float sigma = ts > 0 ? coef[4 * n_steps + ts] : 0.f;
     const float xv = x[idx];
-    const float ev = eps[((size_t)s * T + tt) * ld_eps + c];
+    const float ev = static_cast<float>(eps[((size_t)s * T + tt) * ld_eps + c]);
     const float x0 = __fsub_rn(__fmul_rn(r, xv), __fmul_rn(m, ev));
     const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv));
     const float xn = __fadd_rn(mean, __fmul_rn(sigma, z[j]));
@@ -239,21 +239,28 @@ __global__ void advance_t_kernel(const long long* __restrict__ t, long long* __r
   if (i < S) t_next[i] = t[i] - 1;
 }
 
-int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
+int ddpm_step(float* x, const void* eps, int ld_eps, int eps_dtype, const float* noise, const long long* t, const float* coef,
               int n_steps, int S, int T, int C, unsigned long long seed, const unsigned long long* seed_dev, void* packed,
               int ld_packed, int packed_dtype, long long* t_next, cudaStream_t stream) {
   if (!x || !eps || !t || !coef || S <= 0 || T <= 0 || C <= 0 || n_steps <= 0)
     return set_error(HIG_ERR_INVALID, "ddpm_step: bad arguments");
+  if (eps_dtype != HIG_F32 && eps_dtype != HIG_F16) return set_error(HIG_ERR_INVALID, "ddpm_step: eps is fp32 or fp16");
   if (packed && ld_packed < C + 4) return set_error(HIG_ERR_INVALID, "ddpm_step: ld_packed < C+4");
   const long long total = (long long)S * T * C;
   if (total >= (1LL << 31)) return set_error(HIG_ERR_UNSUPPORTED, "ddpm_step: more than 2^31 elements");
   const int blocks = (int)(((total + 3) / 4 + 255) / 256);
-  if (packed && packed_dtype == HIG_BF16)
-    launch_pdl(ddpm_step_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, x, eps, ld_eps, noise, t, coef,
-               n_steps, S, T, C, seed, seed_dev, (__nv_bfloat16*)packed, ld_packed);
-  else
-    ddpm_step_kernel<float><<<blocks, 256, 0, stream>>>(x, eps, ld_eps, noise, t, coef, n_steps, S, T, C, seed, seed_dev,
-                                                        (float*)packed, ld_packed);
+  const bool pk16 = packed && packed_dtype == HIG_BF16;
+  if (eps_dtype == HIG_F16) {
+    if (!pk16) return set_error(HIG_ERR_UNSUPPORTED, "ddpm_step: fp16 eps goes with the bf16 packed operand (product path)");
+    launch_pdl(ddpm_step_kernel<__nv_bfloat16, __half>, dim3(blocks), dim3(256), 0, stream, x, (const __half*)eps, ld_eps,
+               noise, t, coef, n_steps, S, T, C, seed, seed_dev, (__nv_bfloat16*)packed, ld_packed);
+  } else if (pk16) {
+    launch_pdl(ddpm_step_kernel<__nv_bfloat16, float>, dim3(blocks), dim3(256), 0, stream, x, (const float*)eps, ld_eps, noise,
+               t, coef, n_steps, S, T, C, seed, seed_dev, (__nv_bfloat16*)packed, ld_packed);
+  } else {
+    ddpm_step_kernel<float, float><<<blocks, 256, 0, stream>>>(x, (const float*)eps, ld_eps, noise, t, coef, n_steps, S, T, C,
+                                                                seed, seed_dev, (float*)packed, ld_packed);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("ddpm_step launch: ") + cudaGetErrorString(e));
   count_launch();

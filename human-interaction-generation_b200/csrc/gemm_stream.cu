@@ -18,6 +18,8 @@
 //                 Q/K/V projections :119-121,153,190-194: A is the raw fp16 stream, W = gamma o W_qkv in fp16,
 //                 wsum_n = sum_k W_nk, bias_n = b_n + sum_k beta_k Wqkv_nk, (mu, rstd) from the row partials the
 //                 previous ST_RES_H epilogue left behind — the three LayerNorm kernels per layer disappear)
+//   ST_F16        out = acc + bias                                  -> fp16     (output heads out / out2 :613-616 reading the
+//                 fp16 stream directly; resident-W kernel only)
 // Operands are bf16 x bf16 or fp16 x fp16 (kind::f16 instruction descriptor formats), fp32 accumulate.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -42,7 +44,7 @@ constexpr int GS_BAR_BYTES = (2 * GS_STAGES + 4 + 2 * GS_EPI_WARPS) * 8 + 16;
 constexpr int GS_SMEM = GS_STAGES * (GS_A_BYTES + GS_B_BYTES) + GS_EPI_BYTES + GS_BAR_BYTES + 1024;
 static_assert(GS_SMEM <= 232448, "shared memory budget");
 
-enum StreamKind : int { ST_BF16 = 0, ST_BF16_GELU = 1, ST_RES_H = 2, ST_LN_BF16 = 3 };
+enum StreamKind : int { ST_BF16 = 0, ST_BF16_GELU = 1, ST_RES_H = 2, ST_LN_BF16 = 3, ST_F16 = 4 };
 
 struct StreamEpi {
   const float* bias;       // [N]
@@ -446,6 +448,10 @@ HIG_DEVICE void wres_chunk(const uint32_t (&r)[32], const uint32_t (&res)[32], u
         f2_unpack(v[i], lo[i], hi[i]);
       }
       st_shared_u4(addr, pack_h2_sat(lo[0], hi[0]), pack_h2_sat(lo[1], hi[1]), pack_h2_sat(lo[2], hi[2]), pack_h2_sat(lo[3], hi[3]));
+    } else if (KIND == ST_F16) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) f2_unpack(v[i], lo[i], hi[i]);
+      st_shared_u4(addr, pack_h2_sat(lo[0], hi[0]), pack_h2_sat(lo[1], hi[1]), pack_h2_sat(lo[2], hi[2]), pack_h2_sat(lo[3], hi[3]));
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) f2_unpack(v[i], lo[i], hi[i]);
@@ -781,7 +787,7 @@ int gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op
                 const float* bias, const float* wsum, const float* stats_in, float* stats_out, int ln_width,
                 void* out, int ldo, cudaStream_t stream) {
   if (!A || !W || !bias || !out || M <= 0 || N <= 0 || K <= 0) return set_error(HIG_ERR_INVALID, "gemm_stream: null operand or empty shape");
-  if (kind < ST_BF16 || kind > ST_LN_BF16) return set_error(HIG_ERR_INVALID, "gemm_stream: bad kind");
+  if (kind < ST_BF16 || kind > ST_F16) return set_error(HIG_ERR_INVALID, "gemm_stream: bad kind");
   if (op_dtype != HIG_BF16 && op_dtype != HIG_F16) return set_error(HIG_ERR_INVALID, "gemm_stream: operands are bf16 or fp16");
   if ((lda % 8) || (ldw % 8) || (ldo % 8) || (K % 8)) return set_error(HIG_ERR_INVALID, "gemm_stream: leading dims / K must be multiples of 8");
   if (N % 64) return set_error(HIG_ERR_UNSUPPORTED, "gemm_stream: N must be a multiple of 64");
@@ -812,15 +818,17 @@ int gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op
   const bool wres = wres_enabled() && K <= WR_KB * GS_BK && (N % GS_BN) == 0 &&
                     (kind != ST_RES_H || (reinterpret_cast<uintptr_t>(out) & 31) == 0);
   if (wres) {
-    rc = get_tmap_2b(out, M, N, ldo, 32, (kind == ST_RES_H ? 1 : 0) | 2, &tmC);   // 32 x 32 boxes, 64-byte swizzle
+    rc = get_tmap_2b(out, M, N, ldo, 32, ((kind == ST_RES_H || kind == ST_F16) ? 1 : 0) | 2, &tmC);   // 32 x 32 boxes, 64-byte swizzle
     if (rc) return rc;
     switch (kind) {
+      case ST_F16: return launch_wres<ST_F16>(tmA, tmB, tmC, nullptr, 0, M, N, K, ep, f16, stream);
       case ST_BF16: return launch_wres<ST_BF16>(tmA, tmB, tmC, nullptr, 0, M, N, K, ep, f16, stream);
       case ST_BF16_GELU: return launch_wres<ST_BF16_GELU>(tmA, tmB, tmC, nullptr, 0, M, N, K, ep, f16, stream);
       case ST_RES_H: return launch_wres<ST_RES_H>(tmA, tmB, tmC, out, ldo, M, N, K, ep, f16, stream);
       default: return launch_wres<ST_LN_BF16>(tmA, tmB, tmC, nullptr, 0, M, N, K, ep, f16, stream);
     }
   }
+  if (kind == ST_F16) return set_error(HIG_ERR_UNSUPPORTED, "gemm_stream: the fp16-output kind needs K <= 512 and N % 256 == 0");
   rc = get_tmap_2b(out, M, N, ldo, 32, kind == ST_RES_H, &tmC);
   if (rc) return rc;
   switch (kind) {

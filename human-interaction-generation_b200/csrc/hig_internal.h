@@ -73,7 +73,7 @@ int tile_rows(const float* table, int period, int width, long long rows, void* o
 
 int pack_motion(const float* x, int S, int T, int C, int ld_out, void* out, int out_dtype, cudaStream_t stream);
 
-int ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
+int ddpm_step(float* x, const void* eps, int ld_eps, int eps_dtype, const float* noise, const long long* t, const float* coef,
               int n_steps, int S, int T, int C, unsigned long long seed, const unsigned long long* seed_dev, void* packed,
               int ld_packed, int packed_dtype, long long* t_next, cudaStream_t stream);
 

@@ -61,6 +61,8 @@ class DenoiserEngine:
         self._time_table = None
         # product path: projections with the TMA-staged epilogue, pre-attention LayerNorms folded into them
         self.stream = precision == "bf16"
+        # output heads through the resident-W kernel with fp16 eps (HIG_HEADS16=0: the general GEMM with fp32 eps)
+        self.heads16 = self.stream and os.environ.get("HIG_HEADS16", "1") != "0"
 
     # ------------------------------------------------------------------------------------------ weights
     def _param_key(self):
@@ -126,6 +128,15 @@ class DenoiserEngine:
             W["n_styl"] = len(emb_w)
             W["out.w"], W["out.b"] = op(m.out.weight), f32(m.out.bias)
             W["out2.w"], W["out2.b"] = op(m.out2.weight), f32(m.out2.bias)
+            if self.stream:
+                # output heads on the resident-W kernel: fp16 weights padded to 512 rows (N % 256 == 0), reading the fp16
+                # stream directly (no bf16 copy of the stream), eps stored as fp16 [tok, 512]
+                for nm, lin in (("out", m.out), ("out2", m.out2)):
+                    wp = torch.zeros(self.D, self.D, device=dev, dtype=torch.float16)
+                    wp[:self.C] = lin.weight.detach().to(torch.float16)
+                    bp = torch.zeros(self.D, device=dev, dtype=torch.float32)
+                    bp[:self.C] = lin.bias.detach().float()
+                    W[nm + ".w16"], W[nm + ".b16"] = wp, bp
             half = self.D // 2
             W["freqs"] = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(dev)
         self._packed, self._packed_key = W, key
@@ -185,6 +196,7 @@ class DenoiserEngine:
             "temb": e(S, D), "te_h": e(S, self.E), "semb": e(S, self.E),
             "ss": e(S, n_styl * 2 * D, dtype=torch.float32),
             "eps": e(tok, self.LD_EPS, dtype=torch.float32),
+            "eps16": e(tok, D, dtype=torch.float16) if self.stream else None,   # product path: fp16 eps, 512-wide rows
             "len": torch.empty(S, device=dev, dtype=torch.int32),
             "a_blk": e(S, self.H, HEAD_DIM, HEAD_DIM),
             "stats": e(tok, 8, dtype=torch.float32),   # LayerNorm row statistics of the stream (4 partials per row)
@@ -346,10 +358,10 @@ class DenoiserEngine:
             gs(ops.GS_BF16, ws["g"], W[p + "ffn.w2"], W[p + "ffn.b2"], ws["y"])
             ops.ln_film_silu(ws["y"], W[p + "ffn.po.ln.w"], W[p + "ffn.po.ln.b"], sact, rows_per_seq=T,
                              scale_shift=self._ss(ws, W, p + "ffn"), silu=True)
-            if last:
+            if last and not self.heads16:
                 self._project(ws, W, p + "ffn", True)        # also writes the bf16 copy the output heads read
             else:
-                gs(ops.GS_RES_H, sact, W[p + "ffn.po.w"], W[p + "ffn.po.b"], xres, stats_out=stats)
+                gs(ops.GS_RES_H, sact, W[p + "ffn.po.w"], W[p + "ffn.po.b"], xres, stats_out=None if last else stats)
 
     def layers(self, ws, a_text, S, T):
         if self.stream:
@@ -383,13 +395,21 @@ class DenoiserEngine:
             self._stylize_and_project(ws, W, p + "ffn", T, True)
 
     def heads(self, ws, S, T):
-        """out on frames 1.., out2 on frame 0 (:613-616) into eps [tok, 264]."""
+        """out on frames 1.., out2 on frame 0 (:613-616) into eps [tok, 264] fp32 — or, on the product path, into
+        eps16 [tok, 512] fp16 (columns >= 263 are zero) by two resident-W projections that read the fp16 stream."""
         W = self.packed()
+        if self.heads16:
+            eps16, xres = ws["eps16"], ws["xres"]
+            ops.gemm_stream(ops.GS_F16, xres, W["out.w16"], W["out.b16"], eps16)
+            a0 = xres.view(S, T * self.D)[:, :self.D]
+            ops.gemm_stream(ops.GS_F16, a0, W["out2.w16"], W["out2.b16"], eps16.view(S, T * self.D)[:, :self.D])
+            return eps16
         eps, xb = ws["eps"], ws["xb"]
         self._gemm(xb, W["out.w"], W["out.b"], out_f32=eps[:, :self.C])
         a0 = xb.view(S, T * self.D)[:, :self.D]
         o0 = eps.view(S, T * self.LD_EPS)[:, :self.C]
         self._gemm(a0, W["out2.w"], W["out2.b"], out_f32=o0)
+        return eps
 
     def embed_motion(self, ws, T):
         W = self.packed()
@@ -408,8 +428,7 @@ class DenoiserEngine:
         self.embed(ws, t_dev, xf_proj, S, time_table)
         self.embed_motion(ws, T)
         self.layers(ws, a_text, S, T)
-        self.heads(ws, S, T)
-        return ws["eps"]
+        return self.heads(ws, S, T)
 
     def forward(self, x, timesteps, length, xf_proj, xf_out):
         S, T, C = x.shape
@@ -424,4 +443,4 @@ class DenoiserEngine:
         t_dev = timesteps.to(device=x.device, dtype=torch.int64).contiguous()
         xfp = xf_proj.detach().to(torch.float32).contiguous()
         eps = self.run_packed(ws, t_dev, xfp, a_text, S, T)
-        return eps.view(S, T, self.LD_EPS)[:, :, :C].contiguous()
+        return eps.view(S, T, eps.shape[1])[:, :, :C].float().contiguous()

@@ -88,7 +88,7 @@ def gemm(a, w, bias=None, residual=None, res_row_mod=0, out_f32=None, out_bf16=N
     raise TypeError(f"hig_b200.gemm: unsupported dtype {a.dtype}")
 
 
-GS_BF16, GS_BF16_GELU, GS_RES_H, GS_LN_BF16 = 0, 1, 2, 3
+GS_BF16, GS_BF16_GELU, GS_RES_H, GS_LN_BF16, GS_F16 = 0, 1, 2, 3, 4
 
 
 def gemm_stream(kind, a, w, bias, out, wsum=None, stats_in=None, stats_out=None, ln_width=0):
@@ -99,7 +99,7 @@ def gemm_stream(kind, a, w, bias, out, wsum=None, stats_in=None, stats_out=None,
     N = w.shape[0]
     if w.shape[1] != K or a.dtype != w.dtype or a.dtype not in (torch.bfloat16, torch.float16):
         raise TypeError("hig_b200.gemm_stream: A and W must both be bf16 or both fp16, with matching K")
-    want = torch.float16 if kind == GS_RES_H else torch.bfloat16
+    want = torch.float16 if kind in (GS_RES_H, GS_F16) else torch.bfloat16
     if out.dtype != want or tuple(out.shape) != (M, N):
         raise TypeError(f"hig_b200.gemm_stream: out must be {want} [{M},{N}]")
     for t, nm in ((bias, "bias"), (wsum, "wsum"), (stats_in, "stats_in"), (stats_out, "stats_out")):
@@ -210,7 +210,9 @@ def ddpm_step(x, eps, t, coef, noise=None, seed=0, packed=None, t_next=None, see
     if noise is not None and (noise.dtype != torch.float32 or not noise.is_contiguous()):
         raise ValueError("hig_b200.ddpm_step: noise must be contiguous fp32")
     eps2 = eps.reshape(S * T, -1) if eps.dim() == 3 else eps
-    rc = lib.hig_ddpm_step(_ptr(x), _ptr(eps2), eps2.stride(0), _ptr(noise), _ptr(t), _ptr(coef), coef.shape[1],
+    if eps2.dtype not in (torch.float32, torch.float16) or eps2.stride(1) != 1:
+        raise ValueError("hig_b200.ddpm_step: eps must be fp32 or fp16 with unit inner stride")
+    rc = lib.hig_ddpm_step(_ptr(x), _ptr(eps2), eps2.stride(0), _dt(eps2), _ptr(noise), _ptr(t), _ptr(coef), coef.shape[1],
                            S, T, C, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(seed_dev), _ptr(packed),
                            packed.stride(0) if packed is not None else 0,
                            _dt(packed) if packed is not None else F32, _ptr(t_next), _stream())

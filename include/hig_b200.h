@@ -83,6 +83,7 @@ int hig_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int 
 #define HIG_GS_BF16_GELU 1
 #define HIG_GS_RES_H 2
 #define HIG_GS_LN_BF16 3
+#define HIG_GS_F16 4 /* out fp16 = A.W^T + bias (K <= 512, N % 256 == 0): the output heads out / out2 (:613-616) */
 int hig_gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op_dtype, int M, int N, int K,
                     const float* bias, const float* wsum, const float* stats_in, float* stats_out, int ln_width,
                     void* out, int ldo, void* stream);
@@ -135,9 +136,10 @@ int hig_pack_motion(const float* x, int S, int T, int C, int ld_out, void* out, 
  * exp(0.5*posterior_log_variance_clipped)}.  noise nullable -> Philox4x32-10(seed, t, index) + Box-Muller
  * (replaces th.randn_like, :657); seed_dev nullable: when given, the key is read from device memory instead of `seed`,
  * so a CUDA graph holding this launch can be replayed for a new sample after an 8-byte update.
+ * eps [S*T, ld_eps] is HIG_F32 or HIG_F16 (eps_dtype; the product path's output heads write fp16).
  * packed nullable: also writes the next step's pack_motion operand.  t_next nullable: t_next[s] = t[s]-1
  * (may alias t; issued as a trailing launch). */
-int hig_ddpm_step(float* x, const float* eps, int ld_eps, const float* noise, const long long* t, const float* coef,
+int hig_ddpm_step(float* x, const void* eps, int ld_eps, int eps_dtype, const float* noise, const long long* t, const float* coef,
                   int n_steps, int S, int T, int C, unsigned long long seed, const unsigned long long* seed_dev, void* packed,
                   int ld_packed, int packed_dtype, long long* t_next, void* stream);
 

@@ -186,6 +186,32 @@ def test_gemm_stream_layernorm_folded(cuda, M, N):
     assert _rel(out4.float(), ref) < 4e-3
 
 
+def test_gemm_stream_fp16_out_heads(cuda):
+    """HIG_GS_F16 (output heads): fp16 operands, bias, fp16 out; dense rows and the out2 pattern (one row per sequence,
+    row pitch T * 512 on both the operand and the output).  fp16 storage of an fp32-accumulated result: 1e-3."""
+    ops = _ops()
+    g = torch.Generator(device=cuda).manual_seed(9)
+    for M in (1000, 25088):
+        a = torch.randn(M, 512, device=cuda, generator=g).half()
+        w = (torch.randn(512, 512, device=cuda, generator=g) / 22.6).half()
+        w[263:] = 0
+        b = torch.randn(512, device=cuda, generator=g)
+        b[263:] = 0
+        out = torch.full((M, 512), 7.0, device=cuda, dtype=torch.float16)
+        ops.gemm_stream(ops.GS_F16, a, w, b, out)
+        ref = a.float() @ w.float().t() + b
+        assert _rel(out, ref) < 1e-3 and out[:, 263:].abs().max() == 0
+    S, T = 6, 11
+    x = torch.randn(S * T, 512, device=cuda, generator=g).half()
+    o = torch.zeros(S * T, 512, device=cuda, dtype=torch.float16)
+    ops.gemm_stream(ops.GS_F16, x.view(S, T * 512)[:, :512], w, b, o.view(S, T * 512)[:, :512])
+    ref0 = x.view(S, T, 512)[:, 0].float() @ w.float().t() + b
+    assert _rel(o.view(S, T, 512)[:, 0], ref0) < 1e-3 and o.view(S, T, 512)[:, 1:].abs().max() == 0
+    with pytest.raises(RuntimeError):     # K > 512 has no resident-W variant
+        ops.gemm_stream(ops.GS_F16, torch.zeros(256, 1024, device=cuda).half(), torch.zeros(512, 1024, device=cuda).half(), b,
+                        torch.zeros(256, 512, device=cuda).half())
+
+
 def test_gemm_stream_rejects_bad_input(cuda):
     ops = _ops()
     a = torch.zeros(512, 512, device=cuda, dtype=torch.bfloat16)

@@ -94,7 +94,7 @@ W = eng.packed()
 time_fn("embed (time MLP + 32 FiLM linears)", lambda: eng.embed(ws, t, xf_proj, S))
 time_fn("embed_motion", lambda: eng.embed_motion(ws, T))
 time_fn("heads (out / out2)", lambda: eng.heads(ws, S, T))
-time_fn("ddpm_step + pack + t--", lambda: ops.ddpm_step(x, ws["eps"], t, coef, noise=None, seed=1, packed=ws["xa"], t_next=None))
+time_fn("ddpm_step + pack + t--", lambda: ops.ddpm_step(x, ws["eps16"] if eng.heads16 else ws["eps"], t, coef, noise=None, seed=1, packed=ws["xa"], t_next=None))
 D = 512
 qkv = ws["qkv"]
 time_fn("1 x qkv GEMM", lambda: eng._gemm(ws["n"], W["l0.sa.qkv.w"], W["l0.sa.qkv.b"], out=qkv))
