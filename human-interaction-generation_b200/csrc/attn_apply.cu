@@ -90,6 +90,10 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
   ap_commit();
 
   const int g = lane >> 2, tg = lane & 3;
+  // flags: bit 0 = SiLU after the FiLM affine; bit 1 = q already holds softmax_feat(Q) (written by the Q / Q|K|V
+  // projection's epilogue, HIG_GS_LN_QSM): the fragments ldmatrix returns are the MMA operands as they are
+  const bool q_ready = (apply_silu & 2) != 0;
+  apply_silu &= 1;
   const float hs = apply_silu ? 0.5f : 1.0f;
   const uint32_t sAw = sA + w * (AP_HD * 128);
   int buf = 0, cur_s = -1;
@@ -133,6 +137,7 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
     }
     // feature softmax on the fragments: row g <- regs {0,2}, row g+8 <- regs {1,3} of every k-step.  Column pairs stay
     // packed (FFMA2 / FADD2 / FMUL2); exp(x - m) = ex2(x log2e - m log2e) is one packed FMA + one MUFU per element.
+    if (!q_ready) {
     uint64_t x0[8], x1[8];   // pair j of row g / g+8: columns 16 kk + {0,1} (j = 2kk) and 16 kk + 8 + {0,1} (j = 2kk+1) + 2tg
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -182,6 +187,7 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
         f2_unpack(f2_mul(x1[2 * kk + 0], i12), a, b); af[kk][1] = pack_bf16x2(a, b);
         f2_unpack(f2_mul(x1[2 * kk + 1], i12), a, b); af[kk][3] = pack_bf16x2(a, b);
       }
+    }
     }
     float acc[8][4];
 #pragma unroll

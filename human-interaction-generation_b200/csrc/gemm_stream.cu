@@ -20,6 +20,10 @@
 //                 previous ST_RES_H epilogue left behind — the three LayerNorm kernels per layer disappear)
 //   ST_F16        out = acc + bias                                  -> fp16     (output heads out / out2 :613-616 reading the
 //                 fp16 stream directly; resident-W kernel only)
+//   ST_LN_QSM     ST_LN_BF16 whose first 512 output columns — the query block of a Q / Q|K|V projection — are replaced by
+//                 softmax over each head's 64 features (:120,156,195 `F.softmax(query, dim=-1)`): one accumulator row
+//                 chunk pair is exactly one head of one row, so the softmax is lane-local in the epilogue and the
+//                 attention-apply kernel reads ready-made MMA operands (resident-W kernel only)
 // Operands are bf16 x bf16 or fp16 x fp16 (kind::f16 instruction descriptor formats), fp32 accumulate.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -44,7 +48,8 @@ constexpr int GS_BAR_BYTES = (2 * GS_STAGES + 4 + 2 * GS_EPI_WARPS) * 8 + 16;
 constexpr int GS_SMEM = GS_STAGES * (GS_A_BYTES + GS_B_BYTES) + GS_EPI_BYTES + GS_BAR_BYTES + 1024;
 static_assert(GS_SMEM <= 232448, "shared memory budget");
 
-enum StreamKind : int { ST_BF16 = 0, ST_BF16_GELU = 1, ST_RES_H = 2, ST_LN_BF16 = 3, ST_F16 = 4 };
+enum StreamKind : int { ST_BF16 = 0, ST_BF16_GELU = 1, ST_RES_H = 2, ST_LN_BF16 = 3, ST_F16 = 4, ST_LN_QSM = 5 };
+constexpr int QSM_COLS = 512;   // ST_LN_QSM: output columns [0, 512) are the query block (8 heads x 64 features)
 
 struct StreamEpi {
   const float* bias;       // [N]
@@ -411,9 +416,64 @@ HIG_DEVICE void wr_load_res(const __half* p, bool ok, uint32_t (&r)[32]) {
 
 // One 32-column chunk of this lane's accumulator row -> 64 bytes of a sub-slab (16-byte chunks 0..3 of the row,
 // XOR-swizzled with (row >> 1) & 3 as CU_TENSOR_MAP_SWIZZLE_64B expects).  res: 16 registers = the 32 fp16 residuals.
+// The 64 accumulator columns col0 .. col0+63 of this lane's row (one head of the query block) -> in place, as fp32 bit
+// patterns: softmax over the 64 features of LayerNorm-folded projection values.  Same arithmetic as the attention
+// kernels' feature softmax: exp(x - m) = ex2(x log2e - m log2e), sum of the unrounded exponentials, one reciprocal.
+HIG_DEVICE void wres_softmax64(uint32_t (&ra)[32], uint32_t (&rb)[32], const StreamEpi& ep, int col0, float rstd, float nmr) {
+  const float kL2E = 1.4426950408889634f;
+  float m = -INFINITY;
+  auto affine = [&](uint32_t (&r)[32], int c0) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + c0 + 4 * g));
+      const float4 w = __ldg(reinterpret_cast<const float4*>(ep.wsum + c0 + 4 * g));
+      const float v0 = fmaf(rstd, __uint_as_float(r[4 * g + 0]), fmaf(nmr, w.x, b.x));
+      const float v1 = fmaf(rstd, __uint_as_float(r[4 * g + 1]), fmaf(nmr, w.y, b.y));
+      const float v2 = fmaf(rstd, __uint_as_float(r[4 * g + 2]), fmaf(nmr, w.z, b.z));
+      const float v3 = fmaf(rstd, __uint_as_float(r[4 * g + 3]), fmaf(nmr, w.w, b.w));
+      m = fmaxf(m, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));
+      r[4 * g + 0] = __float_as_uint(v0); r[4 * g + 1] = __float_as_uint(v1);
+      r[4 * g + 2] = __float_as_uint(v2); r[4 * g + 3] = __float_as_uint(v3);
+    }
+  };
+  affine(ra, col0);
+  affine(rb, col0 + 32);
+  const float nml = -m * kL2E;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  auto expo = [&](uint32_t (&r)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float e0 = ex2_ftz(fmaf(__uint_as_float(r[i + 0]), kL2E, nml)), e1 = ex2_ftz(fmaf(__uint_as_float(r[i + 1]), kL2E, nml));
+      const float e2 = ex2_ftz(fmaf(__uint_as_float(r[i + 2]), kL2E, nml)), e3 = ex2_ftz(fmaf(__uint_as_float(r[i + 3]), kL2E, nml));
+      s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+      r[i + 0] = __float_as_uint(e0); r[i + 1] = __float_as_uint(e1); r[i + 2] = __float_as_uint(e2); r[i + 3] = __float_as_uint(e3);
+    }
+  };
+  expo(ra);
+  expo(rb);
+  const float inv = 1.0f / ((s0 + s1) + (s2 + s3));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    ra[i] = __float_as_uint(__uint_as_float(ra[i]) * inv);
+    rb[i] = __float_as_uint(__uint_as_float(rb[i]) * inv);
+  }
+}
+
+// final_vals: r already holds the finished fp32 outputs (query-block softmax) — pack and store only
 template <int KIND, int ROFF>
 HIG_DEVICE void wres_chunk(const uint32_t (&r)[32], const uint32_t (&res)[32], uint32_t sub_row, int sw2, const StreamEpi& ep,
-                           int col0, uint64_t rstd2, uint64_t nmr2, uint64_t& s1, uint64_t& s2) {
+                           int col0, uint64_t rstd2, uint64_t nmr2, uint64_t& s1, uint64_t& s2, bool final_vals = false) {
+  constexpr bool IS_LN = KIND == ST_LN_BF16 || KIND == ST_LN_QSM;
+  if (KIND == ST_LN_QSM && final_vals) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      st_shared_u4(sub_row + ((g ^ sw2) << 4),
+                   pack_bf16x2(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1])),
+                   pack_bf16x2(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3])),
+                   pack_bf16x2(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5])),
+                   pack_bf16x2(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
+    return;
+  }
 #pragma unroll
   for (int g = 0; g < 4; ++g) {  // 8 columns -> one 16-byte chunk
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 8 * g));
@@ -422,7 +482,7 @@ HIG_DEVICE void wres_chunk(const uint32_t (&r)[32], const uint32_t (&res)[32], u
     bb[0] = f2_pack(b0.x, b0.y); bb[1] = f2_pack(b0.z, b0.w); bb[2] = f2_pack(b1.x, b1.y); bb[3] = f2_pack(b1.z, b1.w);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = f2_pack_u(r[8 * g + 2 * i], r[8 * g + 2 * i + 1]);
-    if (KIND == ST_LN_BF16) {
+    if (IS_LN) {
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(ep.wsum + col0 + 8 * g));
       const float4 w1 = __ldg(reinterpret_cast<const float4*>(ep.wsum + col0 + 8 * g + 4));
       const uint64_t ww[4] = {f2_pack(w0.x, w0.y), f2_pack(w0.z, w0.w), f2_pack(w1.x, w1.y), f2_pack(w1.z, w1.w)};
@@ -632,7 +692,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int gc0 = n_blk * GS_BN + ch * (GS_BN / 2);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GS_BN + ch * (GS_BN / 2);
       float rstd = 0.f, nmr = 0.f;
-      if (KIND == ST_LN_BF16) {
+      if (KIND == ST_LN_BF16 || KIND == ST_LN_QSM) {
         const int row = min(row0 + lane, M - 1);
         const float4 p0 = __ldg(reinterpret_cast<const float4*>(ep.stats_in + (size_t)row * 8));
         const float4 p1 = __ldg(reinterpret_cast<const float4*>(ep.stats_in + (size_t)row * 8 + 4));
@@ -657,15 +717,18 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tmem_ld_32x32(taddr, ra);
       tmem_ld_32x32(taddr + 32, rb);
       tmem_ld_wait();
+      // query block of a Q / Q|K|V projection: (ra, rb) is one head of this lane's row -> feature softmax in place
+      const bool qsm = KIND == ST_LN_QSM && gc0 < QSM_COLS;
+      if (qsm) wres_softmax64(ra, rb, ep, gc0, rstd, nmr);
       // ---- columns 0..31 -> sub-slab 0, 32..63 -> sub-slab 1 (each store group is waited for two chunks later)
       if (lane == 0) bulk_wait_read<1>();
       __syncwarp();
-      wres_chunk<KIND, 0>(ra, res0, row_s0, sw2, ep, gc0, rstd2, nmr2, s1, s2);
+      wres_chunk<KIND, 0>(ra, res0, row_s0, sw2, ep, gc0, rstd2, nmr2, s1, s2, qsm);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) { tma_store_2d(&tmC, reinterpret_cast<const void*>(sub0), gc0, row0); bulk_commit(); bulk_wait_read<1>(); }
       __syncwarp();
-      wres_chunk<KIND, 16>(rb, res0, row_s1, sw2, ep, gc0 + 32, rstd2, nmr2, s1, s2);
+      wres_chunk<KIND, 16>(rb, res0, row_s1, sw2, ep, gc0 + 32, rstd2, nmr2, s1, s2, qsm);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) { tma_store_2d(&tmC, reinterpret_cast<const void*>(sub0 + WR_SUB), gc0 + 32, row0); bulk_commit(); }
@@ -684,12 +747,13 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) { mbar_arrive_cluster(tempty_bar + as, 0); bulk_wait_read<1>(); }
       __syncwarp();
-      wres_chunk<KIND, 0>(ra, res1, row_s0, sw2, ep, gc0 + 64, rstd2, nmr2, s1, s2);
+      if (qsm) wres_softmax64(ra, rb, ep, gc0 + 64, rstd, nmr);     // gc0 is a multiple of 128: same block as the first head
+      wres_chunk<KIND, 0>(ra, res1, row_s0, sw2, ep, gc0 + 64, rstd2, nmr2, s1, s2, qsm);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) { tma_store_2d(&tmC, reinterpret_cast<const void*>(sub0), gc0 + 64, row0); bulk_commit(); bulk_wait_read<1>(); }
       __syncwarp();
-      wres_chunk<KIND, 16>(rb, res1, row_s1, sw2, ep, gc0 + 96, rstd2, nmr2, s1, s2);
+      wres_chunk<KIND, 16>(rb, res1, row_s1, sw2, ep, gc0 + 96, rstd2, nmr2, s1, s2, qsm);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) { tma_store_2d(&tmC, reinterpret_cast<const void*>(sub0 + WR_SUB), gc0 + 96, row0); bulk_commit(); }
@@ -787,14 +851,15 @@ int gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op
                 const float* bias, const float* wsum, const float* stats_in, float* stats_out, int ln_width,
                 void* out, int ldo, cudaStream_t stream) {
   if (!A || !W || !bias || !out || M <= 0 || N <= 0 || K <= 0) return set_error(HIG_ERR_INVALID, "gemm_stream: null operand or empty shape");
-  if (kind < ST_BF16 || kind > ST_F16) return set_error(HIG_ERR_INVALID, "gemm_stream: bad kind");
+  if (kind < ST_BF16 || kind > ST_LN_QSM) return set_error(HIG_ERR_INVALID, "gemm_stream: bad kind");
   if (op_dtype != HIG_BF16 && op_dtype != HIG_F16) return set_error(HIG_ERR_INVALID, "gemm_stream: operands are bf16 or fp16");
   if ((lda % 8) || (ldw % 8) || (ldo % 8) || (K % 8)) return set_error(HIG_ERR_INVALID, "gemm_stream: leading dims / K must be multiples of 8");
   if (N % 64) return set_error(HIG_ERR_UNSUPPORTED, "gemm_stream: N must be a multiple of 64");
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
       (reinterpret_cast<uintptr_t>(bias) & 15))
     return set_error(HIG_ERR_INVALID, "gemm_stream: operands must be 16-byte aligned");
-  if (kind == ST_LN_BF16) {
+  if (kind == ST_LN_BF16 || kind == ST_LN_QSM) {
+    if (kind == ST_LN_QSM && N < QSM_COLS) return set_error(HIG_ERR_INVALID, "gemm_stream: the query block is the first 512 output columns");
     if (!wsum || !stats_in || ln_width <= 0) return set_error(HIG_ERR_INVALID, "gemm_stream: LN kind needs wsum, stats_in, ln_width");
     if ((reinterpret_cast<uintptr_t>(wsum) & 15) || (reinterpret_cast<uintptr_t>(stats_in) & 15))
       return set_error(HIG_ERR_INVALID, "gemm_stream: wsum / stats_in must be 16-byte aligned");
@@ -822,13 +887,15 @@ int gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op
     if (rc) return rc;
     switch (kind) {
       case ST_F16: return launch_wres<ST_F16>(tmA, tmB, tmC, nullptr, 0, M, N, K, ep, f16, stream);
+      case ST_LN_QSM: return launch_wres<ST_LN_QSM>(tmA, tmB, tmC, nullptr, 0, M, N, K, ep, f16, stream);
       case ST_BF16: return launch_wres<ST_BF16>(tmA, tmB, tmC, nullptr, 0, M, N, K, ep, f16, stream);
       case ST_BF16_GELU: return launch_wres<ST_BF16_GELU>(tmA, tmB, tmC, nullptr, 0, M, N, K, ep, f16, stream);
       case ST_RES_H: return launch_wres<ST_RES_H>(tmA, tmB, tmC, out, ldo, M, N, K, ep, f16, stream);
       default: return launch_wres<ST_LN_BF16>(tmA, tmB, tmC, nullptr, 0, M, N, K, ep, f16, stream);
     }
   }
-  if (kind == ST_F16) return set_error(HIG_ERR_UNSUPPORTED, "gemm_stream: the fp16-output kind needs K <= 512 and N % 256 == 0");
+  if (kind == ST_F16 || kind == ST_LN_QSM)
+    return set_error(HIG_ERR_UNSUPPORTED, "gemm_stream: this kind exists on the resident-W kernel only (K <= 512, N % 256 == 0)");
   rc = get_tmap_2b(out, M, N, ldo, 32, kind == ST_RES_H, &tmC);
   if (rc) return rc;
   switch (kind) {

@@ -64,6 +64,12 @@ class DenoiserEngine:
         # output heads through the resident-W kernel with fp16 eps (HIG_HEADS16=0: the general GEMM with fp32 eps)
         self.heads16 = self.stream and os.environ.get("HIG_HEADS16", "1") != "0"
 
+    @property
+    def qsm(self):
+        """Feature softmax of the queries in the Q / Q|K|V projection's epilogue (resident-W kernel only); read at call
+        time so that HIG_QSM / HIG_WRES can be A/B-toggled between captures."""
+        return self.stream and os.environ.get("HIG_QSM", "1") != "0" and os.environ.get("HIG_WRES", "1") != "0"
+
     # ------------------------------------------------------------------------------------------ weights
     def _param_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.m.parameters())
@@ -300,7 +306,7 @@ class DenoiserEngine:
                          scale_shift=self._ss(ws, W, p), silu=True)
         self._project(ws, W, p, write_xb)
 
-    def _attend(self, ws, W, p, S, T, q, k=None, v=None, a_in=None, pair_shift=0, mask_v=True):
+    def _attend(self, ws, W, p, S, T, q, k=None, v=None, a_in=None, pair_shift=0, mask_v=True, q_softmaxed=False):
         """Attention output -> SiLU(FiLM(LN(.))) in ws['sact'].
         bf16: K/V half (A = softmax_time(K)^T V, 8 MB, stays in L2) then the fused query half + stylization front end:
         the attention output never reaches HBM.  fp32 mode: the unfused validation kernels."""
@@ -311,7 +317,7 @@ class DenoiserEngine:
                 ops.eff_attn(ops.ATTN_KV_ONLY, S, T, H, k=k, v=v, a_out=a_in, length=ws["len"], pair_shift=pair_shift,
                              mask_v=mask_v)
             ops.attn_apply_stylize(q, a_in, W[p + ".po.ln.w"], W[p + ".po.ln.b"], ws["sact"], S, T, H,
-                                   scale_shift=self._ss(ws, W, p), silu=True)
+                                   scale_shift=self._ss(ws, W, p), silu=True, q_softmaxed=q_softmaxed)
             return
         if a_in is not None:
             ops.eff_attn(ops.ATTN_Q_ONLY, S, T, H, q=q, a_in=a_in, y=ws["y"])
@@ -330,6 +336,7 @@ class DenoiserEngine:
         of the stream it has just updated in ws['stats'], the next projection reads the raw fp16 stream."""
         W, D = self.packed(), self.D
         gs = ops.gemm_stream
+        ln_kind = ops.GS_LN_QSM if self.qsm else ops.GS_LN_BF16   # queries leave the projection already softmaxed
         qkv, xres, sact, stats = ws["qkv"], ws["xres"], ws["sact"], ws["stats"]
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         tok = S * T
@@ -338,20 +345,20 @@ class DenoiserEngine:
             p = f"l{li}."
             last = li == self.L - 1
             # --- self attention (:112-130)
-            gs(ops.GS_LN_BF16, xres, W[p + "sa.qkv.wg"], W[p + "sa.qkv.bg"], qkv, wsum=W[p + "sa.qkv.wsum"],
+            gs(ln_kind, xres, W[p + "sa.qkv.wg"], W[p + "sa.qkv.bg"], qkv, wsum=W[p + "sa.qkv.wsum"],
                stats_in=stats, ln_width=D)
-            self._attend(ws, W, p + "sa", S, T, q, k, v, mask_v=True)
+            self._attend(ws, W, p + "sa", S, T, q, k, v, mask_v=True, q_softmaxed=self.qsm)
             gs(ops.GS_RES_H, sact, W[p + "sa.po.w"], W[p + "sa.po.b"], xres, stats_out=stats)
             # --- text cross attention (:145-165), K/V side precomputed in text_state()
-            gs(ops.GS_LN_BF16, xres, W[p + "ca.q.wg"], W[p + "ca.q.bg"], q_ca, wsum=W[p + "ca.q.wsum"],
+            gs(ln_kind, xres, W[p + "ca.q.wg"], W[p + "ca.q.bg"], q_ca, wsum=W[p + "ca.q.wsum"],
                stats_in=stats, ln_width=D)
-            self._attend(ws, W, p + "ca", S, T, q_ca, a_in=a_text[li])
+            self._attend(ws, W, p + "ca", S, T, q_ca, a_in=a_text[li], q_softmaxed=self.qsm)
             gs(ops.GS_RES_H, sact, W[p + "ca.po.w"], W[p + "ca.po.b"], xres, stats_out=stats if self.has_ic else None)
             # --- inter-person cross attention (:181-207): K,V of the partner, mask of the query side
             if self.has_ic:
-                gs(ops.GS_LN_BF16, xres, W[p + "ic.qkv.wg"], W[p + "ic.qkv.bg"], qkv, wsum=W[p + "ic.qkv.wsum"],
+                gs(ln_kind, xres, W[p + "ic.qkv.wg"], W[p + "ic.qkv.bg"], qkv, wsum=W[p + "ic.qkv.wsum"],
                    stats_in=stats, ln_width=D)
-                self._attend(ws, W, p + "ic", S, T, q, k, v, pair_shift=S // 2, mask_v=False)
+                self._attend(ws, W, p + "ic", S, T, q, k, v, pair_shift=S // 2, mask_v=False, q_softmaxed=self.qsm)
                 gs(ops.GS_RES_H, sact, W[p + "ic.po.w"], W[p + "ic.po.b"], xres)
             # --- FFN (:261-264): no pre-norm, linear1 reads the fp16 stream, GELU fused in its epilogue
             gs(ops.GS_BF16_GELU, xres, W[p + "ffn.w1h"], W[p + "ffn.b1"], ws["g"])

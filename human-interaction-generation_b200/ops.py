@@ -88,7 +88,7 @@ def gemm(a, w, bias=None, residual=None, res_row_mod=0, out_f32=None, out_bf16=N
     raise TypeError(f"hig_b200.gemm: unsupported dtype {a.dtype}")
 
 
-GS_BF16, GS_BF16_GELU, GS_RES_H, GS_LN_BF16, GS_F16 = 0, 1, 2, 3, 4
+GS_BF16, GS_BF16_GELU, GS_RES_H, GS_LN_BF16, GS_F16, GS_LN_QSM = 0, 1, 2, 3, 4, 5
 
 
 def gemm_stream(kind, a, w, bias, out, wsum=None, stats_in=None, stats_out=None, ln_width=0):
@@ -100,6 +100,8 @@ def gemm_stream(kind, a, w, bias, out, wsum=None, stats_in=None, stats_out=None,
     if w.shape[1] != K or a.dtype != w.dtype or a.dtype not in (torch.bfloat16, torch.float16):
         raise TypeError("hig_b200.gemm_stream: A and W must both be bf16 or both fp16, with matching K")
     want = torch.float16 if kind in (GS_RES_H, GS_F16) else torch.bfloat16
+    if kind == GS_LN_QSM and (wsum is None or stats_in is None):
+        raise ValueError("hig_b200.gemm_stream: GS_LN_QSM needs wsum and stats_in like GS_LN_BF16")
     if out.dtype != want or tuple(out.shape) != (M, N):
         raise TypeError(f"hig_b200.gemm_stream: out must be {want} [{M},{N}]")
     for t, nm in ((bias, "bias"), (wsum, "wsum"), (stats_in, "stats_in"), (stats_out, "stats_out")):
@@ -162,8 +164,9 @@ def eff_attn(mode, S, T, H, q=None, k=None, v=None, a_in=None, a_out=None, y=Non
     return y if y is not None else a_out
 
 
-def attn_apply_stylize(q, a_in, gamma, beta, out, S, T, H, scale_shift=None, silu=True):
-    """out = [SiLU](LN(concat_h softmax_feat(q_h) @ a_in[s,h]) * (1 + scale) + shift), bf16; q is a [S*T, ld] view."""
+def attn_apply_stylize(q, a_in, gamma, beta, out, S, T, H, scale_shift=None, silu=True, q_softmaxed=False):
+    """out = [SiLU](LN(concat_h softmax_feat(q_h) @ a_in[s,h]) * (1 + scale) + shift), bf16; q is a [S*T, ld] view.
+    q_softmaxed: q already holds softmax_feat(Q) (written by a GS_LN_QSM projection)."""
     lib = _lib.load()
     if q.dtype != torch.bfloat16 or a_in.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
         raise TypeError("hig_b200.attn_apply_stylize: bf16 storage only (fp32 mode uses eff_attn + ln_film_silu)")
@@ -175,7 +178,7 @@ def attn_apply_stylize(q, a_in, gamma, beta, out, S, T, H, scale_shift=None, sil
             raise ValueError("hig_b200.attn_apply_stylize: scale_shift must be fp32 with unit inner stride")
         ss_stride = scale_shift.stride(0)
     rc = lib.hig_attn_apply_stylize(_ptr(q), q.stride(0), _ptr(a_in), _ptr(gamma), _ptr(beta), _ptr(scale_shift),
-                                    ss_stride, 1 if silu else 0, _ptr(out), S, T, H, _stream())
+                                    ss_stride, (1 if silu else 0) | (2 if q_softmaxed else 0), _ptr(out), S, T, H, _stream())
     _lib.check(rc, "hig_attn_apply_stylize")
     return out
 

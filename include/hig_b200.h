@@ -84,6 +84,10 @@ int hig_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int 
 #define HIG_GS_RES_H 2
 #define HIG_GS_LN_BF16 3
 #define HIG_GS_F16 4 /* out fp16 = A.W^T + bias (K <= 512, N % 256 == 0): the output heads out / out2 (:613-616) */
+/* HIG_GS_LN_BF16 whose first 512 output columns (the query block of a Q or Q|K|V projection) are replaced by the softmax
+ * over each head's 64 features — F.softmax(query, dim=-1) of :120,156,195 — computed lane-locally in the epilogue
+ * (K <= 512, N % 256 == 0).  hig_attn_apply_stylize then takes q with flag bit 1 set. */
+#define HIG_GS_LN_QSM 5
 int hig_gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op_dtype, int M, int N, int K,
                     const float* bias, const float* wsum, const float* stats_in, float* stats_out, int ln_width,
                     void* out, int ldo, void* stream);
@@ -116,7 +120,9 @@ int hig_eff_attn(int mode, const void* q, int ldq, const void* k, const void* v,
  *   out[t,:] = SiLU( LN_512( concat_h softmax_feat(Q[t,h]) . A[s,h] ) * (1 + scale_s) + shift_s )
  * (einsum + reshape at models/interaction_transformer.py:128,162,201, then StylizationBlock.forward :86-97 up to its
  * SiLU).  q [S*T, ldq] at head 0, a_in [S,8,64,64] from hig_eff_attn KV_ONLY (which honours `length` and
- * `pair_shift`: the K/V half of the self / inter-person attention), scale_shift as in hig_ln_film_silu, out [S*T,512]. */
+ * `pair_shift`: the K/V half of the self / inter-person attention), scale_shift as in hig_ln_film_silu, out [S*T,512].
+ * apply_silu is a flag word: bit 0 = SiLU after the affine; bit 1 = q already holds softmax_feat(Q) (the projection
+ * that produced it ran with HIG_GS_LN_QSM), so the kernel feeds it to the contraction as it is. */
 int hig_attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
                            const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
                            void* stream);

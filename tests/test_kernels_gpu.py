@@ -186,6 +186,56 @@ def test_gemm_stream_layernorm_folded(cuda, M, N):
     assert _rel(out4.float(), ref) < 4e-3
 
 
+@pytest.mark.parametrize("M,N", [(25088, 1536), (1000, 512), (300, 1536)])
+def test_gemm_stream_layernorm_folded_query_softmax(cuda, M, N):
+    """HIG_GS_LN_QSM: the first 512 output columns hold softmax over each head's 64 features of the LayerNorm-folded
+    projection (F.softmax(query, dim=-1), :120,156,195), the rest equals HIG_GS_LN_BF16.  Softmax outputs are bf16
+    probabilities: 4e-3 relative (bf16 rounding), rows sum to 1 within 64 roundings."""
+    ops = _ops()
+    K = 512
+    g = torch.Generator(device=cuda).manual_seed(N + M + 1)
+    x = (torch.randn(M, K, device=cuda, generator=g) * 1.7 + 0.3).half()
+    gamma = 1 + 0.2 * torch.randn(K, device=cuda, generator=g)
+    beta = 0.1 * torch.randn(K, device=cuda, generator=g)
+    w = 2.0 * torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K)
+    b = torch.randn(N, device=cuda, generator=g)
+    wg = (w * gamma).half()
+    wsum = wg.float().sum(1).contiguous()
+    bias = (b + w @ beta).contiguous()
+    stats = torch.empty(M, 8, device=cuda)
+    ops.row_stats(x, stats)
+    out = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm_stream(ops.GS_LN_QSM, x, wg, bias, out, wsum=wsum, stats_in=stats, ln_width=K)
+    ref = F.layer_norm(x.float(), (K,), gamma, beta) @ w.t() + b
+    ref_q = torch.softmax(ref[:, :512].view(M, 8, 64), dim=-1).view(M, 512)
+    assert _rel(out[:, :512].float(), ref_q) < 6e-3, _rel(out[:, :512].float(), ref_q)
+    assert (out[:, :512].float().view(M, 8, 64).sum(-1) - 1).abs().max() < 2e-2
+    if N > 512:
+        plain = torch.empty_like(out)
+        ops.gemm_stream(ops.GS_LN_BF16, x, wg, bias, plain, wsum=wsum, stats_in=stats, ln_width=K)
+        assert torch.equal(out[:, 512:], plain[:, 512:])
+
+
+def test_attn_apply_takes_presoftmaxed_queries(cuda):
+    """flag bit 1 of hig_attn_apply_stylize: q already holds softmax_feat(Q) in bf16 — same result as handing it the raw
+    queries whose softmax rounds to those bf16 values."""
+    ops = _ops()
+    S, T, H, D = 4, 50, 8, 512
+    g = torch.Generator(device=cuda).manual_seed(77)
+    q = (torch.randn(S * T, D, device=cuda, generator=g) * 1.5).bfloat16()
+    a = (torch.randn(S, H, 64, 64, device=cuda, generator=g) * 0.3).bfloat16()
+    gamma = 1 + 0.1 * torch.randn(D, device=cuda, generator=g)
+    beta = 0.1 * torch.randn(D, device=cuda, generator=g)
+    ss = 0.5 * torch.randn(S, 2 * D, device=cuda, generator=g)
+    qs = torch.softmax(q.float().view(S * T, H, 64), dim=-1).view(S * T, D).bfloat16()
+    o1, o2 = torch.empty(S * T, D, device=cuda, dtype=torch.bfloat16), torch.empty(S * T, D, device=cuda, dtype=torch.bfloat16)
+    ops.attn_apply_stylize(q, a, gamma, beta, o1, S, T, H, scale_shift=ss, silu=True)
+    ops.attn_apply_stylize(qs, a, gamma, beta, o2, S, T, H, scale_shift=ss, silu=True, q_softmaxed=True)
+    y = torch.einsum("nhd,nhdl->nhl", qs.float().view(S * T, H, 64), a.float()[:, None].expand(S, T, H, 64, 64).reshape(S * T, H, 64, 64))
+    ref = F.silu(F.layer_norm(y.reshape(S, T, D), (D,), gamma, beta, 1e-5) * (1 + ss[:, None, :D]) + ss[:, None, D:]).reshape(S * T, D)
+    assert _rel(o2.float(), ref) < 1e-2 and _rel(o1.float(), o2.float()) < 1e-2
+
+
 def test_gemm_stream_fp16_out_heads(cuda):
     """HIG_GS_F16 (output heads): fp16 operands, bias, fp16 out; dense rows and the out2 pattern (one row per sequence,
     row pitch T * 512 on both the operand and the output).  fp16 storage of an fp32-accumulated result: 1e-3."""
