@@ -21,7 +21,7 @@ SIGNATURES = {
     "hig_version": [],
     "hig_last_error": [],
     "hig_launch_count": [],
-    "hig_debug_trace": [c_void_p],
+    "hig_debug_trace": [c_void_p, c_int],
     "hig_l2_persist": [c_void_p, c_ull, ctypes.c_float, c_void_p],
     "hig_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                       c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],

@@ -138,56 +138,56 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
     // feature softmax on the fragments: row g <- regs {0,2}, row g+8 <- regs {1,3} of every k-step.  Column pairs stay
     // packed (FFMA2 / FADD2 / FMUL2); exp(x - m) = ex2(x log2e - m log2e) is one packed FMA + one MUFU per element.
     if (!q_ready) {
-    uint64_t x0[8], x1[8];   // pair j of row g / g+8: columns 16 kk + {0,1} (j = 2kk) and 16 kk + 8 + {0,1} (j = 2kk+1) + 2tg
+      uint64_t x0[8], x1[8];   // pair j of row g / g+8: columns 16 kk + {0,1} (j = 2kk) and 16 kk + 8 + {0,1} (j = 2kk+1) + 2tg
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      x0[2 * kk + 0] = f2_pack_u(af[kk][0] << 16, af[kk][0] & 0xffff0000u);
-      x0[2 * kk + 1] = f2_pack_u(af[kk][2] << 16, af[kk][2] & 0xffff0000u);
-      x1[2 * kk + 0] = f2_pack_u(af[kk][1] << 16, af[kk][1] & 0xffff0000u);
-      x1[2 * kk + 1] = f2_pack_u(af[kk][3] << 16, af[kk][3] & 0xffff0000u);
-    }
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a, b;
-      f2_unpack(x0[j], a, b); m0 = fmaxf(m0, fmaxf(a, b));
-      f2_unpack(x1[j], a, b); m1 = fmaxf(m1, fmaxf(a, b));
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    {
-      const float kL2E = 1.4426950408889634f;
-      const uint64_t l2e = f2_pack(kL2E, kL2E);
-      const uint64_t nm0 = f2_pack(-m0 * kL2E, -m0 * kL2E), nm1 = f2_pack(-m1 * kL2E, -m1 * kL2E);
-      uint64_t sum0 = 0ull, sum1 = 0ull;
+      for (int kk = 0; kk < 4; ++kk) {
+        x0[2 * kk + 0] = f2_pack_u(af[kk][0] << 16, af[kk][0] & 0xffff0000u);
+        x0[2 * kk + 1] = f2_pack_u(af[kk][2] << 16, af[kk][2] & 0xffff0000u);
+        x1[2 * kk + 0] = f2_pack_u(af[kk][1] << 16, af[kk][1] & 0xffff0000u);
+        x1[2 * kk + 1] = f2_pack_u(af[kk][3] << 16, af[kk][3] & 0xffff0000u);
+      }
+      float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float a, b;
-        f2_unpack(f2_fma(x0[j], l2e, nm0), a, b);
-        x0[j] = f2_pack(ex2_ftz(a), ex2_ftz(b));
-        sum0 = f2_add(sum0, x0[j]);
-        f2_unpack(f2_fma(x1[j], l2e, nm1), a, b);
-        x1[j] = f2_pack(ex2_ftz(a), ex2_ftz(b));
-        sum1 = f2_add(sum1, x1[j]);
+        f2_unpack(x0[j], a, b); m0 = fmaxf(m0, fmaxf(a, b));
+        f2_unpack(x1[j], a, b); m1 = fmaxf(m1, fmaxf(a, b));
       }
-      float s0, s1, t0, t1;
-      f2_unpack(sum0, s0, t0);
-      f2_unpack(sum1, s1, t1);
-      s0 += t0;
-      s1 += t1;
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      const float i0 = 1.0f / s0, i1 = 1.0f / s1;
-      const uint64_t i02 = f2_pack(i0, i0), i12 = f2_pack(i1, i1);
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      {
+        const float kL2E = 1.4426950408889634f;
+        const uint64_t l2e = f2_pack(kL2E, kL2E);
+        const uint64_t nm0 = f2_pack(-m0 * kL2E, -m0 * kL2E), nm1 = f2_pack(-m1 * kL2E, -m1 * kL2E);
+        uint64_t sum0 = 0ull, sum1 = 0ull;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        float a, b;
-        f2_unpack(f2_mul(x0[2 * kk + 0], i02), a, b); af[kk][0] = pack_bf16x2(a, b);
-        f2_unpack(f2_mul(x0[2 * kk + 1], i02), a, b); af[kk][2] = pack_bf16x2(a, b);
-        f2_unpack(f2_mul(x1[2 * kk + 0], i12), a, b); af[kk][1] = pack_bf16x2(a, b);
-        f2_unpack(f2_mul(x1[2 * kk + 1], i12), a, b); af[kk][3] = pack_bf16x2(a, b);
+        for (int j = 0; j < 8; ++j) {
+          float a, b;
+          f2_unpack(f2_fma(x0[j], l2e, nm0), a, b);
+          x0[j] = f2_pack(ex2_ftz(a), ex2_ftz(b));
+          sum0 = f2_add(sum0, x0[j]);
+          f2_unpack(f2_fma(x1[j], l2e, nm1), a, b);
+          x1[j] = f2_pack(ex2_ftz(a), ex2_ftz(b));
+          sum1 = f2_add(sum1, x1[j]);
+        }
+        float s0, s1, t0, t1;
+        f2_unpack(sum0, s0, t0);
+        f2_unpack(sum1, s1, t1);
+        s0 += t0;
+        s1 += t1;
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+        const uint64_t i02 = f2_pack(i0, i0), i12 = f2_pack(i1, i1);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          float a, b;
+          f2_unpack(f2_mul(x0[2 * kk + 0], i02), a, b); af[kk][0] = pack_bf16x2(a, b);
+          f2_unpack(f2_mul(x0[2 * kk + 1], i02), a, b); af[kk][2] = pack_bf16x2(a, b);
+          f2_unpack(f2_mul(x1[2 * kk + 0], i12), a, b); af[kk][1] = pack_bf16x2(a, b);
+          f2_unpack(f2_mul(x1[2 * kk + 1], i12), a, b); af[kk][3] = pack_bf16x2(a, b);
+        }
       }
-    }
     }
     float acc[8][4];
 #pragma unroll

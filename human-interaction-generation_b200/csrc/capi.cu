@@ -136,8 +136,8 @@ int hig_tile_rows(const float* table, int period, int width, long long rows, voi
   return hig::tile_rows(table, period, width, rows, out_f16, static_cast<cudaStream_t>(stream));
 }
 
-int hig_debug_trace(unsigned long long* buf) {
-  hig::set_gemm_trace(buf);
+int hig_debug_trace(unsigned long long* buf, int max_launches) {
+  hig::set_gemm_trace(buf, max_launches);
   return HIG_OK;
 }
 

@@ -785,10 +785,13 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-// debug: set through hig_debug_trace; every traced launch takes the next block of 74 * 32 slots (the caller sizes the
-// buffer for the launches it makes before clearing the pointer)
+// debug: set through hig_debug_trace(buf, max_launches); every traced launch takes the next block of 74 * 32 slots
 static unsigned long long* g_trace = nullptr;
-void set_gemm_trace(unsigned long long* buf) { g_trace = buf; }
+static int g_trace_left = 0;
+void set_gemm_trace(unsigned long long* buf, int max_launches) {
+  g_trace = max_launches > 0 ? buf : nullptr;
+  g_trace_left = g_trace ? max_launches : 0;
+}
 
 // ---------------------------------------------------------------------------------------------- host side
 int get_tmap_2b(const void* ptr, int rows, int cols, int ld, int box_rows, int is_f16, CUtensorMap* out);  // gemm_tcgen05.cu
@@ -834,7 +837,10 @@ static int launch_wres(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   if (const char* pe = getenv("HIG_GS_PAIRS")) { const int v = atoi(pe); if (v > 0 && v < pairs) pairs = v; }  // experiment knob
   cudaError_t e = launch_pdl(kern, dim3(2 * pairs), dim3(GS_THREADS), WR_SMEM, stream, tmA, tmB, tmC,
                              static_cast<const __half*>(resid), ldr, M, N, K, ep, f16_ops, g_trace);
-  if (g_trace != nullptr) g_trace += 74 * 32;
+  if (g_trace != nullptr) {   // next traced launch takes the next block; tracing switches itself off when the buffer is full
+    g_trace += 74 * 32;
+    if (--g_trace_left <= 0) g_trace = nullptr;
+  }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("resident-W gemm launch: ") + cudaGetErrorString(e));
   count_launch();

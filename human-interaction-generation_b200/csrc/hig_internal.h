@@ -47,7 +47,7 @@ int gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op
                 const float* bias, const float* wsum, const float* stats_in, float* stats_out, int ln_width,
                 void* out, int ldo, cudaStream_t stream);
 
-void set_gemm_trace(unsigned long long* buf);
+void set_gemm_trace(unsigned long long* buf, int max_launches);
 
 int row_stats(const void* x, int x_dtype, int rows, int width, float* stats, cudaStream_t stream);
 

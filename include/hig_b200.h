@@ -41,9 +41,10 @@ const char* hig_last_error(void);
 unsigned long long hig_launch_count(void);
 
 /* Debug aid (no reference counterpart): when buf != NULL the resident-W projection kernel writes 32 clock64 / globaltimer
- * slots per CTA pair into buf, each launch taking the next block of 74 * 32 entries (size buf for the launches made
- * before clearing it) — tile-by-tile timeline read by tools/gemm_trace.py; NULL disables. */
-int hig_debug_trace(unsigned long long* buf);
+ * slots per CTA pair into buf, each launch taking the next block of 74 * 32 entries; tracing stops by itself after
+ * max_launches launches (buf holds max_launches * 74 * 32 entries) — tile-by-tile timeline read by tools/gemm_trace.py;
+ * NULL or max_launches <= 0 disables. */
+int hig_debug_trace(unsigned long long* buf, int max_launches);
 
 /* L2 residency hint (no reference counterpart): pins [ptr, ptr+bytes) — the fp32 residual stream — in the 126 MB L2
  * through an access-policy window on `stream`; ptr == NULL clears it. */

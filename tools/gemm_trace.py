@@ -47,11 +47,11 @@ for name, kind, N, K in CASES:
         run()
     e1.record()
     torch.cuda.synchronize()
-    lib.hig_debug_trace(buf.data_ptr())
+    lib.hig_debug_trace(buf.data_ptr(), NL)
     for _ in range(NL):
         run()
     torch.cuda.synchronize()
-    lib.hig_debug_trace(None)
+    lib.hig_debug_trace(None, 0)
     allt = buf.view(NL, 74, 32).cpu().double()
     # kernel boundary on the global timer: last CTA exit of launch n -> dependents of launch n+1 released (griddepcontrol.wait
     # returns), and -> first / mean CTA entry of launch n+1
