@@ -13,7 +13,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 dev = torch.device("cuda:0")
 model = bench.build_model(dev)
 eng = model.engine()
-S, T, C = 128, 196, 263
+S, T, C = int(os.environ.get("BD_S", "128")), 196, 263   # BD_S: sequences (C2 = 128; 1024 = the C3 batch on one GPU)
 g = torch.Generator(device=dev).manual_seed(0)
 xf_proj = torch.randn(S, 2048, device=dev, generator=g) * 0.5
 xf_out = torch.randn(S, 77, 256, device=dev, generator=g)
