@@ -127,7 +127,7 @@ def make_trainer(model, device, steps):
 
 def time_qkv_kernel(device, peak_burst):
     """The dominant kernel alone: the LayerNorm-folded SA/IC QKV projection [25088 x 1536 x 512] exactly as the step
-    launches it (hig_gemm_stream, HIG_GS_LN_BF16 -> resident-W CTA-pair tcgen05 kernel).  30 back-to-back launches
+    launches it (hig_gemm_stream, HIG_GS_LN_QSM -> resident-W CTA-pair tcgen05 kernel, query block softmaxed in the epilogue).  30 back-to-back launches
     between two CUDA events on the launching stream, operands rotating through 6 sets (617 MB, 5x the L2) so that no
     launch finds its input or output lines cached.  `traffic` = DRAM bytes per launch of the same kernel from the
     committed ncu --set full capture (profiles/r01d_ncu_full_summary.txt: 30.6 MB read + 31.1 MB written, cold L2)."""
@@ -140,7 +140,7 @@ def time_qkv_kernel(device, peak_burst):
     stats = torch.empty(M, 8, device=device)
     ops.row_stats(a[0], stats)
     o = [torch.empty(M, N, device=device, dtype=torch.bfloat16) for _ in range(R)]
-    run = lambda i: ops.gemm_stream(ops.GS_LN_BF16, a[i % R], w, b, o[i % R], wsum=wsum, stats_in=stats, ln_width=K)
+    run = lambda i: ops.gemm_stream(ops.GS_LN_QSM, a[i % R], w, b, o[i % R], wsum=wsum, stats_in=stats, ln_width=K)
     for i in range(R):
         run(i)
     ts = []
@@ -155,7 +155,7 @@ def time_qkv_kernel(device, peak_burst):
         ts.append(e0.elapsed_time(e1) * 1e-3 / 30)
     t = sorted(ts)[len(ts) // 2]
     ach = 2.0 * M * N * K / t / 1e12
-    return {"name": "gemm_wres_kernel<LN_BF16> (QKV 25088x1536x512, LayerNorm folded)", "us": t * 1e6, "achieved": ach,
+    return {"name": "gemm_wres_kernel<LN_QSM> (QKV 25088x1536x512, LayerNorm folded, query softmax)", "us": t * 1e6, "achieved": ach,
             "peak": peak_burst, "unit": "TFLOP/s", "frac": ach / peak_burst,
             "l2": "30 back-to-back launches over 6 rotating operand sets (617 MB > L2)", "traffic": 61.7e6}
 
