@@ -559,9 +559,23 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int n_tiles = N / GS_BN;                       // N % 256 == 0 (host-checked)
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (K + GS_BK - 1) / GS_BK;        // <= WR_KB (host-checked)
-  // column-block-major order, one contiguous range of tiles per pair (sizes differ by at most one)
-  const int lo = (int)((long long)num_tiles * pair / num_pairs);
-  const int hi = (int)((long long)num_tiles * (pair + 1) / num_pairs);
+  // column-block-major order, one contiguous range of tiles per pair (sizes differ by at most one).  With the query softmax
+  // in the epilogue the query-block tiles (first in this order) are epilogue-bound and cost ~5/4 of a plain tile
+  // (measured 3.9 vs 3.2 us), so the ranges are cut by weight: pairs on query tiles take ~6.9 tiles, the others ~8.6.
+  int lo, hi;
+  if (KIND == ST_LN_QSM && n_tiles > QSM_COLS / GS_BN) {
+    const long long tq = (long long)(QSM_COLS / GS_BN) * m_tiles;
+    const long long wtot = 5 * tq + 4 * ((long long)num_tiles - tq);
+    auto cut = [&](long long p) {
+      const long long w = wtot * p / num_pairs;
+      return (int)(w <= 5 * tq ? w / 5 : tq + (w - 5 * tq) / 4);
+    };
+    lo = cut(pair);
+    hi = cut(pair + 1);
+  } else {
+    lo = (int)((long long)num_tiles * pair / num_pairs);
+    hi = (int)((long long)num_tiles * (pair + 1) / num_pairs);
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
