@@ -218,10 +218,12 @@ class DenoiserEngine:
     def text_state(self, xf_out):
         """A_text[l] = softmax_tokens(K_l)^T V_l for every layer: depends only on xf_out, so it is computed once
         per batch and reused by all 1000 steps (the reference recomputes it every step, :145-161)."""
-        key = (xf_out.data_ptr(), xf_out._version, tuple(xf_out.shape))
-        if self._text_cache is not None and self._text_cache[0] == key:
-            return self._text_cache[1]
+        # keyed on the tensor OBJECT (kept alive by the cache, so its address cannot be recycled for another batch's text),
+        # its version counter and the weights it was projected with
         W = self.packed()
+        c = self._text_cache
+        if c is not None and c[0] is xf_out and c[1] == (xf_out._version, self.packed_generation):
+            return c[2]
         S, N, Dt = xf_out.shape
         dt, dev = self.act_dtype, xf_out.device
         xf = xf_out.detach().to(torch.float32).contiguous().view(S * N, Dt)
@@ -233,7 +235,7 @@ class DenoiserEngine:
             ops.ln_film_silu(xf, W[p + "tln.w"], W[p + "tln.b"], tn)
             self._gemm(tn, W[p + "kv.w"], W[p + "kv.b"], out=kv)
             ops.eff_attn(ops.ATTN_KV_ONLY, S, N, self.H, k=kv[:, :self.D], v=kv[:, self.D:], a_out=a_all[i])
-        self._text_cache = (key, a_all)
+        self._text_cache = (xf_out, (xf_out._version, self.packed_generation), a_all)
         return a_all
 
     # ------------------------------------------------------------------------------------------ helpers

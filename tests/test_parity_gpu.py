@@ -340,3 +340,26 @@ def test_bucketed_generation_and_joints_end_to_end(cuda):
     js = tr.generate_joints(c1, c2, lens.view(-1), 263, mean=mean, std=std, init_mean=im, init_std=isd)
     assert [j1.shape for j1, _ in js] == [(n - 1, 22, 3) for n in (40, 12, 33, 40, 7)]
     assert all(torch.isfinite(j1).all() and torch.isfinite(j2).all() for j1, j2 in js)
+
+
+def test_text_state_cache_not_fooled_by_recycled_memory(cuda):
+    """The step-invariant text state (A_text) is cached per xf_out tensor.  A second batch whose xf_out lands on the
+    recycled address of the first (the caching allocator hands the freed block straight back) must not hit that cache."""
+    import weights
+    m, _ = build(1, "bf16", cuda)
+    m.cap_id = False
+    inp = weights.make_inputs(31, 4, 24, n_text=77, lengths=[24, 10, 24, 10])
+    g = lambda k: inp[k].to(cuda)
+    x, t, ln, xp = g("x"), g("t"), g("length"), g("xf_proj")
+    with torch.no_grad():
+        a = g("xf_out")
+        ptr_a = a.data_ptr()
+        ya = m(x, t, length=ln, xf_proj=xp, xf_out=a)
+        del a
+        b = (inp["xf_out"] * -1.5 + 0.3).to(cuda)          # different text, same shape: usually the same address
+        same_address = b.data_ptr() == ptr_a
+        yb = m(x, t, length=ln, xf_proj=xp, xf_out=b)
+        m.engine()._text_cache = None
+        yb_fresh = m(x, t, length=ln, xf_proj=xp, xf_out=b)
+    print(f"xf_out address recycled: {same_address}")
+    assert torch.equal(yb, yb_fresh) and not torch.equal(ya, yb)
