@@ -27,6 +27,33 @@ def test_library_exports_every_declared_symbol():
     assert lib.hig_launch_count() == 0 or lib.hig_launch_count() > 0
 
 
+def test_ctypes_prototypes_match_header_arity_and_kinds():
+    """Header / binding drift check: every prototype in include/hig_b200.h has as many parameters as its ctypes
+    argtypes entry, pointers are bound as c_void_p and scalars as the matching C integer / float type."""
+    import ctypes
+    import hig_b200  # noqa: F401
+    from hig_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "hig_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(?:int|unsigned long long|const char\*)\s+(hig_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)
+    assert len(protos) == len(_lib.SIGNATURES)
+    for name, params in protos:
+        params = [p.strip() for p in params.split(",") if p.strip() and p.strip() != "void"]
+        argtypes = _lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for p_decl, at in zip(params, argtypes):
+            if "*" in p_decl:
+                assert at is ctypes.c_void_p, (name, p_decl)
+            elif p_decl.startswith("unsigned long long"):
+                assert at is ctypes.c_ulonglong, (name, p_decl)
+            elif p_decl.startswith("long long"):
+                assert at is ctypes.c_longlong, (name, p_decl)
+            elif p_decl.startswith("float"):
+                assert at is ctypes.c_float, (name, p_decl)
+            else:
+                assert p_decl.startswith("int ") and at is ctypes.c_int, (name, p_decl)
+
+
 def test_product_path_refuses_cpu_tensors():
     import pytest
     import torch
