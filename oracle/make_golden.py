@@ -27,6 +27,8 @@ CASES = {
                           n_text=77),
     "loop": dict(layers=2, S=2, T=16, seed=14, lengths=[16, 11], mode="text", n_text=5, steps=50),
     "train": dict(layers=2, S=4, T=12, seed=15, lengths=[12, 7, 12, 7], mode="text", n_text=3),
+    # BASELINE config 1 exactly: full-depth denoiser, one pair, 196 frames, the 50-step schedule (CPU plumbing case)
+    "c1": dict(layers=8, S=2, T=196, seed=17, lengths=[196, 196], mode="text", n_text=77, steps=50),
     # sample -> joints post-processing (tools/visualization.py:149-155 + utils/motion_process.recover_from_ric2)
     "joints": dict(S=6, T=24, seed=16),
 }
@@ -92,7 +94,7 @@ def main():
         if name.startswith("fwd"):
             with torch.no_grad():
                 out["eps"] = ref_forward(m, inp, c["mode"]).numpy()
-        elif name == "loop":
+        elif name in ("loop", "c1"):
             steps = c["steps"]
             noise = weights.make_noise(c["seed"] + 100, steps, c["S"], c["T"])
             diff = gd.GaussianDiffusion(betas=gd.get_named_beta_schedule("linear", steps),

@@ -72,6 +72,21 @@ def test_sampling_loop_matches_reference_golden():
     assert rel(final, d["final"]) < 1e-3, rel(final, d["final"])
 
 
+def test_c1_full_depth_50_step_sample_matches_reference_golden():
+    """BASELINE config 1 (8 layers, one pair, 196 frames, 50-step schedule) end to end on the CPU: the oracle's final
+    sample against the real reference's (tests/golden/c1.npz).  |x| grows to 2e4 through the untrained network; two fp32
+    evaluations with different op order stay within 1e-3 relative."""
+    d, cfg, sd, inp = load_case("c1")
+    sch = DF.Schedule(cfg["steps"])
+    noise = weights.make_noise(cfg["seed"] + 100, cfg["steps"], cfg["S"], cfg["T"])
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    with torch.no_grad():
+        final, _ = DF.p_sample_loop(
+            sch, lambda x, t: DO.denoiser_forward(sd, x, t, inp["length"], inp["xf_proj"], inp["xf_out"]), noise)
+    assert torch.isfinite(final).all()
+    assert rel(final, d["final"]) < 1e-3, rel(final, d["final"])
+
+
 def test_training_terms_match_reference_golden():
     d, cfg, sd, inp = load_case("train")
     sch = DF.Schedule(1000)
