@@ -141,8 +141,8 @@ def test_sampling_loop_golden_and_graph(cuda, precision):
     assert torch.equal(a, b) and torch.equal(a, c)
     err = rel(a, d["final"])
     print(f"loop {precision}: final-sample rel-L2 vs reference {err:.3e}")
-    # 50 steps through an untrained eps-network are expansive (|x| reaches 1e4): fp32-vs-fp32 sits at
-    # ~1e-4; bf16 is only required to stay finite and in the same regime here (per-step parity is the bf16 gate)
+    # 50 steps through an untrained eps-network are expansive (|x| reaches 1e4).  Measured on B200: fp32
+    # mode 3.3e-7, bf16 2.9e-3 .. 4.0e-3 relative; gates 1e-4 and 5e-2 (per-step parity is the primary bf16 gate)
     assert err < (1e-4 if precision == "fp32" else 5e-2), err
     if precision == "fp32":
         # final sampled joints: the chain's |x| reaches 1e4, so the comparison is made on the sample rescaled to unit RMS
@@ -386,4 +386,4 @@ def test_c1_full_depth_50_step_sample_against_reference_golden(cuda, precision):
     err = rel(out, d["final"])
     print(f"C1 {precision}: final-sample rel-L2 vs reference {err:.3e}")
     assert torch.isfinite(out).all()
-    assert err < (2e-3 if precision == "fp32" else 0.5), err
+    assert err < (1e-4 if precision == "fp32" else 5e-2), err
