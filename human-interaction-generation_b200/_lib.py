@@ -38,6 +38,9 @@ SIGNATURES = {
                      c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "hig_attn_apply_stylize": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                                c_int, c_void_p],
+    "hig_attn_kv": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "hig_attn_apply_stylize_tc": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                  c_int, c_int, c_void_p],
     "hig_timestep_embed": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_time_table_silu": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_tile_rows": [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p],
@@ -49,6 +52,8 @@ SIGNATURES = {
     "hig_q_sample": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
     # training path
     "hig_gemm_bf16_splitk": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
+    "hig_gemm_bf16_t": [c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                        c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
     "hig_transpose": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
                       c_void_p],
     "hig_colsum": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],

@@ -301,6 +301,8 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
 constexpr int KV_THREADS = 256;
 constexpr int KV_WARPS = 8;
 
+// TRANSPOSED: the output is A^T[s,h] ([l][d]) — the K-major B operand attn_apply_tc_kernel's tcgen05.mma reads.
+template <bool TRANSPOSED>
 __global__ void __launch_bounds__(KV_THREADS, 4)
 attn_kv_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int ldkv,
                __nv_bfloat16* __restrict__ a_out, const int* __restrict__ length, int S, int T, int pair_shift) {
@@ -418,18 +420,20 @@ attn_kv_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restr
   const int dw = (warp & 3) * 16, lw = (warp >> 2) * 32;
   const int kend = (len + 15) & ~15;
   for (int kt = 0; kt < kend; kt += 16) {
+    // TRANSPOSED: A^T[l,d] = sum_t V[t,l] e[t,d] — the same loop with the roles of the two tiles swapped
+    const uint32_t sRowOp = TRANSPOSED ? sV : sK, sColOp = TRANSPOSED ? sK : sV;
     uint32_t a[4];
     {
       const int row = kt + (lane & 7) + ((lane >> 4) & 1) * 8;
       const int c = (dw >> 3) + ((lane >> 3) & 1);
-      ap_ldsm_x4_t(sK + ap_swz(row, c), a[0], a[1], a[2], a[3]);
+      ap_ldsm_x4_t(sRowOp + ap_swz(row, c), a[0], a[1], a[2], a[3]);
     }
 #pragma unroll
     for (int np = 0; np < 2; ++np) {
       uint32_t b0, b1, b2, b3;
       const int row = kt + (lane & 7) + ((lane >> 3) & 1) * 8;
       const int c = (lw >> 3) + np * 2 + ((lane >> 4) & 1);
-      ap_ldsm_x4_t(sV + ap_swz(row, c), b0, b1, b2, b3);
+      ap_ldsm_x4_t(sColOp + ap_swz(row, c), b0, b1, b2, b3);
       ap_mma(acc[2 * np], a, b0, b1);
       ap_mma(acc[2 * np + 1], a, b2, b3);
     }
@@ -440,13 +444,19 @@ attn_kv_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restr
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
     const int col = lw + nt * 8 + 2 * tg;
-    *reinterpret_cast<uint32_t*>(dst + (dw + g) * AP_HD + col) = pack_bf16x2(acc[nt][0] * i0, acc[nt][1] * i0);
-    *reinterpret_cast<uint32_t*>(dst + (dw + g + 8) * AP_HD + col) = pack_bf16x2(acc[nt][2] * i1, acc[nt][3] * i1);
+    if (TRANSPOSED) {   // rows are l, columns are d: the softmax normaliser belongs to the column
+      const float c0 = sinv[col], c1 = sinv[col + 1];
+      *reinterpret_cast<uint32_t*>(dst + (dw + g) * AP_HD + col) = pack_bf16x2(acc[nt][0] * c0, acc[nt][1] * c1);
+      *reinterpret_cast<uint32_t*>(dst + (dw + g + 8) * AP_HD + col) = pack_bf16x2(acc[nt][2] * c0, acc[nt][3] * c1);
+    } else {
+      *reinterpret_cast<uint32_t*>(dst + (dw + g) * AP_HD + col) = pack_bf16x2(acc[nt][0] * i0, acc[nt][1] * i0);
+      *reinterpret_cast<uint32_t*>(dst + (dw + g + 8) * AP_HD + col) = pack_bf16x2(acc[nt][2] * i1, acc[nt][3] * i1);
+    }
   }
 }
 
 int attn_kv(const void* k, const void* v, int ldkv, void* a_out, const int* length, int S, int T, int H,
-            int pair_shift, cudaStream_t stream) {
+            int pair_shift, int transposed, cudaStream_t stream) {
   if (!k || !v || !a_out || S <= 0 || T <= 0 || H <= 0) return set_error(HIG_ERR_INVALID, "attn_kv: bad arguments");
   if (T > 256) return set_error(HIG_ERR_UNSUPPORTED, "attn_kv: T > 256 not supported");
   if (ldkv % 8) return set_error(HIG_ERR_INVALID, "attn_kv: ldkv must be a multiple of 8");
@@ -454,12 +464,14 @@ int attn_kv(const void* k, const void* v, int ldkv, void* a_out, const int* leng
   const size_t smem = (size_t)2 * TP * 128 + (KV_WARPS + 1) * 64 * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_kv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_kv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_kv attr: ") + cudaGetErrorString(e));
     configured = smem;
   }
-  cudaError_t e = launch_pdl(attn_kv_kernel, dim3(H, S), dim3(KV_THREADS), smem, stream, (const __nv_bfloat16*)k,
-                             (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)a_out, length, S, T, pair_shift);
+  cudaError_t e = launch_pdl(transposed ? attn_kv_kernel<true> : attn_kv_kernel<false>, dim3(H, S), dim3(KV_THREADS), smem,
+                             stream, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)a_out, length, S,
+                             T, pair_shift);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_kv launch: ") + cudaGetErrorString(e));
   count_launch();

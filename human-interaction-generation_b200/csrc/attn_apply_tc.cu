@@ -1,0 +1,388 @@
+// hig_attn_apply_stylize on tcgen05 / TMEM (product path): the query half of the efficient attention fused with the
+// StylizationBlock front end, one 128-row tile of one sequence per step of a persistent CTA:
+//
+//   Y[t, 64h : 64h+64] = Qs[t, 64h : 64h+64] . A[s, h]            8 heads -> 8 x (4 x tcgen05.mma M=128 N=64 K=16)
+//   out[t, :]          = SiLU( LayerNorm_512(Y[t, :]) (1 + scale_s) + shift_s )
+//
+// (einsum 'bnhd,bhdl->bnhl' + reshape of LinearTemporal{Self,Cross,InteractionCross}Attention.forward,
+// codes/models/interaction_transformer.py:128,162,201, then StylizationBlock.forward's norm / FiLM / SiLU :86-97.)
+//
+// Why tcgen05 here although the contraction is < 2 % of the step's FLOPs: the 128 x 512 fp32 tile lands in the SM's
+// whole TMEM (128 lanes x 512 columns) with ONE ROW PER LANE, so the LayerNorm statistics of a row are a lane-local
+// sum over tcgen05.ld chunks — no ldmatrix / mma.sync / quad-shuffle / shared-memory-statistics dependency chain, which
+// is what held the mma.sync kernel of attn_apply.cu at 26.6 us against a 7.9 us HBM floor (0.30 of peak, 44 % issue
+// active at 16 warps per SM; profiles/r01e_ncu_full_summary.txt).  Y never exists outside TMEM.
+//
+// Operands: Qs = softmax_feat(Q) as the Q / Q|K|V projection's epilogue leaves it (bf16, HIG_GS_LN_QSM), streamed
+// head by head (128 rows x 64 columns = 16 KB, K-major, 128B swizzle) through a 5-stage TMA ring; A^T[s, h] ([l][d],
+// i.e. the K-major B operand; written in that layout by attn_kv_kernel / the text precompute) resident for the tile
+// (8 x 8 KB).  3-D tensor maps [S][T][cols] clip rows >= T on load (zero fill) and on store.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 epilogue (TMEM lane quarter = warp % 4,
+// column half = (warp - 2) / 4): pass 1 row statistics, one 64-thread named barrier per quarter to swap the two column
+// halves' partials, pass 2 normalise + FiLM + SiLU -> bf16 -> 128B-swizzled 32 x 64 slabs -> TMA store.
+#include <cuda.h>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include "hig_common.cuh"
+#include "hig_internal.h"
+
+namespace hig {
+
+namespace atc {
+constexpr int THREADS = 320;
+constexpr int STAGES = 5;
+constexpr int Q_BYTES = 128 * 64 * 2;          // one head block of the tile
+constexpr int A_BYTES = 8 * 64 * 64 * 2;       // A^T of the 8 heads
+constexpr int SLAB = 32 * 128;                 // 32 rows x 64 bf16 columns
+constexpr int EPI_BYTES = 8 * 2 * SLAB;        // two slabs per epilogue warp
+constexpr int GB_BYTES = 2 * 2 * 512 * 4;      // (G, B) x two tile parities
+constexpr int RED_BYTES = 8 * 32 * 8;
+constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+constexpr int SMEM = STAGES * Q_BYTES + A_BYTES + EPI_BYTES + GB_BYTES + RED_BYTES + BAR_BYTES + 1024;
+static_assert(SMEM <= 232448, "shared memory budget");
+
+HIG_DEVICE void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+HIG_DEVICE void tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+HIG_DEVICE void bulk_commit_g() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> HIG_DEVICE void bulk_wait_read_g() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> HIG_DEVICE void bulk_wait_g() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+HIG_DEVICE void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+HIG_DEVICE float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+HIG_DEVICE void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+}  // namespace atc
+using namespace atc;
+
+__global__ void __launch_bounds__(atc::THREADS, 1)
+attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmA,
+                     const __grid_constant__ CUtensorMap tmO, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ scale_shift, int ss_stride, int apply_silu,
+                     int S, int T) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sAT = sQ + STAGES * Q_BYTES;
+  uint8_t* sEpi = sAT + A_BYTES;
+  float* sGB = reinterpret_cast<float*>(sEpi + EPI_BYTES);            // [parity][G | B][512]
+  float2* sRed = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(sGB) + GB_BYTES);   // [8 warps][32 lanes]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sRed) + RED_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* afull_bar = empty_bar + STAGES;
+  uint64_t* afree_bar = afull_bar + 1;
+  uint64_t* tfull_bar = afree_bar + 1;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = T > 128 ? 2 : 1;            // tiles per sequence: rows [0, 128) and [128, T)
+  const int num_tiles = S * nt;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(afull_bar, 1);
+    mbar_init(afree_bar, 1);
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile i: the first S tiles are rows [0, 128) of sequence i, the next S rows [128, T) of sequence i - S
+  auto tile_seq = [&](int i) { return i < S ? i : i - S; };
+  auto tile_row0 = [&](int i) { return i < S ? 0 : 128; };
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      pdl_wait();        // Qs and A^T are the outputs of the two previous kernels
+      pdl_trigger();
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int s = tile_seq(tile), r0 = tile_row0(tile);
+        if (lt > 0) mbar_wait(afree_bar, (lt - 1u) & 1u);     // the previous tile's MMAs have read A^T
+        mbar_arrive_expect_tx(afull_bar, A_BYTES);
+#pragma unroll
+        for (int h = 0; h < 8; ++h) tma_load_2d(sAT + h * 8192, &tmA, afull_bar, 0, (s * 8 + h) * 64);
+        for (int h = 0; h < 8; ++h, ++it) {
+          const uint32_t stage = it % STAGES, phase = (it / STAGES) & 1u;
+          mbar_wait(empty_bar + stage, phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar + stage, Q_BYTES);
+          tma_load_3d(sQ + stage * Q_BYTES, &tmQ, full_bar + stage, h * 64, r0, s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        mbar_wait(afull_bar, lt & 1u);
+        mbar_wait(tempty_bar, (lt & 1u) ^ 1u);     // the epilogue has drained the previous tile's accumulator
+        tc_fence_after();
+        for (int h = 0; h < 8; ++h, ++it) {
+          const uint32_t stage = it % STAGES, phase = (it / STAGES) & 1u;
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + stage * Q_BYTES));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sAT + h * 8192));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + h * 64, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);
+          umma_commit(empty_bar + stage);
+        }
+        umma_commit(tfull_bar);
+        umma_commit(afree_bar);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue warps 2..9 =================
+    const int ew = warp - 2;
+    const int q = warp & 3;            // TMEM lane quarter (hardware rule: warp id % 4)
+    const int ch = ew >> 2;            // column half
+    const int et = threadIdx.x - 64;   // 0..255
+    const uint32_t slab0 = smem_u32(sEpi) + ew * 2 * SLAB;
+    const uint32_t row_s[2] = {slab0 + lane * 128, slab0 + SLAB + lane * 128};
+    const int sw = lane & 7;
+    const bool silu = (apply_silu & 1) != 0;
+    const float hs = silu ? 0.5f : 1.0f;     // SiLU(x) = h + h tanh(h), h = x / 2: the affine carries the 1/2
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int s = tile_seq(tile), r0 = tile_row0(tile);
+      const uint32_t par = lt & 1u;
+      // folded FiLM affine of this sequence: out = n_hat * G + B,  G = gamma (1 + scale),  B = beta (1 + scale) + shift
+      float* sG = sGB + par * 1024;
+      float* sB = sG + 512;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = et + 256 * j;
+        float gg = __ldg(gamma + c), bb = __ldg(beta + c);
+        if (scale_shift != nullptr) {
+          const float m1 = 1.0f + __ldg(scale_shift + (size_t)s * ss_stride + c);
+          gg *= m1;
+          bb = fmaf(bb, m1, __ldg(scale_shift + (size_t)s * ss_stride + 512 + c));
+        }
+        sG[c] = gg * hs;
+        sB[c] = bb * hs;
+      }
+      named_bar(5, 256);
+      const int qrow0 = r0 + q * 32;
+      const bool live = qrow0 < T;       // warp-uniform: this quarter holds at least one valid row
+      mbar_wait(tfull_bar, par);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ch * 256;
+      // ---- pass 1: row statistics over this warp's 256 columns
+      uint64_t s1 = 0ull, s2 = 0ull;
+      if (live) {
+#pragma unroll 2
+        for (int c = 0; c < 8; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t v = f2_pack_u(r[2 * i], r[2 * i + 1]);
+            s1 = f2_add(s1, v);
+            s2 = f2_fma(v, v, s2);
+          }
+        }
+      }
+      {
+        float a0, a1, b0, b1;
+        f2_unpack(s1, a0, a1);
+        f2_unpack(s2, b0, b1);
+        sRed[ew * 32 + lane] = make_float2(a0 + a1, b0 + b1);
+      }
+      named_bar(1 + q, 64);              // the two column halves of this lane quarter
+      float rstd, nmr;
+      {
+        const float2 mine = sRed[ew * 32 + lane], other = sRed[(ew ^ 4) * 32 + lane];
+        const float mean = (mine.x + other.x) * (1.0f / 512.0f);
+        const float var = fmaxf(fmaf(mine.y + other.y, 1.0f / 512.0f, -mean * mean), 0.f);
+        rstd = rsqrtf(var + 1e-5f);
+        nmr = -mean * rstd;
+      }
+      const uint64_t rstd2 = f2_pack(rstd, rstd), nmr2 = f2_pack(nmr, nmr);
+      // ---- pass 2: normalise + FiLM + SiLU -> bf16 -> slab -> TMA store (64 columns per slab, 4 slabs per warp)
+      if (live) {
+        const uint32_t gB = smem_u32(sG) + ch * 1024, bB = smem_u32(sB) + ch * 1024;
+#pragma unroll 1
+        for (int sl = 0; sl < 4; ++sl) {
+          if (lane == 0) bulk_wait_read_g<1>();     // the store issued from this slab two slabs ago has been read out
+          __syncwarp();
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t r[32];
+            const int c32 = sl * 2 + hf;             // 32-column chunk of this warp's half
+            tmem_ld_32x32(taddr + c32 * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {         // 8 columns -> one 16-byte chunk
+              const uint32_t off = (uint32_t)(c32 * 32 + g8 * 8) * 4;
+              const float4 G0 = lds_f4(gB + off), G1 = lds_f4(gB + off + 16);
+              const float4 B0 = lds_f4(bB + off), B1 = lds_f4(bB + off + 16);
+              const uint64_t GG[4] = {f2_pack(G0.x, G0.y), f2_pack(G0.z, G0.w), f2_pack(G1.x, G1.y), f2_pack(G1.z, G1.w)};
+              const uint64_t BB[4] = {f2_pack(B0.x, B0.y), f2_pack(B0.z, B0.w), f2_pack(B1.x, B1.y), f2_pack(B1.z, B1.w)};
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint64_t v = f2_fma(f2_pack_u(r[8 * g8 + 2 * i], r[8 * g8 + 2 * i + 1]), rstd2, nmr2);
+                v = f2_fma(v, GG[i], BB[i]);
+                float a, b;
+                f2_unpack(v, a, b);
+                if (silu) {
+                  v = f2_fma(v, f2_pack(tanh_approx_f(a), tanh_approx_f(b)), v);
+                  f2_unpack(v, a, b);
+                }
+                pk[i] = pack_bf16x2(a, b);
+              }
+              sts_u4(row_s[sl & 1] + (((hf * 4 + g8) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          if (sl == 3) {                 // every tcgen05.ld of this tile has completed: hand TMEM back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmO, slab0 + (sl & 1) * SLAB, ch * 256 + sl * 64, qrow0, s);
+            bulk_commit_g();
+          }
+        }
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar);
+      }
+    }
+    if (lane == 0) bulk_wait_g<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// bf16 [S][T][cols] with row pitch ld (elements) and sequence pitch T * ld; box = [1][box_rows][64 cols], 128B swizzle
+static int get_tmap_3d(const void* ptr, int S, int T, int cols, int ld, int box_rows, CUtensorMap* out) {
+  struct Key {
+    const void* p; int S, T, cols, ld, br;
+    bool operator==(const Key& o) const { return p == o.p && S == o.S && T == o.T && cols == o.cols && ld == o.ld && br == o.br; }
+  };
+  struct KH {
+    size_t operator()(const Key& k) const {
+      size_t h = reinterpret_cast<size_t>(k.p);
+      h ^= (size_t)k.S * 0x9E3779B97F4A7C15ull + (h << 6);
+      h ^= (size_t)k.T * 0xC2B2AE3D27D4EB4Full + (h >> 3);
+      h ^= (size_t)(k.cols * 31 + k.ld) * 0x165667B19E3779F9ull + (h << 9);
+      h ^= (size_t)k.br * 0x27D4EB2F165667C5ull;
+      return h;
+    }
+  };
+  static std::unordered_map<Key, CUtensorMap, KH> cache;
+  static std::mutex mu;
+  static PFN_encodeTiled3 enc = []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<PFN_encodeTiled3>(p);
+    return (PFN_encodeTiled3) nullptr;
+  }();
+  Key key{ptr, S, T, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto itr = cache.find(key);
+    if (itr != cache.end()) { *out = itr->second; return HIG_OK; }
+  }
+  if (!enc) return set_error(HIG_ERR_NO_DRIVER, "cuTensorMapEncodeTiled not available");
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)S};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap tm;
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(HIG_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed: " + std::to_string((int)r));
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 1024) cache.clear();
+    cache[key] = tm;
+  }
+  *out = tm;
+  return HIG_OK;
+}
+
+int get_tmap_2b(const void* ptr, int rows, int cols, int ld, int box_rows, int flags, CUtensorMap* out);  // gemm_tcgen05.cu
+int device_num_sms();
+
+// q: Qs (bf16, already softmaxed over each head's 64 features), a_t: A^T [S, 8, 64 (l), 64 (d)] bf16
+int attn_apply_stylize_tc(const void* q, int ldq, const void* a_t, const float* gamma, const float* beta,
+                          const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
+                          cudaStream_t stream) {
+  if (!q || !a_t || !gamma || !beta || !out || S <= 0 || T <= 0)
+    return set_error(HIG_ERR_INVALID, "attn_apply_stylize_tc: bad arguments");
+  if (H != 8) return set_error(HIG_ERR_UNSUPPORTED, "attn_apply_stylize_tc: built for 8 heads x 64 (latent_dim 512)");
+  if (T > 256) return set_error(HIG_ERR_UNSUPPORTED, "attn_apply_stylize_tc: T > 256 not supported");
+  if (ldq % 8) return set_error(HIG_ERR_INVALID, "attn_apply_stylize_tc: ldq must be a multiple of 8");
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(a_t) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return set_error(HIG_ERR_INVALID, "attn_apply_stylize_tc: pointers must be 16-byte aligned");
+  CUtensorMap tmQ, tmA, tmO;
+  int rc = get_tmap_3d(q, S, T, 512, ldq, 128, &tmQ);
+  if (rc) return rc;
+  rc = get_tmap_2b(a_t, S * 8 * 64, 64, 64, 64, 0, &tmA);
+  if (rc) return rc;
+  rc = get_tmap_3d(out, S, T, 512, 512, 32, &tmO);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::SMEM);
+    if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_apply_stylize_tc attr: ") + cudaGetErrorString(e));
+    attr = true;
+  }
+  const int tiles = S * (T > 128 ? 2 : 1);
+  int ctas = device_num_sms();
+  if (ctas > tiles) ctas = tiles;
+  cudaError_t e = launch_pdl(attn_apply_tc_kernel, dim3(ctas), dim3(atc::THREADS), atc::SMEM, stream, tmQ, tmA, tmO,
+                             gamma, beta, scale_shift, ss_stride, apply_silu, S, T);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_apply_stylize_tc launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
+}  // namespace hig

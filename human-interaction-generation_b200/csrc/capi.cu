@@ -160,10 +160,29 @@ int hig_attn_apply_stylize(const void* q, int ldq, const void* a_in, const float
                                  static_cast<cudaStream_t>(stream));
 }
 
+int hig_attn_kv(const void* k, const void* v, int ldkv, void* a_out, const int* length, int S, int T, int H,
+                int pair_shift, int transposed, void* stream) {
+  return hig::attn_kv(k, v, ldkv, a_out, length, S, T, H, pair_shift, transposed, static_cast<cudaStream_t>(stream));
+}
+
+int hig_attn_apply_stylize_tc(const void* q, int ldq, const void* a_t, const float* gamma, const float* beta,
+                              const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
+                              void* stream) {
+  return hig::attn_apply_stylize_tc(q, ldq, a_t, gamma, beta, scale_shift, ss_stride, apply_silu, out, S, T, H,
+                                    static_cast<cudaStream_t>(stream));
+}
+
 // ---------------------------------------------------------------- training path
 int hig_gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32,
                          int ldo_f32, int k_splits, void* stream) {
   return hig::gemm_bf16_splitk(A, lda, W, ldw, M, N, K, out_f32, ldo_f32, k_splits, static_cast<cudaStream_t>(stream));
+}
+
+int hig_gemm_bf16_t(int trans_a, int trans_b, const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                    const float* bias, const float* residual, int ldr, float* out_f32, int ldo_f32, void* out_bf16,
+                    int ldo_bf16, int split_k, void* stream) {
+  return hig::gemm_bf16_t(trans_a, trans_b, A, lda, W, ldw, M, N, K, bias, residual, ldr, out_f32, ldo_f32, out_bf16,
+                          ldo_bf16, split_k, static_cast<cudaStream_t>(stream));
 }
 
 int hig_transpose(const void* in, int in_dtype, int M, int N, int ld_in, void* outT, int ld_t, void* copy, int ld_c,

@@ -404,7 +404,7 @@ int eff_attn(int mode, const void* q, int ldq, const void* k, const void* v, int
   // bf16 K/V half: dedicated kernel (4 CTAs per SM).  The mask makes V*mask and unmasked V equivalent (Ks == 0).
   if (dtype == HIG_BF16 && mode == 2 && (ldkv % 8) == 0 && !(reinterpret_cast<uintptr_t>(k) & 15) &&
       !(reinterpret_cast<uintptr_t>(v) & 15))
-    return attn_kv(k, v, ldkv, a_out, length, S, T, H, pair_shift, stream);
+    return attn_kv(k, v, ldkv, a_out, length, S, T, H, pair_shift, 0, stream);
   if (dtype == HIG_BF16) {
     if ((do_q && ((ldq % 8) || (ldy % 8))) || (do_kv && (ldkv % 8)))
       return set_error(HIG_ERR_INVALID, "eff_attn: bf16 leading dimensions must be multiples of 8");

@@ -15,10 +15,15 @@
 //        3 Q_ONLY   q, a_in, dY                              -> dq, dA (fp32, output)  (text query side)
 // All arithmetic is fp32 on CUDA cores; storage type (bf16 / fp32) is a template parameter.  Shared memory holds
 // Ks and V for the whole sequence, A and dA, and a 32-row chunk of (Qs, dY) at a time.
+#include <cstdlib>
 #include "hig_common.cuh"
 #include "hig_internal.h"
 
 namespace hig {
+
+int eff_attn_bwd_tc(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
+                    const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
+                    const int* length, int S, int T, int H, int pair_shift, cudaStream_t stream);
 
 constexpr int BW_HD = 64;
 constexpr int BW_LD = 65;       // padded fp32 row
@@ -217,6 +222,15 @@ int eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void* v,
   const size_t smem = ((size_t)(do_kv ? 2 * T : 0) * BW_LD + 2 * BW_HD * BW_LD + 2 * BW_CHUNK * BW_LD + 4 * 64) * sizeof(float);
   dim3 grid(H, S);
   cudaError_t e;
+  if (dtype == HIG_BF16) {
+    // tensor-core kernel (eff_attn_bwd_tc.cu); HIG_ATTN_BWD_TC=0 keeps the CUDA-core kernel below for A/B runs
+    static const bool use_tc = []() { const char* ev = getenv("HIG_ATTN_BWD_TC"); return !(ev && ev[0] == '0'); }();
+    if (use_tc) {
+      const int rc = eff_attn_bwd_tc(mode, q, ldq, k, v, ldkv, a_in, dy, lddy, dq, lddq, dk, dv, lddkv, dA, length, S, T,
+                                     H, pair_shift, stream);
+      if (rc != HIG_ERR_UNSUPPORTED) return rc;
+    }
+  }
   if (dtype == HIG_BF16) {
     using bf = __nv_bfloat16;
     static size_t configured = 0;

@@ -31,7 +31,12 @@ constexpr int G2_EPI_BYTES = G2_EPI_WARPS * 32 * 32 * 4;
 constexpr int G2_BAR_BYTES = (2 * G2_STAGES + 4) * 8 + 16;
 constexpr int G2_SMEM = G2_STAGES * (G2_A_BYTES + G2_B_BYTES) + G2_EPI_BYTES + G2_BAR_BYTES + 1024;
 
-template <int KIND>
+// TA / TB = 1: the operand is given "MN-major" — A as [K, M] row-major (A^T in memory), W as [K, N] row-major — and is
+// consumed as it lies: TMA boxes of 64 k-rows x 64 MN-columns (128 B, 128B swizzle), two per CTA per stage, described to
+// the tensor core with MN-major shared-memory descriptors (instruction-descriptor bits 15 / 16).  This is what lets the
+// training path compute  dW = dY^T X  (both operands token-major) and  dX = dY W  (W as stored) without ever
+// materialising a transposed copy.
+template <int KIND, int TA, int TB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                       int K, GemmEpilogue ep, int vec_ok, int k_splits) {
@@ -97,17 +102,29 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint32_t phase = (it / G2_STAGES) & 1u;
           mbar_wait(empty_bar + stage, phase ^ 1u);
           if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * (G2_A_BYTES + G2_B_BYTES));
-          tma_load_2d_2cta(sA + stage * G2_A_BYTES, &tmA, full_bar + stage, kb * G2_BK,
-                           m_blk * 2 * G2_BM + (int)rank * G2_BM);
-          tma_load_2d_2cta(sB + stage * G2_B_BYTES, &tmB, full_bar + stage, kb * G2_BK,
-                           n_blk * G2_BN + (int)rank * (G2_BN / 2));
+          if (TA) {   // [K, M] source: two boxes of 64 k-rows x 64 m-columns
+            tma_load_2d_2cta(sA + stage * G2_A_BYTES, &tmA, full_bar + stage, m_blk * 2 * G2_BM + (int)rank * G2_BM, kb * G2_BK);
+            tma_load_2d_2cta(sA + stage * G2_A_BYTES + G2_A_BYTES / 2, &tmA, full_bar + stage,
+                             m_blk * 2 * G2_BM + (int)rank * G2_BM + 64, kb * G2_BK);
+          } else {
+            tma_load_2d_2cta(sA + stage * G2_A_BYTES, &tmA, full_bar + stage, kb * G2_BK,
+                             m_blk * 2 * G2_BM + (int)rank * G2_BM);
+          }
+          if (TB) {
+            tma_load_2d_2cta(sB + stage * G2_B_BYTES, &tmB, full_bar + stage, n_blk * G2_BN + (int)rank * (G2_BN / 2), kb * G2_BK);
+            tma_load_2d_2cta(sB + stage * G2_B_BYTES + G2_B_BYTES / 2, &tmB, full_bar + stage,
+                             n_blk * G2_BN + (int)rank * (G2_BN / 2) + 64, kb * G2_BK);
+          } else {
+            tma_load_2d_2cta(sB + stage * G2_B_BYTES, &tmB, full_bar + stage, kb * G2_BK,
+                             n_blk * G2_BN + (int)rank * (G2_BN / 2));
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * G2_BM, G2_BN);
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * G2_BM, G2_BN) | (TA ? (1u << 15) : 0u) | (TB ? (1u << 16) : 0u);
       uint32_t it = 0, lt = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
         const uint32_t as = lt & 1u;
@@ -122,11 +139,15 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint32_t phase = (it / G2_STAGES) & 1u;
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
-          const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * G2_A_BYTES));
-          const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * G2_B_BYTES));
+          // K-major: a k-step of 16 elements is 32 B inside the 128-byte swizzle row (+2 in 16-byte units);
+          // MN-major: a k-step is two 8-row groups of 1024 B (+128), the two 64-wide MN blocks lie 8 KB apart (LBO)
+          const uint64_t da = TA ? umma_desc_mn_sw128(smem_u32(sA + stage * G2_A_BYTES), G2_A_BYTES / 2)
+                                 : umma_desc_k_sw128(smem_u32(sA + stage * G2_A_BYTES));
+          const uint64_t db = TB ? umma_desc_mn_sw128(smem_u32(sB + stage * G2_B_BYTES), G2_B_BYTES / 2)
+                                 : umma_desc_k_sw128(smem_u32(sB + stage * G2_B_BYTES));
 #pragma unroll
           for (int k = 0; k < G2_BK / 16; ++k)
-            umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            umma_f16_2cta(tmem_d, da + (TA ? 128 : 2) * k, db + (TB ? 128 : 2) * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           umma_commit_2cta_mc(empty_bar + stage, 0b11);  // frees this smem slot in both CTAs
         }
         umma_commit_2cta_mc(tfull_bar + as, 0b11);  // accumulator halves ready in both CTAs
@@ -192,11 +213,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
-template <int KIND>
+template <int KIND, int TA = 0, int TB = 0>
 static int launch_2cta_kind(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
                             int vec_ok, int num_sms, int k_splits, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kern = gemm_bf16_2cta_kernel<KIND>;
+  auto kern = gemm_bf16_2cta_kernel<KIND, TA, TB>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
     if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("cudaFuncSetAttribute(2cta): ") + cudaGetErrorString(e));
@@ -225,6 +246,23 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int 
     case EPI_RES_H_BF16: return launch_2cta_kind<EPI_RES_H_BF16>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
     default: return launch_2cta_kind<EPI_GENERIC>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
   }
+}
+
+// transposed-operand variants (training dgrad / wgrad): bf16 / fp32-residual / generic (split-K atomics) epilogues only
+int launch_gemm_2cta_t(int ta, int tb, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
+                       const GemmEpilogue& ep, int vec_ok, int num_sms, int k_splits, cudaStream_t stream) {
+  int kind = (ep.act >= 100) ? EPI_GENERIC : classify_epilogue(ep, vec_ok, N);
+  if (kind != EPI_BF16 && kind != EPI_RES_F32) kind = EPI_GENERIC;
+#define HIG_G2T(KD)                                                                                                   \
+  do {                                                                                                                \
+    if (ta && tb) return launch_2cta_kind<KD, 1, 1>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);         \
+    if (ta) return launch_2cta_kind<KD, 1, 0>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);               \
+    return launch_2cta_kind<KD, 0, 1>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);                       \
+  } while (0)
+  if (kind == EPI_BF16) HIG_G2T(EPI_BF16);
+  if (kind == EPI_RES_F32) HIG_G2T(EPI_RES_F32);
+  HIG_G2T(EPI_GENERIC);
+#undef HIG_G2T
 }
 
 }  // namespace hig

@@ -384,6 +384,57 @@ int gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int N, i
                         r16 ? residual : nullptr, ldr, o16 ? out : nullptr, ldo);
 }
 
+int launch_gemm_2cta_t(int ta, int tb, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
+                       const GemmEpilogue& ep, int vec_ok, int num_sms, int k_splits, cudaStream_t stream);
+
+// C[M,N] (+)= opA(A) . opB(W)^T with either operand given MN-major (contraction index on the rows):
+//   trans_a: A is stored [K, M] (lda = its row pitch)      trans_b: W is stored [K, N] (ldw = its row pitch)
+// Training path:  dW[n,k] = sum_m dY[m,n] X[m,k]  -> trans_a = trans_b = 1 (A = dY, W = X, contraction = tokens, split-K);
+//                 dX[m,k] = sum_n dY[m,n] W[n,k]  -> trans_b = 1 (A = dY K-major as stored, W = the weight as stored).
+// split_k != 0: fp32 atomic accumulation into out_f32 (caller initialises it); no bias / residual / bf16 output then.
+int gemm_bf16_t(int trans_a, int trans_b, const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                const float* bias, const float* residual, int ldr, float* out_f32, int ldo_f32, void* out_bf16,
+                int ldo_bf16, int split_k, cudaStream_t stream) {
+  if (!trans_a && !trans_b)
+    return gemm_bf16_impl(A, lda, W, ldw, M, N, K, bias, residual, ldr, 0, out_f32, ldo_f32, out_bf16, ldo_bf16, 0,
+                          split_k, stream);
+  if (!A || !W || M <= 0 || N <= 0 || K <= 0) return set_error(HIG_ERR_INVALID, "gemm_t: null operand or empty shape");
+  if (!out_f32 && !out_bf16) return set_error(HIG_ERR_INVALID, "gemm_t: no output");
+  if ((lda % 8) || (ldw % 8)) return set_error(HIG_ERR_INVALID, "gemm_t: lda/ldw must be multiples of 8 (TMA 16B rule)");
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return set_error(HIG_ERR_INVALID, "gemm_t: operands must be 16-byte aligned");
+  if (split_k && (bias || residual || out_bf16 || !out_f32))
+    return set_error(HIG_ERR_INVALID, "gemm_t: split-K accumulates raw products into out_f32 only");
+  GemmEpilogue ep;
+  ep.bias = bias; ep.residual = residual; ep.ldr = ldr; ep.res_row_mod = 0;
+  ep.out_f32 = out_f32; ep.ldo_f32 = ldo_f32;
+  ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); ep.ldo_bf16 = ldo_bf16;
+  ep.act = 0; ep.atomic = split_k ? 1 : 0;
+  ep.residual16 = nullptr; ep.ldr16 = 0; ep.out16 = nullptr; ep.ldo16 = 0;
+  int vec_ok = 1;
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) vec_ok = 0;
+  if (residual && ((reinterpret_cast<uintptr_t>(residual) & 15) || (ldr % 4))) vec_ok = 0;
+  if (out_f32 && ((reinterpret_cast<uintptr_t>(out_f32) & 15) || (ldo_f32 % 4))) vec_ok = 0;
+  if (out_bf16 && ((reinterpret_cast<uintptr_t>(out_bf16) & 7) || (ldo_bf16 % 4))) vec_ok = 0;
+  CUtensorMap tmA, tmB;
+  int rc = trans_a ? get_tmap(A, K, M, lda, 64, &tmA) : get_tmap(A, M, K, lda, 128, &tmA);
+  if (rc) return rc;
+  rc = trans_b ? get_tmap(W, K, N, ldw, 64, &tmB) : get_tmap(W, N, K, ldw, 128, &tmB);
+  if (rc) return rc;
+  const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const int mn = ((M + 255) / 256) * ((N + 255) / 256);
+  int ks = 1;
+  if (split_k) {
+    const int workers = num_sms() / 2;
+    int want = split_k > 0 ? split_k : (workers + mn - 1) / mn;
+    if (want > k_blocks) want = k_blocks;
+    if (want < 1) want = 1;
+    const int per = (k_blocks + want - 1) / want;
+    ks = (k_blocks + per - 1) / per;
+  }
+  return launch_gemm_2cta_t(trans_a, trans_b, tmA, tmB, M, N, K, ep, vec_ok, num_sms(), ks, stream);
+}
+
 int gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32, int ldo_f32,
                      int k_splits, cudaStream_t stream) {
   return gemm_bf16_impl(A, lda, W, ldw, M, N, K, nullptr, nullptr, 0, 0, out_f32, ldo_f32, nullptr, 0, 0,

@@ -233,6 +233,19 @@ HIG_DEVICE uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile, 128B swizzle: [k rows][64 MN elements = 128 B] boxes as TMA writes them; 8-row k groups are
+// 1024 B apart (SBO), consecutive 64-element MN blocks `mn_block_bytes` apart (LBO).  Canonical layout (16-byte units):
+// ((8,n),(8,k)) : ((1,LBO),(8,SBO)).
+HIG_DEVICE uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((mn_block_bytes >> 4) & 0x3FFFu) << 16;   // LBO
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                         // SBO
+  d |= static_cast<uint64_t>(1) << 46;                                  // version = 1
+  d |= static_cast<uint64_t>(2) << 61;                                  // layout = SWIZZLE_128B
+  return d;
+}
+
 // Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, shape M x N.
 HIG_DEVICE constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4)            // D format = F32

@@ -84,16 +84,26 @@ int recover_joints(const float* x, int S, int T, int C, int init_row, const floa
 int q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac, const float* sqrt_1mac,
              int S, int TC, float* out, cudaStream_t stream);
 
+// transposed != 0: a_out[s, h] is written as A^T ([l][d]) — the K-major B operand of attn_apply_stylize_tc
 int attn_kv(const void* k, const void* v, int ldkv, void* a_out, const int* length, int S, int T, int H,
-            int pair_shift, cudaStream_t stream);
+            int pair_shift, int transposed, cudaStream_t stream);
 
 int attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
                        const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
                        cudaStream_t stream);
 
+// tcgen05 / TMEM variant (attn_apply_tc.cu): q holds softmax_feat(Q) already, a_t = A^T [S, 8, 64 (l), 64 (d)]
+int attn_apply_stylize_tc(const void* q, int ldq, const void* a_t, const float* gamma, const float* beta,
+                          const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
+                          cudaStream_t stream);
+
 // ---- training path (bwd_ops.cu, eff_attn_bwd.cu, gemm_tcgen05.cu) ----
 int gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32, int ldo_f32,
                      int k_splits, cudaStream_t stream);
+
+int gemm_bf16_t(int trans_a, int trans_b, const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                const float* bias, const float* residual, int ldr, float* out_f32, int ldo_f32, void* out_bf16,
+                int ldo_bf16, int split_k, cudaStream_t stream);
 
 int transpose(const void* in, int in_dtype, int M, int N, int ld_in, void* outT, int ld_t, void* copy, int ld_c,
               int out_dtype, float* colsum, int rows_zero_mod, cudaStream_t stream);

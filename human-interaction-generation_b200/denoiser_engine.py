@@ -70,6 +70,12 @@ class DenoiserEngine:
         time so that HIG_QSM / HIG_WRES can be A/B-toggled between captures."""
         return self.stream and os.environ.get("HIG_QSM", "1") != "0" and os.environ.get("HIG_WRES", "1") != "0"
 
+    @property
+    def apply_tc(self):
+        """Query half of the attention on tcgen05 / TMEM (attn_apply_tc.cu): needs the queries softmaxed by the projection
+        (qsm) and A^T from the K/V half.  HIG_APPLY_TC=0 keeps the mma.sync kernel (A/B runs)."""
+        return self.qsm and os.environ.get("HIG_APPLY_TC", "1") != "0"
+
     # ------------------------------------------------------------------------------------------ weights
     def _param_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.m.parameters())
@@ -222,7 +228,8 @@ class DenoiserEngine:
         # its version counter and the weights it was projected with
         W = self.packed()
         c = self._text_cache
-        if c is not None and c[0] is xf_out and c[1] == (xf_out._version, self.packed_generation):
+        transposed = self.apply_tc      # the tcgen05 apply kernel takes A^T (its K-major B operand)
+        if c is not None and c[0] is xf_out and c[1] == (xf_out._version, self.packed_generation, transposed):
             return c[2]
         S, N, Dt = xf_out.shape
         dt, dev = self.act_dtype, xf_out.device
@@ -234,8 +241,11 @@ class DenoiserEngine:
             p = f"l{i}.ca."
             ops.ln_film_silu(xf, W[p + "tln.w"], W[p + "tln.b"], tn)
             self._gemm(tn, W[p + "kv.w"], W[p + "kv.b"], out=kv)
-            ops.eff_attn(ops.ATTN_KV_ONLY, S, N, self.H, k=kv[:, :self.D], v=kv[:, self.D:], a_out=a_all[i])
-        self._text_cache = (xf_out, (xf_out._version, self.packed_generation), a_all)
+            if transposed:
+                ops.attn_kv(kv[:, :self.D], kv[:, self.D:], a_all[i], S, N, self.H, transposed=True)
+            else:
+                ops.eff_attn(ops.ATTN_KV_ONLY, S, N, self.H, k=kv[:, :self.D], v=kv[:, self.D:], a_out=a_all[i])
+        self._text_cache = (xf_out, (xf_out._version, self.packed_generation, transposed), a_all)
         return a_all
 
     # ------------------------------------------------------------------------------------------ helpers
@@ -314,12 +324,20 @@ class DenoiserEngine:
         the attention output never reaches HBM.  fp32 mode: the unfused validation kernels."""
         H = self.H
         if self.precision == "bf16":
+            tc = q_softmaxed and self.apply_tc
             if a_in is None:
                 a_in = ws["a_blk"]
-                ops.eff_attn(ops.ATTN_KV_ONLY, S, T, H, k=k, v=v, a_out=a_in, length=ws["len"], pair_shift=pair_shift,
-                             mask_v=mask_v)
-            ops.attn_apply_stylize(q, a_in, W[p + ".po.ln.w"], W[p + ".po.ln.b"], ws["sact"], S, T, H,
-                                   scale_shift=self._ss(ws, W, p), silu=True, q_softmaxed=q_softmaxed)
+                if tc:
+                    ops.attn_kv(k, v, a_in, S, T, H, length=ws["len"], pair_shift=pair_shift, transposed=True)
+                else:
+                    ops.eff_attn(ops.ATTN_KV_ONLY, S, T, H, k=k, v=v, a_out=a_in, length=ws["len"],
+                                 pair_shift=pair_shift, mask_v=mask_v)
+            if tc:
+                ops.attn_apply_stylize_tc(q, a_in, W[p + ".po.ln.w"], W[p + ".po.ln.b"], ws["sact"], S, T, H,
+                                          scale_shift=self._ss(ws, W, p), silu=True)
+            else:
+                ops.attn_apply_stylize(q, a_in, W[p + ".po.ln.w"], W[p + ".po.ln.b"], ws["sact"], S, T, H,
+                                       scale_shift=self._ss(ws, W, p), silu=True, q_softmaxed=q_softmaxed)
             return
         if a_in is not None:
             ops.eff_attn(ops.ATTN_Q_ONLY, S, T, H, q=q, a_in=a_in, y=ws["y"])

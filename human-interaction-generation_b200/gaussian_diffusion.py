@@ -296,7 +296,7 @@ class GaussianDiffusion:
             eng.packed()
             graph_key = (eng.packed_generation, coef.data_ptr(), self.num_timesteps,
                          tuple(_os.environ.get(k) for k in ("HIG_WRES", "HIG_L2_PERSIST", "HIG_PDL", "HIG_GS_PAIRS",
-                                                            "HIG_TIME_TABLE", "HIG_EMBED_STREAM", "HIG_QSM")))
+                                                            "HIG_TIME_TABLE", "HIG_EMBED_STREAM", "HIG_QSM", "HIG_APPLY_TC")))
             if st["graph_key"] != graph_key:
                 st["graph"], st["graph_key"] = None, graph_key
 

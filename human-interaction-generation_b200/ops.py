@@ -183,6 +183,39 @@ def attn_apply_stylize(q, a_in, gamma, beta, out, S, T, H, scale_shift=None, sil
     return out
 
 
+def attn_kv(k, v, a_out, S, T, H, length=None, pair_shift=0, transposed=False):
+    """a_out[s,h] = softmax_time(K_masked)^T V (bf16 [S,H,64,64]); transposed: A^T for attn_apply_stylize_tc."""
+    lib = _lib.load()
+    if k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16 or a_out.dtype != torch.bfloat16 or not a_out.is_contiguous():
+        raise TypeError("hig_b200.attn_kv: bf16 storage, contiguous a_out")
+    if v.stride(0) != k.stride(0):
+        raise ValueError("hig_b200.attn_kv: K and V must share a leading dimension")
+    if length is not None and length.dtype != torch.int32:
+        raise TypeError("hig_b200.attn_kv: length must be int32")
+    rc = lib.hig_attn_kv(_ptr(k), _ptr(v), k.stride(0), _ptr(a_out), _ptr(length), S, T, H, pair_shift,
+                         1 if transposed else 0, _stream())
+    _lib.check(rc, "hig_attn_kv")
+    return a_out
+
+
+def attn_apply_stylize_tc(q, a_t, gamma, beta, out, S, T, H, scale_shift=None, silu=True):
+    """tcgen05 / TMEM variant of attn_apply_stylize: q already softmaxed, a_t = A^T [S,H,64,64] (attn_kv transposed)."""
+    lib = _lib.load()
+    if q.dtype != torch.bfloat16 or a_t.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        raise TypeError("hig_b200.attn_apply_stylize_tc: bf16 storage only")
+    if not out.is_contiguous() or not a_t.is_contiguous():
+        raise ValueError("hig_b200.attn_apply_stylize_tc: contiguous out / a_t required")
+    ss_stride = 0
+    if scale_shift is not None:
+        if scale_shift.dtype != torch.float32 or scale_shift.stride(1) != 1:
+            raise ValueError("hig_b200.attn_apply_stylize_tc: scale_shift must be fp32 with unit inner stride")
+        ss_stride = scale_shift.stride(0)
+    rc = lib.hig_attn_apply_stylize_tc(_ptr(q), q.stride(0), _ptr(a_t), _ptr(gamma), _ptr(beta), _ptr(scale_shift),
+                                       ss_stride, 1 if silu else 0, _ptr(out), S, T, H, _stream())
+    _lib.check(rc, "hig_attn_apply_stylize_tc")
+    return out
+
+
 def timestep_embed(t, freqs, out):
     lib = _lib.load()
     if t.dtype != torch.int64:
@@ -305,6 +338,28 @@ def gemm_splitk(a, w, out_f32, k_splits=0):
                                   _rowmajor(out_f32, "out_f32"), int(k_splits), _stream())
     _lib.check(rc, "hig_gemm_bf16_splitk")
     return out_f32
+
+
+def gemm_t(a, w, trans_a=False, trans_b=False, bias=None, residual=None, out_f32=None, out_bf16=None, split_k=0):
+    """C[M,N] (+)= opA(a) @ opB(w).T on tcgen05 with MN-major operands read in place (no transposed copies).
+    trans_a: a is [K, M]; trans_b: w is [K, N].  split_k != 0: fp32 atomic accumulation into out_f32."""
+    lib = _lib.load()
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise TypeError("hig_b200.gemm_t: bf16 operands required")
+    K, M = (a.shape if trans_a else a.shape[::-1])
+    Kw, N = (w.shape if trans_b else w.shape[::-1])
+    if K != Kw:
+        raise ValueError(f"hig_b200.gemm_t: contraction mismatch {K} vs {Kw}")
+    for t, nm in ((bias, "bias"), (residual, "residual"), (out_f32, "out_f32")):
+        if t is not None and t.dtype != torch.float32:
+            raise TypeError(f"hig_b200.gemm_t: {nm} must be fp32")
+    rc = lib.hig_gemm_bf16_t(1 if trans_a else 0, 1 if trans_b else 0, _ptr(a), _rowmajor(a, "A"), _ptr(w),
+                             _rowmajor(w, "W"), M, N, K, _ptr(bias), _ptr(residual),
+                             _rowmajor(residual, "residual") if residual is not None else 0, _ptr(out_f32),
+                             _rowmajor(out_f32, "out_f32") if out_f32 is not None else 0, _ptr(out_bf16),
+                             _rowmajor(out_bf16, "out_bf16") if out_bf16 is not None else 0, int(split_k), _stream())
+    _lib.check(rc, "hig_gemm_bf16_t")
+    return out_f32 if out_bf16 is None else out_bf16
 
 
 def transpose(x, out_t=None, copy=None, colsum=None, rows_zero_mod=0):

@@ -178,6 +178,21 @@ int hig_recover_joints(const float* x, int S, int T, int C, int init_row, const 
 int hig_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
                  const float* sqrt_1mac, int S, int TC, float* out, void* stream);
 
+/* K/V half of the efficient attention, bf16: a_out[s,h] = softmax_time(K_masked)^T (V mask) (64 x 64 per head;
+ * models/interaction_transformer.py:121-127 / :194-200), K/V of sequence (s + pair_shift) % S, rows >= length[s] masked.
+ * transposed != 0 writes A^T ([l][d]), the K-major B operand hig_attn_apply_stylize_tc consumes. */
+int hig_attn_kv(const void* k, const void* v, int ldkv, void* a_out, const int* length, int S, int T, int H,
+                int pair_shift, int transposed, void* stream);
+
+/* hig_attn_apply_stylize on tcgen05 / TMEM (the product path's kernel): q holds softmax_feat(Q) already (written by a
+ * HIG_GS_LN_QSM projection), a_t = A^T [S, 8, 64, 64] from hig_attn_kv(transposed = 1); one 128-row tile of a sequence per
+ * CTA step, 8 heads x tcgen05.mma (M=128, N=64, K=64) into the SM's 512 TMEM columns, one row per TMEM lane so the
+ * LayerNorm of models/interaction_transformer.py:93 is lane-local; FiLM + SiLU (:94-97) in registers, TMA store.
+ * apply_silu: bit 0 only.  T <= 256. */
+int hig_attn_apply_stylize_tc(const void* q, int ldq, const void* a_t, const float* gamma, const float* beta,
+                              const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
+                              void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Training path.  The reference has no backward code: torch.autograd differentiates the forward above
  * (loss.backward() in DDPMMulTrainer.update, trainers/mul_ddpm_trainer.py:249-256).  These are the hand-written
@@ -188,6 +203,17 @@ int hig_q_sample(const float* x0, const float* noise, const long long* t, const 
  * initialises out_f32).  Weight gradients dW = dY^T . X: M, N are weight dims, K = tokens.  k_splits <= 0: auto. */
 int hig_gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32,
                          int ldo_f32, int k_splits, void* stream);
+
+/* C[M,N] (+)= opA(A) . opB(W)^T on the CTA-pair tcgen05 kernel with either operand consumed MN-major (as it lies in
+ * memory, no transposed copy): trans_a: A stored [K, M]; trans_b: W stored [K, N].  What torch.autograd computes for
+ * nn.Linear (every nn.Linear call site of models/interaction_transformer.py, see hig_gemm_bf16):
+ *   grad_weight = dY^T . X   -> trans_a = trans_b = 1, A = dY [tok, out], W = X [tok, in], K = tok, split_k = -1
+ *   grad_input  = dY . W     -> trans_b = 1, A = dY [tok, out], W = weight [out, in] as stored, K = out
+ * bias (fp32 [N]) / residual (fp32 [M, ldr], may alias out_f32 for accumulation) / out_bf16 as in hig_gemm_bf16;
+ * split_k != 0 accumulates with fp32 atomics into out_f32 (caller-initialised), raw products only. */
+int hig_gemm_bf16_t(int trans_a, int trans_b, const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                    const float* bias, const float* residual, int ldr, float* out_f32, int ldo_f32, void* out_bf16,
+                    int ldo_bf16, int split_k, void* stream);
 
 /* in [M,N] -> outT [N,M] (nullable), copy [M,N] in the output dtype (nullable), colsum[n] += sum_m in[m,n] (nullable,
  * fp32 atomics: bias gradients).  rows_zero_mod > 0 treats rows with m % rows_zero_mod == 0 as zero (frame 0 of a

@@ -236,6 +236,43 @@ def test_attn_apply_takes_presoftmaxed_queries(cuda):
     assert _rel(o2.float(), ref) < 1e-2 and _rel(o1.float(), o2.float()) < 1e-2
 
 
+@pytest.mark.parametrize("S,T", [(4, 196), (6, 128), (2, 50), (4, 129), (2, 1), (160, 196)])
+def test_attn_apply_tc_matches_reference_and_mma_kernel(cuda, S, T):
+    """tcgen05 / TMEM query half (hig_attn_apply_stylize_tc) with A^T from hig_attn_kv(transposed): against the fp32
+    formulation (:128 einsum, :86-97 LayerNorm + FiLM + SiLU) and against the mma.sync kernel on the same operands.
+    T = 196 / 129 exercise the partial second tile, T = 50 / 1 the partial first tile, S = 160 > one tile per SM."""
+    ops = _ops()
+    H, D = 8, 512
+    g = torch.Generator(device=cuda).manual_seed(S * 1000 + T)
+    qkv = (torch.randn(S * T, 3 * D, device=cuda, generator=g) * 1.5).bfloat16()
+    lens = torch.randint(1, T + 1, (S,), device=cuda, generator=g, dtype=torch.int32)
+    gamma = 1 + 0.1 * torch.randn(D, device=cuda, generator=g)
+    beta = 0.1 * torch.randn(D, device=cuda, generator=g)
+    ss = 0.5 * torch.randn(S, 2 * D + 64, device=cuda, generator=g)[:, :2 * D]
+    a = torch.empty(S, H, 64, 64, device=cuda, dtype=torch.bfloat16)
+    a_t = torch.empty_like(a)
+    ops.attn_kv(qkv[:, D:2 * D], qkv[:, 2 * D:], a, S, T, H, length=lens)
+    ops.attn_kv(qkv[:, D:2 * D], qkv[:, 2 * D:], a_t, S, T, H, length=lens, transposed=True)
+    assert torch.equal(a_t, a.transpose(-1, -2).contiguous())
+    qs = torch.softmax(qkv[:, :D].float().view(S * T, H, 64), dim=-1).view(S * T, D).bfloat16()
+    qsv = torch.zeros(S * T, 3 * D, device=cuda, dtype=torch.bfloat16)     # a [tok, 512] view with ld = 1536, as in the engine
+    qsv[:, :D] = qs
+    out = torch.full((S * T + 3, D), float("nan"), device=cuda, dtype=torch.bfloat16)
+    ops.attn_apply_stylize_tc(qsv[:, :D], a_t, gamma, beta, out[:S * T], S, T, H, scale_shift=ss, silu=True)
+    assert torch.isnan(out[S * T:].float()).all()                          # nothing written past the last row
+    out = out[:S * T]
+    assert torch.isfinite(out.float()).all()
+    y = torch.einsum("sthd,shdl->sthl", qs.float().view(S, T, H, 64), a.float()).reshape(S, T, D)
+    ref = F.silu(F.layer_norm(y, (D,), gamma, beta, 1e-5) * (1 + ss[:, None, :D]) + ss[:, None, D:]).reshape(S * T, D)
+    assert _rel(out.float(), ref) < 1e-2, _rel(out.float(), ref)
+    o2 = torch.empty_like(out)
+    ops.attn_apply_stylize(qsv[:, :D], a, gamma, beta, o2, S, T, H, scale_shift=ss, silu=True, q_softmaxed=True)
+    assert _rel(out.float(), o2.float()) < 6e-3
+    o3 = torch.empty_like(out)                                             # no FiLM, no SiLU: plain LayerNorm of the attention
+    ops.attn_apply_stylize_tc(qsv[:, :D], a_t, gamma, beta, o3, S, T, H, scale_shift=None, silu=False)
+    assert _rel(o3.float(), F.layer_norm(y, (D,), gamma, beta, 1e-5).reshape(S * T, D)) < 6e-3
+
+
 def test_gemm_stream_fp16_out_heads(cuda):
     """HIG_GS_F16 (output heads): fp16 operands, bias, fp16 out; dense rows and the out2 pattern (one row per sequence,
     row pitch T * 512 on both the operand and the output).  fp16 storage of an fp32-accumulated result: 1e-3."""

@@ -91,6 +91,47 @@ def test_gemm_splitk(cuda, M, N, K):
     assert rel(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 512, 23296), (1536, 512, 1000), (264, 512, 784), (512, 272, 23296),
+                                   (2048, 2048, 256), (1024, 512, 100)])
+def test_gemm_t_wgrad_form(cuda, M, N, K):
+    """dW[M,N] += dY[K,M]^T X[K,N]: both operands MN-major (token-major as the activations lie), split-K atomics."""
+    ops = _ops()
+    Mp, Np = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    dy = torch.randn(K, Mp, device=cuda).bfloat16()[:, :M]
+    x = torch.randn(K, Np, device=cuda).bfloat16()[:, :N]
+    base = torch.randn(M, N, device=cuda)
+    out = base.clone()
+    ops.gemm_t(dy, x, trans_a=True, trans_b=True, out_f32=out, split_k=-1)
+    ref = base.double() + dy.double().t() @ x.double()
+    assert rel(out, ref) < 1e-5
+    out2 = torch.empty(M, N, device=cuda)
+    ops.gemm_t(dy, x, trans_a=True, trans_b=True, out_f32=out2)       # single pass, no atomics: deterministic
+    assert rel(out2, dy.double().t() @ x.double()) < 1e-4           # one fp32 accumulator over all K tokens
+    out3 = torch.empty(M, N, device=cuda)
+    ops.gemm_t(dy, x, trans_a=True, trans_b=True, out_f32=out3)
+    assert torch.equal(out2, out3)
+
+
+@pytest.mark.parametrize("M,N,K", [(23296, 512, 512), (1000, 512, 1536), (784, 512, 264), (300, 1024, 512),
+                                   (23296, 256, 1024), (130, 2048, 2048)])
+def test_gemm_t_dgrad_form(cuda, M, N, K):
+    """dX[M,N] = dY[M,K] W[K,N]: W consumed as stored ([out, in] row-major = MN-major B operand), bf16 / fp32-accumulate
+    outputs."""
+    ops = _ops()
+    Kp = (K + 7) // 8 * 8
+    dy = torch.randn(M, Kp, device=cuda).bfloat16()[:, :K]
+    w = (torch.randn(K, N, device=cuda) / K ** 0.5).bfloat16()
+    ref = dy.double() @ w.double()
+    zb = torch.zeros(N, device=cuda)
+    o16 = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm_t(dy, w, trans_b=True, bias=zb, out_bf16=o16)
+    assert rel(o16, ref) < 4e-3
+    base = torch.randn(M, N, device=cuda)
+    acc = base.clone()
+    ops.gemm_t(dy, w, trans_b=True, bias=zb, residual=acc, out_f32=acc)
+    assert rel(acc, base.double() + ref) < 1e-5
+
+
 @pytest.mark.parametrize("width", [512, 256])
 @pytest.mark.parametrize("x_dt,g_dt,dx_dt", [(torch.float32, torch.float32, torch.float32),
                                              (torch.float32, torch.bfloat16, torch.float32),
