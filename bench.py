@@ -7,9 +7,16 @@ One bench "step" = one pass of the hot path over one batch: a complete 1000-step
   e2e    : the same through the reference-facing API  DDPMMulTrainer.generate(captions, lengths)  with host inputs
            (caption strings + host lengths) and the sampled motions copied back to host memory
   roofline / cpu_baseline / clocks / gpu_launches: see the module docstrings of the helpers below.
+  train  : BASELINE configs[3], the DDP training step (128 pairs per GPU, T = 91, labelled, synthetic motion + caption ids):
+           ms per iteration through DDPMMulTrainer.forward / update on the graph-replayed training engine, achieved
+           denoiser fwd+bwd TFLOP/s against the sustained bf16 peak; at N > 1 also the NCCL gradient-equality check, the same
+           loop with the all-reduce disabled (exposed communication) and the all-reduce alone (overlap fraction)
+  reference_gpu_eager : the reference's formulation (oracle port: eager PyTorch fp32, TF32 off) on the SAME B200 at the bench
+           shape — the "what a user gets by running the reference on this GPU" comparator (BASELINE.md)
 `--impl reference` times the reference's algorithm on the host CPU (the oracle port, all host threads).
-Multi-GPU: one process per GPU (torchrun), pairs sharded across ranks, no collective in the loop; the e2e arm
-gathers the samples to rank 0.  Scaling is weak (64 pairs per GPU).
+Multi-GPU: one process per GPU (torchrun), pairs sharded across ranks, no collective in the loop.  N = 1 runs configs[1]
+(64 pairs); N > 1 runs configs[2], a FIXED batch of 512 pairs split over the N GPUs (strong scaling; 64 pairs per GPU at
+N = 8).  The e2e arm lands every rank's samples in one shared pinned host buffer (ddp.HostGather): no gather collective.
 """
 import argparse
 import json
@@ -155,9 +162,24 @@ def time_qkv_kernel(device, peak_burst):
         ts.append(e0.elapsed_time(e1) * 1e-3 / 30)
     t = sorted(ts)[len(ts) // 2]
     ach = 2.0 * M * N * K / t / 1e12
+    tr = kernel_traffic()
     return {"name": "gemm_wres_kernel<LN_QSM> (QKV 25088x1536x512, LayerNorm folded, query softmax)", "us": t * 1e6, "achieved": ach,
             "peak": peak_burst, "unit": "TFLOP/s", "frac": ach / peak_burst,
-            "l2": "30 back-to-back launches over 6 rotating operand sets (617 MB > L2)", "traffic": 61.7e6}
+            "l2": "30 back-to-back launches over 6 rotating operand sets (617 MB > L2)",
+            "traffic": tr["bytes_per_launch"], "traffic_source": tr["source"]}
+
+
+def kernel_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of THIS kernel kind
+    (profiles/dominant_kernel_traffic.json, refreshed whenever the kernel changes; it names the .csv it was read from).
+    ncu cannot run inside the timed bench, so the number is a citation, not a live measurement — null if the file is gone."""
+    f = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    try:
+        d = json.load(open(f))
+        return {"bytes_per_launch": float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]),
+                "source": f"profiles/dominant_kernel_traffic.json <- {d.get('source')}"}
+    except Exception as ex:  # noqa
+        return {"bytes_per_launch": None, "source": f"unavailable: {ex}"}
 
 
 def cpu_reference_arm(state_dict, B, T, n_denoiser_steps, warm):

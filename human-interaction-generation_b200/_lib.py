@@ -63,6 +63,11 @@ SIGNATURES = {
                              c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
     "hig_eff_attn_bwd": [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                          c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "hig_masked_mse": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                       c_void_p],
+    "hig_sumsq": [c_void_p, ctypes.c_longlong, c_void_p, c_void_p],
+    "hig_adam_flat": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_float, ctypes.c_float,
+                      ctypes.c_float, ctypes.c_float, c_int, c_void_p, ctypes.c_float, c_void_p],
 }
 _RESTYPE = {"hig_last_error": ctypes.c_char_p, "hig_launch_count": c_ull}
 

@@ -97,13 +97,30 @@ def tokenize(texts, truncate=True):
     return out
 
 
-def load_clip():
-    """(model, tokenize_fn): the real CLIP when importable, else the stub."""
-    try:
-        import clip as _clip  # noqa
-        if hasattr(_clip, "load") and getattr(_clip, "__file__", None):
-            model, _ = _clip.load("ViT-B/32", "cpu")
+LOADED = None     # "openai-clip" or "stub": which encoder the last load_clip() call returned
+
+
+def load_clip(stub=None):
+    """(model, tokenize_fn).  The real OpenAI CLIP ViT-B/32 (`clip.load`, models/interaction_transformer.py:436) when the
+    `clip` package is installed; the random-init CLIP-shaped stub ONLY when asked for — `stub=True` or HIG_CLIP_STUB=1 — or
+    when the package itself is absent (no network on the benchmark boxes; a warning says so).  A `clip` package that is
+    present but fails to load its weights raises: a text-conditioned model must never silently run on a random encoder."""
+    global LOADED
+    import os
+    import warnings
+    if stub is None:
+        stub = os.environ.get("HIG_CLIP_STUB", "") not in ("", "0")
+    if not stub:
+        try:
+            import clip as _clip  # noqa
+        except ImportError:
+            _clip = None
+        if _clip is not None and hasattr(_clip, "load") and getattr(_clip, "__file__", None):
+            model, _ = _clip.load("ViT-B/32", "cpu")      # errors (missing weights, no network) propagate
+            LOADED = "openai-clip"
             return model, _clip.tokenize
-    except Exception:
-        pass
+        warnings.warn("hig_b200: the `clip` package is not installed — using the RANDOM-INIT CLIP-shaped text encoder "
+                      "(architecture-faithful, untrained).  Text conditioning is meaningless until real CLIP weights are "
+                      "loaded; set HIG_CLIP_STUB=1 to silence this warning.", RuntimeWarning, stacklevel=2)
+    LOADED = "stub"
     return ClipTextStub(), tokenize

@@ -31,14 +31,15 @@
 namespace hig {
 
 namespace atc {
-constexpr int THREADS = 320;
+constexpr int EPI_WARPS = 16;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;   // warp 0 producer, warp 1 MMA, warps 2..17 epilogue
 constexpr int STAGES = 5;
 constexpr int Q_BYTES = 128 * 64 * 2;          // one head block of the tile
 constexpr int A_BYTES = 8 * 64 * 64 * 2;       // A^T of the 8 heads
-constexpr int SLAB = 32 * 128;                 // 32 rows x 64 bf16 columns
-constexpr int EPI_BYTES = 8 * 2 * SLAB;        // two slabs per epilogue warp
+constexpr int SUB = 32 * 64;                   // staging sub-slab: 32 rows x 32 bf16 columns (64-byte rows, 64B swizzle)
+constexpr int EPI_BYTES = EPI_WARPS * 2 * SUB; // two sub-slabs per epilogue warp
 constexpr int GB_BYTES = 2 * 2 * 512 * 4;      // (G, B) x two tile parities
-constexpr int RED_BYTES = 8 * 32 * 8;
+constexpr int RED_BYTES = EPI_WARPS * 32 * 8;
 constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
 constexpr int SMEM = STAGES * Q_BYTES + A_BYTES + EPI_BYTES + GB_BYTES + RED_BYTES + BAR_BYTES + 1024;
 static_assert(SMEM <= 232448, "shared memory budget");
@@ -66,6 +67,41 @@ HIG_DEVICE float4 lds_f4(uint32_t addr) {
 HIG_DEVICE void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// sum and sum of squares of one 32-column accumulator chunk, packed pairs
+HIG_DEVICE void acc_stats(const uint32_t (&r)[32], uint64_t& s1, uint64_t& s2) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint64_t v = f2_pack_u(r[2 * i], r[2 * i + 1]);
+    s1 = f2_add(s1, v);
+    s2 = f2_fma(v, v, s2);
+  }
+}
+// one 32-column chunk of this lane's row: normalise, FiLM affine, SiLU, bf16 -> the 64-byte row of a sub-slab
+// (16-byte chunks XOR-swizzled with (row >> 1) & 3, as CU_TENSOR_MAP_SWIZZLE_64B expects)
+HIG_DEVICE void finish_chunk(const uint32_t (&r)[32], uint32_t gaddr, uint32_t baddr, uint64_t rstd2, uint64_t nmr2, bool silu,
+                             uint32_t sub_row, int sw2) {
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {         // 8 columns -> one 16-byte chunk
+    const float4 G0 = lds_f4(gaddr + g8 * 32), G1 = lds_f4(gaddr + g8 * 32 + 16);
+    const float4 B0 = lds_f4(baddr + g8 * 32), B1 = lds_f4(baddr + g8 * 32 + 16);
+    const uint64_t GG[4] = {f2_pack(G0.x, G0.y), f2_pack(G0.z, G0.w), f2_pack(G1.x, G1.y), f2_pack(G1.z, G1.w)};
+    const uint64_t BB[4] = {f2_pack(B0.x, B0.y), f2_pack(B0.z, B0.w), f2_pack(B1.x, B1.y), f2_pack(B1.z, B1.w)};
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint64_t v = f2_fma(f2_pack_u(r[8 * g8 + 2 * i], r[8 * g8 + 2 * i + 1]), rstd2, nmr2);
+      v = f2_fma(v, GG[i], BB[i]);
+      float a, b;
+      f2_unpack(v, a, b);
+      if (silu) {
+        v = f2_fma(v, f2_pack(tanh_approx_f(a), tanh_approx_f(b)), v);
+        f2_unpack(v, a, b);
+      }
+      pk[i] = pack_bf16x2(a, b);
+    }
+    sts_u4(sub_row + ((g8 ^ sw2) << 4), pk[0], pk[1], pk[2], pk[3]);
+  }
+}
 }  // namespace atc
 using namespace atc;
 
@@ -80,7 +116,7 @@ attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* sAT = sQ + STAGES * Q_BYTES;
   uint8_t* sEpi = sAT + A_BYTES;
   float* sGB = reinterpret_cast<float*>(sEpi + EPI_BYTES);            // [parity][G | B][512]
-  float2* sRed = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(sGB) + GB_BYTES);   // [8 warps][32 lanes]
+  float2* sRed = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(sGB) + GB_BYTES);   // [16 warps][32 lanes]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sRed) + RED_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* afull_bar = empty_bar + STAGES;
@@ -101,7 +137,7 @@ attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(afull_bar, 1);
     mbar_init(afree_bar, 1);
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 8);
+    mbar_init(tempty_bar, EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -159,14 +195,16 @@ attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     __syncwarp();
   } else {
-    // ================= epilogue warps 2..9 =================
+    // ================= epilogue warps 2..17 =================
+    // TMEM lane quarter = warp % 4 (hardware rule); the four warps of a quarter take 128 columns (two heads) each.
+    // tcgen05.ld of the next 32-column chunk is always in flight while the current one is processed.
     const int ew = warp - 2;
-    const int q = warp & 3;            // TMEM lane quarter (hardware rule: warp id % 4)
-    const int ch = ew >> 2;            // column half
-    const int et = threadIdx.x - 64;   // 0..255
-    const uint32_t slab0 = smem_u32(sEpi) + ew * 2 * SLAB;
-    const uint32_t row_s[2] = {slab0 + lane * 128, slab0 + SLAB + lane * 128};
-    const int sw = lane & 7;
+    const int q = warp & 3;
+    const int cq = ew >> 2;            // column quarter
+    const int et = threadIdx.x - 64;   // 0..511
+    const uint32_t sub0 = smem_u32(sEpi) + ew * 2 * SUB;
+    const uint32_t row_s[2] = {sub0 + lane * 64, sub0 + SUB + lane * 64};
+    const int sw2 = (lane >> 1) & 3;
     const bool silu = (apply_silu & 1) != 0;
     const float hs = silu ? 0.5f : 1.0f;     // SiLU(x) = h + h tanh(h), h = x / 2: the affine carries the 1/2
     uint32_t lt = 0;
@@ -176,9 +214,8 @@ attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // folded FiLM affine of this sequence: out = n_hat * G + B,  G = gamma (1 + scale),  B = beta (1 + scale) + shift
       float* sG = sGB + par * 1024;
       float* sB = sG + 512;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int c = et + 256 * j;
+      {
+        const int c = et;
         float gg = __ldg(gamma + c), bb = __ldg(beta + c);
         if (scale_shift != nullptr) {
           const float m1 = 1.0f + __ldg(scale_shift + (size_t)s * ss_stride + c);
@@ -188,27 +225,29 @@ attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         sG[c] = gg * hs;
         sB[c] = bb * hs;
       }
-      named_bar(5, 256);
+      named_bar(5, 32 * EPI_WARPS);
       const int qrow0 = r0 + q * 32;
       const bool live = qrow0 < T;       // warp-uniform: this quarter holds at least one valid row
       mbar_wait(tfull_bar, par);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ch * 256;
-      // ---- pass 1: row statistics over this warp's 256 columns
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cq * 128;
+      uint32_t ra[32], rb[32];
+      // ---- pass 1: row statistics over this warp's 128 columns
       uint64_t s1 = 0ull, s2 = 0ull;
       if (live) {
-#pragma unroll 2
-        for (int c = 0; c < 8; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const uint64_t v = f2_pack_u(r[2 * i], r[2 * i + 1]);
-            s1 = f2_add(s1, v);
-            s2 = f2_fma(v, v, s2);
-          }
-        }
+        tmem_ld_32x32(taddr, ra);
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + 32, rb);
+        acc_stats(ra, s1, s2);
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + 64, ra);
+        acc_stats(rb, s1, s2);
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + 96, rb);
+        acc_stats(ra, s1, s2);
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr, ra);          // first chunk of pass 2: in flight across the statistics exchange
+        acc_stats(rb, s1, s2);
       }
       {
         float a0, a1, b0, b1;
@@ -216,64 +255,56 @@ attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         f2_unpack(s2, b0, b1);
         sRed[ew * 32 + lane] = make_float2(a0 + a1, b0 + b1);
       }
-      named_bar(1 + q, 64);              // the two column halves of this lane quarter
+      named_bar(1 + q, 128);             // the four column quarters of this lane quarter
       float rstd, nmr;
       {
-        const float2 mine = sRed[ew * 32 + lane], other = sRed[(ew ^ 4) * 32 + lane];
-        const float mean = (mine.x + other.x) * (1.0f / 512.0f);
-        const float var = fmaxf(fmaf(mine.y + other.y, 1.0f / 512.0f, -mean * mean), 0.f);
+        float sum = 0.f, ssq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 p = sRed[(j * 4 + (ew & 3)) * 32 + lane];
+          sum += p.x;
+          ssq += p.y;
+        }
+        const float mean = sum * (1.0f / 512.0f);
+        const float var = fmaxf(fmaf(ssq, 1.0f / 512.0f, -mean * mean), 0.f);
         rstd = rsqrtf(var + 1e-5f);
         nmr = -mean * rstd;
       }
       const uint64_t rstd2 = f2_pack(rstd, rstd), nmr2 = f2_pack(nmr, nmr);
-      // ---- pass 2: normalise + FiLM + SiLU -> bf16 -> slab -> TMA store (64 columns per slab, 4 slabs per warp)
+      // ---- pass 2: normalise + FiLM + SiLU -> bf16 -> sub-slab -> TMA store (32 columns per store)
       if (live) {
-        const uint32_t gB = smem_u32(sG) + ch * 1024, bB = smem_u32(sB) + ch * 1024;
-#pragma unroll 1
-        for (int sl = 0; sl < 4; ++sl) {
-          if (lane == 0) bulk_wait_read_g<1>();     // the store issued from this slab two slabs ago has been read out
-          __syncwarp();
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            uint32_t r[32];
-            const int c32 = sl * 2 + hf;             // 32-column chunk of this warp's half
-            tmem_ld_32x32(taddr + c32 * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {         // 8 columns -> one 16-byte chunk
-              const uint32_t off = (uint32_t)(c32 * 32 + g8 * 8) * 4;
-              const float4 G0 = lds_f4(gB + off), G1 = lds_f4(gB + off + 16);
-              const float4 B0 = lds_f4(bB + off), B1 = lds_f4(bB + off + 16);
-              const uint64_t GG[4] = {f2_pack(G0.x, G0.y), f2_pack(G0.z, G0.w), f2_pack(G1.x, G1.y), f2_pack(G1.z, G1.w)};
-              const uint64_t BB[4] = {f2_pack(B0.x, B0.y), f2_pack(B0.z, B0.w), f2_pack(B1.x, B1.y), f2_pack(B1.z, B1.w)};
-              uint32_t pk[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint64_t v = f2_fma(f2_pack_u(r[8 * g8 + 2 * i], r[8 * g8 + 2 * i + 1]), rstd2, nmr2);
-                v = f2_fma(v, GG[i], BB[i]);
-                float a, b;
-                f2_unpack(v, a, b);
-                if (silu) {
-                  v = f2_fma(v, f2_pack(tanh_approx_f(a), tanh_approx_f(b)), v);
-                  f2_unpack(v, a, b);
-                }
-                pk[i] = pack_bf16x2(a, b);
-              }
-              sts_u4(row_s[sl & 1] + (((hf * 4 + g8) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
-            }
-          }
-          if (sl == 3) {                 // every tcgen05.ld of this tile has completed: hand TMEM back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar);
-          }
+        const uint32_t gB = smem_u32(sG) + cq * 512, bB = smem_u32(sB) + cq * 512;
+        auto store = [&](int c32) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tmO, slab0 + (sl & 1) * SLAB, ch * 256 + sl * 64, qrow0, s);
+            tma_store_3d(&tmO, sub0 + (c32 & 1) * SUB, cq * 128 + c32 * 32, qrow0, s);
             bulk_commit_g();
+            bulk_wait_read_g<1>();       // the other sub-slab's previous store has been read out: it is the next target
           }
-        }
+          __syncwarp();
+        };
+        if (lane == 0) bulk_wait_read_g<0>();
+        __syncwarp();
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + 32, rb);
+        finish_chunk(ra, gB, bB, rstd2, nmr2, silu, row_s[0], sw2);
+        store(0);
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + 64, ra);
+        finish_chunk(rb, gB + 128, bB + 128, rstd2, nmr2, silu, row_s[1], sw2);
+        store(1);
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + 96, rb);
+        finish_chunk(ra, gB + 256, bB + 256, rstd2, nmr2, silu, row_s[0], sw2);
+        store(2);
+        tmem_ld_wait();
+        // every tcgen05.ld of this tile has completed: hand TMEM back to the MMA warp before the last chunk's math
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar);
+        finish_chunk(rb, gB + 384, bB + 384, rstd2, nmr2, silu, row_s[1], sw2);
+        store(3);
       } else {
         tc_fence_before();
         __syncwarp();
@@ -297,7 +328,8 @@ typedef CUresult (*PFN_encodeTiled3)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // bf16 [S][T][cols] with row pitch ld (elements) and sequence pitch T * ld; box = [1][box_rows][64 cols], 128B swizzle
-static int get_tmap_3d(const void* ptr, int S, int T, int cols, int ld, int box_rows, CUtensorMap* out) {
+// (narrow: box = [1][box_rows][32 cols], 64B swizzle — the epilogue's staging sub-slabs)
+static int get_tmap_3d(const void* ptr, int S, int T, int cols, int ld, int box_rows, int narrow, CUtensorMap* out) {
   struct Key {
     const void* p; int S, T, cols, ld, br;
     bool operator==(const Key& o) const { return p == o.p && S == o.S && T == o.T && cols == o.cols && ld == o.ld && br == o.br; }
@@ -322,7 +354,7 @@ static int get_tmap_3d(const void* ptr, int S, int T, int cols, int ld, int box_
       return reinterpret_cast<PFN_encodeTiled3>(p);
     return (PFN_encodeTiled3) nullptr;
   }();
-  Key key{ptr, S, T, cols, ld, box_rows};
+  Key key{ptr, S, T, cols, ld, box_rows * 2 + narrow};
   {
     std::lock_guard<std::mutex> g(mu);
     auto itr = cache.find(key);
@@ -331,11 +363,12 @@ static int get_tmap_3d(const void* ptr, int S, int T, int cols, int ld, int box_
   if (!enc) return set_error(HIG_ERR_NO_DRIVER, "cuTensorMapEncodeTiled not available");
   cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)S};
   cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {narrow ? 32u : 64u, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap tm;
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, narrow ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(HIG_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed: " + std::to_string((int)r));
   {
@@ -362,11 +395,11 @@ int attn_apply_stylize_tc(const void* q, int ldq, const void* a_t, const float* 
   if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(a_t) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
     return set_error(HIG_ERR_INVALID, "attn_apply_stylize_tc: pointers must be 16-byte aligned");
   CUtensorMap tmQ, tmA, tmO;
-  int rc = get_tmap_3d(q, S, T, 512, ldq, 128, &tmQ);
+  int rc = get_tmap_3d(q, S, T, 512, ldq, 128, 0, &tmQ);
   if (rc) return rc;
   rc = get_tmap_2b(a_t, S * 8 * 64, 64, 64, 64, 0, &tmA);
   if (rc) return rc;
-  rc = get_tmap_3d(out, S, T, 512, 512, 32, &tmO);
+  rc = get_tmap_3d(out, S, T, 512, 512, 32, 1, &tmO);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {

@@ -220,4 +220,19 @@ int hig_eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void
                            pair_shift, dtype, static_cast<cudaStream_t>(stream));
 }
 
+int hig_masked_mse(const float* pred, const float* tgt, const int* length, int S, int T, int C, int pit, float* rows,
+                   float* w, float* loss, float* d_pred, void* stream) {
+  return hig::masked_mse(pred, tgt, length, S, T, C, pit, rows, w, loss, d_pred, static_cast<cudaStream_t>(stream));
+}
+
+int hig_sumsq(const float* x, long long n, double* out, void* stream) {
+  return hig::sumsq(x, n, out, static_cast<cudaStream_t>(stream));
+}
+
+int hig_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                  float beta2, float eps, int step, const double* gnorm2, float max_norm, void* stream) {
+  return hig::adam_flat(p, g, m, v, p_bf16, n, lr, beta1, beta2, eps, step, gnorm2, max_norm,
+                        static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

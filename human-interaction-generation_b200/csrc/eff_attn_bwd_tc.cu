@@ -346,8 +346,10 @@ eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, c
           mma16816(acc[2 * np + 1], a, b[2], b[3]);
         }
       }
+      // The bf16-rounded Qs of a row sum to 1 only to ~4e-3; dividing the row dot product by that sum keeps
+      // sum_d dQ[t, d] == 0 (and dQ == 0 when A has identical rows) exactly as with unrounded softmax weights.
       float2 qs0[8], qs1[8];
-      float d0 = 0.f, d1 = 0.f;
+      float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int col = nt * 8 + 2 * tg;
@@ -355,9 +357,15 @@ eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, c
         qs1[nt] = unpack_bf16x2(lds32(sQ + swz_el(t0 + g + 8, col)));
         d0 = fmaf(acc[nt][0], qs0[nt].x, fmaf(acc[nt][1], qs0[nt].y, d0));
         d1 = fmaf(acc[nt][2], qs1[nt].x, fmaf(acc[nt][3], qs1[nt].y, d1));
+        n0 += qs0[nt].x + qs0[nt].y;
+        n1 += qs1[nt].x + qs1[nt].y;
       }
       d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
       d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+      n0 += __shfl_xor_sync(0xffffffffu, n0, 1); n0 += __shfl_xor_sync(0xffffffffu, n0, 2);
+      n1 += __shfl_xor_sync(0xffffffffu, n1, 1); n1 += __shfl_xor_sync(0xffffffffu, n1, 2);
+      d0 = n0 > 0.f ? d0 / n0 : 0.f;     // padding rows (t >= T) carry Qs == 0
+      d1 = n1 > 0.f ? d1 / n1 : 0.f;
       __syncwarp();   // every lane has read its Qs values before the tile's rows are overwritten with dQ
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {

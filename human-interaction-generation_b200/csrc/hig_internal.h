@@ -123,4 +123,11 @@ int eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void* v,
                  const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
                  const int* length, int S, int T, int H, int pair_shift, int dtype, cudaStream_t stream);
 
+// ---- training step around the denoiser (train_ops.cu) ----
+int masked_mse(const float* pred, const float* tgt, const int* length, int S, int T, int C, int pit, float* rows, float* w,
+               float* loss, float* d_pred, cudaStream_t stream);
+int sumsq(const float* x, long long n, double* out, cudaStream_t stream);
+int adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1, float beta2,
+              float eps, int step, const double* gnorm2, float max_norm, cudaStream_t stream);
+
 }  // namespace hig

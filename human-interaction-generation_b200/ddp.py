@@ -151,10 +151,78 @@ def gather_pairs(local, n_pairs, dim_pose, group=None, dst=0):
     return out
 
 
-def generate_sharded(trainer, caption1, caption2, m_lens, dim_pose, batch_size=512, group=None, dst=0):
-    """`DDPMMulTrainer.generate` over all ranks of `group`: every rank samples its contiguous slice of the pairs."""
+class HostGather:
+    """Results of a sharded sampling run straight into ONE host buffer shared by the ranks of a node: a /dev/shm file mapped
+    by every rank and registered with CUDA (cudaHostRegister), so each rank's device -> host copy is an asynchronous DMA
+    into its own slice — no NCCL gather to rank 0, no pageable staging, no single-rank D2H funnel (round 1: dist.gather of
+    211 MB + one pageable .cpu() cost 3.3 % of the 8-GPU end-to-end rate).  `dst` reads the whole buffer after a barrier."""
+
+    def __init__(self, n_pairs, T, dim_pose, group=None, tag="gather"):
+        import mmap
+        import os
+        self.group = group
+        self.world, self.rank = (dist.get_world_size(group), dist.get_rank(group)) if dist.is_initialized() else (1, 0)
+        self.shape = (n_pairs, 2, T, dim_pose)
+        nbytes = max(4 * n_pairs * 2 * T * dim_pose, 4096)
+        port = os.environ.get("MASTER_PORT", "0")
+        self.path = f"/dev/shm/hig_b200_{tag}_{port}_{n_pairs}x{T}x{dim_pose}.bin"
+        if self.rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        if self.world > 1:
+            dist.barrier(group=group)
+        self._f = open(self.path, "r+b")
+        self._mm = mmap.mmap(self._f.fileno(), nbytes)
+        self.host = torch.frombuffer(self._mm, dtype=torch.float32, count=n_pairs * 2 * T * dim_pose).view(self.shape)
+        self._registered = False
+        if torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.host.data_ptr(), nbytes, 0)
+            self._registered = int(rc) == 0
+        self._nbytes = nbytes
+
+    def put(self, lo, pairs_dev):
+        """pairs_dev [n, 2, T, C] (device) -> host rows [lo, lo + n); asynchronous on the current stream."""
+        self.host[lo:lo + pairs_dev.shape[0]].copy_(pairs_dev, non_blocking=self._registered)
+
+    def finish(self, dst=0):
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        return self.host if self.rank == dst else None
+
+    def close(self):
+        import os
+        try:
+            if self._registered:
+                torch.cuda.cudart().cudaHostUnregister(self.host.data_ptr())
+            self.host = None
+            self._mm.close()
+            self._f.close()
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            if self.rank == 0 and os.path.exists(self.path):
+                os.unlink(self.path)
+        except Exception:
+            pass
+
+
+def generate_sharded(trainer, caption1, caption2, m_lens, dim_pose, batch_size=512, group=None, dst=0, host_gather=None):
+    """`DDPMMulTrainer.generate` over all ranks of `group`: every rank samples its contiguous slice of the pairs.
+    host_gather (a HostGather sized for all pairs at a common T): the samples go device -> shared pinned host memory per
+    rank, and `dst` gets ONE host tensor [n_pairs, 2, T, C]; otherwise the padded NCCL gather to `dst` (device lists)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_pairs(len(caption1), world, rank)
+    if host_gather is not None:
+        T = host_gather.shape[2]
+        for b0 in range(lo, hi, batch_size):
+            b1 = min(b0 + batch_size, hi)
+            out = trainer.generate_batch(caption1[b0:b1], caption2[b0:b1], torch.as_tensor(m_lens[b0:b1]), dim_pose)
+            n = b1 - b0
+            if out.shape[1] != T:
+                raise ValueError(f"HostGather was sized for T={T}, this batch sampled T={out.shape[1]}")
+            host_gather.put(b0, torch.stack([out[:n], out[n:]], dim=1))
+        return host_gather.finish(dst)
     local = trainer.generate(caption1[lo:hi], caption2[lo:hi], m_lens[lo:hi], dim_pose, batch_size=batch_size) \
         if hi > lo else []
     return gather_pairs(local, len(caption1), dim_pose, group=group, dst=dst)

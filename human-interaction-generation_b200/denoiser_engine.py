@@ -78,7 +78,8 @@ class DenoiserEngine:
 
     # ------------------------------------------------------------------------------------------ weights
     def _param_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.m.parameters())
+        # _hig_param_generation: bumped by the fused Adam kernel, which updates the parameters through raw pointers
+        return (getattr(self.m, "_hig_param_generation", 0),) + tuple((p.data_ptr(), p._version) for p in self.m.parameters())
 
     def packed(self):
         key = self._param_key()
@@ -277,8 +278,10 @@ class DenoiserEngine:
         value does not depend on how many rows the GEMM has).  Rebuilt when the weights change."""
         W = self.packed()
         key = (self.packed_generation, n_steps)
-        if self._time_table is not None and self._time_table[0] == key:
-            return self._time_table[1]
+        if not isinstance(self._time_table, dict) or self._time_table.get("gen") != self.packed_generation:
+            self._time_table = {"gen": self.packed_generation}      # one table per schedule length, all for these weights
+        if n_steps in self._time_table:
+            return self._time_table[n_steps]
         dev, dt = W["te0.w"].device, self.act_dtype
         t_all = torch.arange(n_steps, device=dev, dtype=torch.int64)
         temb = torch.empty(n_steps, self.D, device=dev, dtype=dt)
@@ -289,7 +292,7 @@ class DenoiserEngine:
             hi = min(lo + 256, n_steps)
             self._gemm(temb[lo:hi], W["te0.w"], W["te0.b"], out=te_h[lo:hi], act=ops.ACT_SILU)
             self._gemm(te_h[lo:hi], W["te2.w"], W["te2.b"], out_f32=table[lo:hi])
-        self._time_table = (key, table)
+        self._time_table[n_steps] = table
         return table
 
     def embed(self, ws, t_dev, xf_proj, S, time_table=None):

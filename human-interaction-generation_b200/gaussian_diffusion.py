@@ -114,7 +114,7 @@ class GaussianDiffusion:
         self.posterior_mean_coef2 = (1.0 - acp) * np.sqrt(alphas) / (1.0 - ac)
         self._dev_tables = {}
         self._fast_state = {}
-        self.seed = 0x5EED
+        self.seed = None          # Philox key of the in-kernel noise: drawn from torch's RNG on first use (see _next_seed)
 
     # ------------------------------------------------------------------------------------------ device tables
     def _tables(self, device):
@@ -134,6 +134,25 @@ class GaussianDiffusion:
 
     def _scale_timesteps(self, t):
         return t
+
+    def _next_seed(self):
+        """64-bit Philox key for one branch of one p_sample_loop call.  The first key comes from torch's default generator
+        (so torch.manual_seed controls sampling noise, as it controls the reference's th.randn_like, :657) mixed with the
+        process rank (ranks that share a seed and a shard shape must not draw the same noise at the same element);
+        later keys follow a 64-bit LCG."""
+        if self.seed is None:
+            s = int(th.randint(0, 2 ** 62, (1,)).item())
+            rank = 0
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    rank = dist.get_rank()
+            except Exception:
+                rank = 0
+            self.seed = (s ^ ((rank + 1) * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
+        seed = self.seed
+        self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        return seed
 
     # ------------------------------------------------------------------------------------------ forward process
     def q_sample(self, x_start, t, noise=None):
@@ -266,8 +285,7 @@ class GaussianDiffusion:
                 br["x"].copy_(sel(x_T))
                 br["t"].fill_(self.num_timesteps - 1)
                 ops.pack_motion(br["x"], ws["xa"])
-                seed = self.seed
-                self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+                seed = self._next_seed()
                 br["seed"].fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
 
             ttab = eng.time_table(self.num_timesteps) if _os.environ.get("HIG_TIME_TABLE", "1") != "0" else None
@@ -294,7 +312,9 @@ class GaussianDiffusion:
             # a cached graph is valid while the packed weights, the schedule tables and the kernel-selection knobs it
             # was recorded with are the ones in force
             eng.packed()
-            graph_key = (eng.packed_generation, coef.data_ptr(), self.num_timesteps,
+            # (the time table's address is baked into the graph: another schedule length rebuilds the table elsewhere)
+            st["ttab"] = ttab
+            graph_key = (eng.packed_generation, coef.data_ptr(), self.num_timesteps, None if ttab is None else ttab.data_ptr(),
                          tuple(_os.environ.get(k) for k in ("HIG_WRES", "HIG_L2_PERSIST", "HIG_PDL", "HIG_GS_PAIRS",
                                                             "HIG_TIME_TABLE", "HIG_EMBED_STREAM", "HIG_QSM", "HIG_APPLY_TC")))
             if st["graph_key"] != graph_key:

@@ -87,8 +87,11 @@ class MotionInteractionTransformer(nn.Module):
             self.cap_embedding = nn.Parameter(torch.randn(43, text_latent_dim))
             self.text_proj = nn.Sequential(nn.Linear(text_latent_dim, self.time_embed_dim))
         else:
-            from .clip_text import load_clip
-            self.clip, self._tokenize = load_clip()
+            from . import clip_text
+            self.clip, self._tokenize = clip_text.load_clip()
+            self.text_encoder_kind = clip_text.LOADED        # "openai-clip" or "stub" (random-init, see clip_text.load_clip)
+            # CLIP's `dtype` property reads visual.conv1.weight, which no_clip deletes below: keep it (the reference's d_type)
+            self._clip_dtype = self.clip.dtype
             self.no_clip = no_clip
             if no_clip:
                 self.clip.initialize_parameters()
@@ -159,10 +162,11 @@ class MotionInteractionTransformer(nn.Module):
 
         def run(caps):
             tokens = self._tokenize(caps, truncate=True).to(device)
-            x = clip.token_embedding(tokens).type(clip.dtype)
-            x = x + clip.positional_embedding.type(clip.dtype)
+            dt = self._clip_dtype
+            x = clip.token_embedding(tokens).type(dt)
+            x = x + clip.positional_embedding.type(dt)
             x = clip.transformer(x.permute(1, 0, 2))
-            return clip.ln_final(x).type(clip.dtype)
+            return clip.ln_final(x).type(dt)
 
         if self.no_clip:                  # trainable CLIP-shaped encoder: nothing can be cached
             with torch.enable_grad():
@@ -188,6 +192,32 @@ class MotionInteractionTransformer(nn.Module):
         e = self.cap_embedding[ids]
         return self.text_proj(e), e.unsqueeze(1)
 
+    def load_my_state_dict(self, state_dict, opt):
+        """:511-531 — partial checkpoint load used by tools/train.py:50 (--pretrained) and tools/label_data.py:85: copies the
+        entries that exist here, restricted to the language side (opt.only_language) or the motion side (opt.only_motion);
+        names it skips are printed, as in the reference (cap_id models stay silent about CLIP / text-encoder keys)."""
+        own_state = self.state_dict()
+        only_language, only_motion = getattr(opt, "only_language", False), getattr(opt, "only_motion", False)
+        with torch.no_grad():
+            for name, param in state_dict.items():
+                lang = "clip" in name or "text" in name
+                if only_language:
+                    if name not in own_state or not lang:
+                        print(name)
+                        continue
+                elif only_motion:
+                    if name not in own_state or lang:
+                        print(name)
+                        continue
+                elif name not in own_state:
+                    if not (getattr(opt, "cap_id", False) and lang):
+                        print(name)
+                    continue
+                if isinstance(param, torch.nn.parameter.Parameter):
+                    param = param.data
+                own_state[name].copy_(param)
+        self._hig_param_generation = getattr(self, "_hig_param_generation", 0) + 1   # packed operands are stale
+
     def generate_src_mask(self, T, length):
         """:568-575 — CPU FloatTensor [len(length), T]; vectorised (the reference loops in Python, 0.53 s at S=1024)."""
         ln = torch.as_tensor(length).reshape(-1).cpu()
@@ -207,7 +237,12 @@ class MotionInteractionTransformer(nn.Module):
         needs_grad = torch.is_grad_enabled() and (
             x.requires_grad or xf_proj.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
-            from .autograd import denoiser_forward_with_grad
+            import os
+            if self.precision == "bf16" and os.environ.get("HIG_TRAIN_ENGINE", "1") != "0":
+                # product training path: captured graphs over static buffers (train_engine.py)
+                from .train_engine import denoiser_forward_graph
+                return denoiser_forward_graph(self, x, timesteps, length, xf_proj, xf_out)
+            from .autograd import denoiser_forward_with_grad     # fp32 validation mode: eager kernel schedule
             return denoiser_forward_with_grad(self, x, timesteps, length, xf_proj, xf_out)
         out = self.engine().forward(x, timesteps, length, xf_proj, xf_out)
         return out.to(x.dtype)

@@ -2,12 +2,17 @@
 
 Kept: the constructor contract `DDPMMulTrainer(args, encoder)` (args.device / multi / label_path / cap_id /
 diffusion_steps / is_train), `generate`, `generate_batch`, `forward`, `backward_G`, `update`, `save`, `load`,
-`train_mode`, `eval_mode`, `to`.  Sampling goes through GaussianDiffusion.p_sample_loop's CUDA-graph path; the
-masked loss follows backward_G (:223-247).  Not re-implemented (out of scope): the
-dataloader-driven `train()` epoch loop with its matplotlib loss plots, and label_batch/eval_data.
+`train_mode`, `eval_mode`, `to`, `train`.  Sampling goes through GaussianDiffusion.p_sample_loop's CUDA-graph path; the
+masked loss follows backward_G (:223-247) — as one fused kernel (hig_masked_mse) when the optimizer is the flat fused Adam
+that `train()` builds, as the reference's eager formulation otherwise.  `train()` (:289-341) keeps the reference's control
+flow (Adam at opt.lr, --is_continue, log_every, save_latest, save_every_e) and writes its loss curve as JSON lines instead
+of a matplotlib figure.  Not re-implemented (out of scope): label_batch / eval_data.
 Deliberate fix, documented: `generate` takes caption2 from caption2 for non-final chunks (the reference reads
 caption1 there, :212 — flagged as a bug in SURVEY.md §3.1); pass `reference_chunk_bug=True` to reproduce it.
 """
+import json
+import os
+import time
 from collections import OrderedDict
 
 import torch
@@ -123,10 +128,12 @@ class DDPMMulTrainer(object):
         if not self.multi:
             raise NotImplementedError("single-person batches belong to the reference's DDPMTrainer (out of scope)")
         caption1, caption2, motion1, motion2, m_lens, _ = batch_data
-        motion = torch.cat([motion1.detach().to(self.device).float(), motion2.detach().to(self.device).float()], dim=0)
+        dev = self.device
+        motion = torch.cat([motion1.detach().to(dev, non_blocking=True).float(),
+                            motion2.detach().to(dev, non_blocking=True).float()], dim=0)
         caption = list(caption1) + list(caption2)
         B, T = motion1.shape[0], motion.shape[1]
-        cur_len = torch.as_tensor([min(T, int(m)) for m in m_lens], dtype=torch.long, device=self.device)
+        cur_len = torch.as_tensor(m_lens).reshape(-1).to(torch.long).clamp(max=T).to(dev, non_blocking=True)
         t, _ = self.sampler.sample(B, motion.device)
         t = torch.cat([t, t], dim=0)
         if not self.with_label:
@@ -138,15 +145,19 @@ class DDPMMulTrainer(object):
             cur_len = torch.cat([cur_len, cur_len], dim=0)
             forward_twice = False
         if self.cap_id:
+            # the dataset yields caption ids as one-element lists (datasets/mul_dataset.py:214-216), which the default
+            # collate turns into [LongTensor[B]]; plain int lists work too.  The reference concatenates them (:561-566).
+            ids = lambda seq: torch.cat([torch.as_tensor(c).reshape(-1) for c in seq])
             half = len(caption) // 2
-            text = [torch.as_tensor(caption[:half]).reshape(-1), torch.as_tensor(caption[half:]).reshape(-1)]
+            text = [ids(caption[:half]), ids(caption[half:])]
         else:
             text = caption
         output = self.diffusion.training_losses(model=self.encoder, x_start=motion, t=t,
                                                 model_kwargs={"text": text, "length": cur_len},
                                                 forward_twice=forward_twice)
         self.real_noise, self.fake_noise = output["target"], output["pred"]
-        self.src_mask = self._net().generate_src_mask(T, cur_len).to(motion.device)
+        self.cur_len = cur_len
+        self.src_mask = (torch.arange(T, device=dev)[None, :] < cur_len[:, None]).float()   # generate_src_mask (:135-139)
 
     def backward_G(self):
         """Masked MSE: frame 0 scores its first 4 dims only, the other frames all dims (:223-247)."""
@@ -163,13 +174,88 @@ class DDPMMulTrainer(object):
         self.loss_mot_rec = loss
         return OrderedDict({"loss_mot_rec": self.loss_mot_rec.item()})
 
+    def _fused(self):
+        from .optim import FusedAdam
+        return isinstance(getattr(self, "opt_encoder", None), FusedAdam) and self.fake_noise.is_cuda
+
+    def update_async(self):
+        """One optimisation step without a host synchronisation; returns {'loss_mot_rec': device scalar}.
+        Fused path (FusedAdam): hig_masked_mse (loss + d loss/d pred) -> backward graphs -> hig_sumsq + hig_adam_flat."""
+        from . import ops
+        if not self._fused():
+            logs = self.update()
+            return OrderedDict((k, torch.as_tensor(v)) for k, v in logs.items())
+        self.opt_encoder.zero_grad()
+        pred = self.fake_noise
+        loss, d_pred = ops.masked_mse(pred.detach().float().contiguous(), self.real_noise.float().contiguous(),
+                                      self.cur_len.to(torch.int32), pit=not self.with_label)
+        pred.backward(d_pred.to(pred.dtype))
+        self.opt_encoder.step(clip_norm=0.5)
+        self.loss_mot_rec = loss
+        return OrderedDict({"loss_mot_rec": loss})
+
     def update(self):
+        if self._fused():
+            return OrderedDict((k, v.item()) for k, v in self.update_async().items())
         self.zero_grad([self.opt_encoder])
         loss_logs = self.backward_G()
         self.loss_mot_rec.backward()
         self.clip_norm([self.encoder])
         self.step([self.opt_encoder])
         return loss_logs
+
+    def train(self, train_dataset, rank, world_size):
+        """The reference's epoch loop (:289-341).  The optimizer is the flat fused Adam (same hyper-parameters and the same
+        state_dict format as `optim.Adam(self.encoder.parameters(), lr=self.opt.lr)`); losses are accumulated on the device
+        and read back every `log_every` iterations only."""
+        from .datasets import build_dataloader
+        from .optim import FusedAdam
+        opt = self.opt
+        self.to(self.device)
+        self.opt_encoder = FusedAdam(self.encoder, lr=opt.lr)
+        it, cur_epoch = 0, 0
+        if getattr(opt, "is_continue", False):
+            cur_epoch, it = self.load(os.path.join(opt.model_dir, "latest.tar"))
+        start_time = time.time()
+        loader = train_dataset if hasattr(train_dataset, "__iter__") and not hasattr(train_dataset, "__getitem__") else \
+            build_dataloader(train_dataset, rank, world_size, samples_per_gpu=opt.batch_size, drop_last=True,
+                             workers_per_gpu=getattr(opt, "workers_per_gpu", 4), shuffle=True)
+        log_path = getattr(opt, "log_file", None) or os.path.join(getattr(opt, "model_dir", "."), "train_log.jsonl")
+        max_iters = getattr(opt, "max_iters", None)
+        acc, n_acc = None, 0
+        self.mean_losses = []
+        for epoch in range(cur_epoch, opt.num_epochs):
+            self.train_mode()
+            if hasattr(getattr(loader, "sampler", None), "set_epoch"):
+                loader.sampler.set_epoch(epoch)
+            for i, batch_data in enumerate(loader):
+                self.forward(batch_data)
+                loss = self.update_async()["loss_mot_rec"].detach()
+                acc = loss.clone() if acc is None else acc + loss
+                n_acc += 1
+                it += 1
+                if it % opt.log_every == 0:
+                    mean = float(acc) / n_acc            # the only host synchronisation of the loop
+                    acc, n_acc = None, 0
+                    if rank == 0:
+                        self.mean_losses.append(mean)
+                        rec = {"it": it, "epoch": epoch, "inner_iter": i, "loss_mot_rec": mean,
+                               "elapsed_s": time.time() - start_time}
+                        print("epoch: %3d niter: %6d inner_iter: %4d %.1fs loss_mot_rec: %.4f"
+                              % (epoch, it, i, rec["elapsed_s"], mean), flush=True)
+                        with open(log_path, "a") as f:
+                            f.write(json.dumps(rec) + "\n")
+                if it % opt.save_latest == 0 and rank == 0:
+                    self.save(os.path.join(opt.model_dir, "latest.tar"), epoch, it)
+                if max_iters is not None and it >= max_iters:
+                    break
+            if rank == 0:
+                self.save(os.path.join(opt.model_dir, "latest.tar"), epoch, it)
+            if epoch % opt.save_every_e == 0 and rank == 0:
+                self.save(os.path.join(opt.model_dir, "ckpt_e%03d.tar" % epoch), epoch, total_it=it)
+            if max_iters is not None and it >= max_iters:
+                break
+        return it
 
     # ------------------------------------------------------------------------------------------ checkpoints (:269-287)
     def save(self, file_name, ep, total_it):

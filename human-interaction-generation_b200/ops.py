@@ -439,3 +439,43 @@ def eff_attn_bwd(mode, S, T, H, q=None, k=None, v=None, a_in=None, dy=None, dq=N
                               _ptr(dk), _ptr(dv), dk.stride(0) if dk is not None else 0, _ptr(dA), _ptr(length), S, T,
                               H, pair_shift, _dt(ref), _stream())
     _lib.check(rc, "hig_eff_attn_bwd")
+
+
+def masked_mse(pred, target, length, pit=False, want_grad=True):
+    """DDPMMulTrainer.backward_G's loss (labelled or PIT) and d loss / d pred.  Returns (loss device scalar, d_pred)."""
+    lib = _lib.load()
+    S, T, C = pred.shape
+    if pred.dtype != torch.float32 or target.dtype != torch.float32 or not pred.is_contiguous() or not target.is_contiguous():
+        raise ValueError("hig_b200.masked_mse: contiguous fp32 pred / target required")
+    if length is not None and (length.dtype != torch.int32 or length.numel() != S):
+        raise ValueError("hig_b200.masked_mse: length must be int32 [S]")
+    scratch = torch.empty(2 * S + 1, device=pred.device, dtype=torch.float32)
+    d_pred = torch.empty_like(pred) if want_grad else None
+    rc = lib.hig_masked_mse(_ptr(pred), _ptr(target), _ptr(length), S, T, C, 1 if pit else 0, _ptr(scratch[:S]),
+                            _ptr(scratch[S:2 * S]), _ptr(scratch[2 * S:]), _ptr(d_pred), _stream())
+    _lib.check(rc, "hig_masked_mse")
+    return scratch[2 * S], d_pred
+
+
+def sumsq(x, out):
+    """out (fp64 device scalar, caller-zeroed) += sum(x ** 2)."""
+    lib = _lib.load()
+    if x.dtype != torch.float32 or not x.is_contiguous() or out.dtype != torch.float64:
+        raise ValueError("hig_b200.sumsq: contiguous fp32 x, fp64 out")
+    rc = lib.hig_sumsq(_ptr(x), x.numel(), _ptr(out), _stream())
+    _lib.check(rc, "hig_sumsq")
+    return out
+
+
+def adam_flat(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, p_bf16=None, gnorm2=None, max_norm=0.0):
+    """One fused clip + Adam step over flat fp32 buffers (+ bf16 mirror of the new parameters)."""
+    lib = _lib.load()
+    n = p.numel()
+    for t in (p, g, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n:
+            raise ValueError("hig_b200.adam_flat: p, g, m, v must be contiguous fp32 of equal size")
+    if p_bf16 is not None and (p_bf16.dtype != torch.bfloat16 or p_bf16.numel() != n or not p_bf16.is_contiguous()):
+        raise ValueError("hig_b200.adam_flat: p_bf16 must be a contiguous bf16 mirror of p")
+    rc = lib.hig_adam_flat(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), n, float(lr), float(betas[0]), float(betas[1]),
+                           float(eps), int(step), _ptr(gnorm2), float(max_norm), _stream())
+    _lib.check(rc, "hig_adam_flat")

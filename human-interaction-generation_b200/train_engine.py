@@ -1,0 +1,617 @@
+"""TrainEngine — the bf16 training step of the denoiser as replayed CUDA graphs over static buffers.
+
+What it replaces: torch.autograd through MotionInteractionTransformer.forward (codes/models/interaction_transformer.py:
+577-616) inside DDPMMulTrainer.forward / update (codes/trainers/mul_ddpm_trainer.py:91-162, 249-256), data-parallel under
+tools/train.py:78-82.  Round 1 scheduled ~1 700 launches per iteration from Python (709 of this library + ~1 000 torch
+fills / casts / optimizer kernels): 54 ms per iteration of which only 28 ms was GPU work.  This module keeps the same
+kernels-only contract (no PyTorch math on the path) and removes the host from the loop:
+
+  * FlatParams: every trainable parameter is a view of ONE flat fp32 buffer (names, shapes and state_dict unchanged), with a
+    flat fp32 gradient buffer laid out in backward-completion order (heads | layer L-1 .. 0 | embeddings | non-denoiser
+    parameters) and a flat bf16 mirror that IS the GEMM operand set: Q|K|V, key|value and the 4L stylization emb-linears
+    are contiguous slices of it, so nothing is concatenated or cast per iteration except the mirror itself — and that is
+    written by the fused Adam kernel (hig_adam_flat) in the same sweep as the parameter update.
+  * the forward is one captured graph, the backward L + 2 graphs cut at the gradient-segment boundaries, so the
+    data-parallel reducer (ddp.py) can start the all-reduce of a segment between two replays while later segments run.
+  * weight gradients  dW = dY^T X  and data gradients  dX = dY W  run on the tcgen05 GEMM with MN-major operands
+    (hig_gemm_bf16_t): no transposed copies of activations, gradients or weights exist (round 1: 91 transposes per iteration).
+  * one memset of the flat gradient buffer replaces the per-tensor zero fills.
+"""
+import os
+
+import torch
+
+from . import ops
+from .autograd import denoiser_param_names
+
+HEAD_DIM = 64
+
+
+def _rup(n, m):
+    return (n + m - 1) // m * m
+
+
+# ====================================================================================================== flat parameters
+class FlatParams:
+    """fp32 parameters / gradients of a module as flat buffers (+ bf16 mirror); p.data become views (names unchanged)."""
+
+    ALIGN = 8     # elements: every parameter starts on a 32-byte (fp32) / 16-byte (bf16) boundary — TMA's operand rule
+
+    def __init__(self, module):
+        named = dict(module.named_parameters())
+        self.segments = denoiser_param_names(module)
+        den = [n for seg in self.segments for n in seg]
+        mine = set(den)
+        self.other_names = [n for n, p in named.items() if n not in mine and p.requires_grad]
+        dev = named[den[0]].device
+        if dev.type != "cuda":
+            raise RuntimeError("hig_b200: training runs on CUDA only (no CPU fallback); move the module to a GPU")
+        self.offsets, self.seg_bounds = {}, []
+        off = 0
+        for seg in self.segments + [self.other_names]:
+            lo = off
+            for n in seg:
+                off = _rup(off, self.ALIGN)
+                self.offsets[n] = off
+                off += named[n].numel()
+            off = _rup(off, self.ALIGN)
+            self.seg_bounds.append((lo, off))
+        self.n_den = self.seg_bounds[len(self.segments) - 1][1]
+        self.n_total = off
+        self.other_bounds = self.seg_bounds.pop()
+        self.param = torch.zeros(self.n_total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(self.n_total, device=dev, dtype=torch.float32)
+        self.mirror = torch.zeros(self.n_den, device=dev, dtype=torch.bfloat16)
+        self.names = den + self.other_names
+        self.shapes = {n: tuple(named[n].shape) for n in self.names}
+        with torch.no_grad():
+            for n in self.names:
+                p = named[n]
+                v = self.view32(n)
+                v.copy_(p.data)
+                p.data = v
+        self.gviews = {n: self._view(self.grad, n) for n in self.names}
+        self._mirror_key = None
+        self.direct = False          # True: gradients are exposed as persistent p.grad views (FusedAdam path)
+
+    def _view(self, flat, n):
+        o = self.offsets[n]
+        shape = self.shapes[n]
+        k = 1
+        for d in shape:
+            k *= d
+        return flat[o:o + k].view(shape)
+
+    def view32(self, n):
+        return self._view(self.param, n)
+
+    def view16(self, n):
+        return self._view(self.mirror, n)
+
+    def region(self, flat, first, count, shape):
+        o = self.offsets[first]
+        return flat[o:o + count].view(shape)
+
+    def owns(self, module):
+        named = dict(module.named_parameters())
+        for n in (self.names[0], self.names[-1]):
+            p = named.get(n)
+            if p is None or p.data_ptr() != self.param.data_ptr() + 4 * self.offsets[n] or tuple(p.shape) != self.shapes[n]:
+                return False
+        return True
+
+    def refresh_mirror(self, module, force=False):
+        """bf16 operand mirror <- fp32 parameters (one cast kernel) when a parameter changed behind our back (a third-party
+        optimizer, load_state_dict, ...).  hig_adam_flat writes the mirror itself and calls mark_mirror_fresh()."""
+        key = (getattr(module, "_hig_param_generation", 0),
+               sum(p._version for p in module.parameters() if p.requires_grad))
+        if force or key != self._mirror_key:
+            ops.act_fwd(self.param[:self.n_den], ops.ACT_NONE, self.mirror)
+            self._mirror_key = key
+            return True
+        return False
+
+    def mark_mirror_fresh(self, module):
+        module._hig_param_generation = getattr(module, "_hig_param_generation", 0) + 1
+        self._mirror_key = (module._hig_param_generation,
+                            sum(p._version for p in module.parameters() if p.requires_grad))
+
+
+def flat_params(module):
+    fp = getattr(module, "_hig_flat", None)
+    if fp is None or not fp.owns(module):
+        fp = FlatParams(module)
+        module._hig_flat = fp
+        module._hig_train_engine = None
+    return fp
+
+
+# ====================================================================================================== operand set
+def build_operands(module, fp, eng):
+    """The W dictionary of denoiser_engine.DenoiserEngine.packed(), as VIEWS: bf16 weights into the mirror, fp32 biases /
+    LayerNorm parameters into the live parameter buffer.  Only the K-padded motion-embedding operand and the positional
+    table are separate buffers (refresh_special)."""
+    D, E, C = eng.D, eng.E, eng.C
+    dev = fp.param.device
+    W = {}
+    w16, f32 = fp.view16, fp.view32
+    r16 = lambda first, rows, cols: fp.region(fp.mirror, first, rows * cols, (rows, cols))
+    r32 = lambda first, n: fp.region(fp.param, first, n, (n,))
+    half = D // 2
+    import math
+    W["freqs"] = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(dev)
+    W["te0.w"], W["te0.b"] = w16("time_embed.0.weight"), f32("time_embed.0.bias")
+    W["te2.w"], W["te2.b"] = w16("time_embed.2.weight"), f32("time_embed.2.bias")
+    subs = [("sa", "sa_block"), ("ca", "ca_block")] + ([] if module.no_cross_attn else [("ic", "int_ca_block")])
+    Dt = module.text_latent_dim
+    n_styl = 0
+    for i in range(module.num_layers):
+        p, mp = f"l{i}.", f"temporal_decoder_blocks.{i}."
+        for name, sub in subs:
+            q = mp + sub + "."
+            W[p + name + ".ln.w"], W[p + name + ".ln.b"] = f32(q + "norm.weight"), f32(q + "norm.bias")
+            if name == "ca":
+                W[p + "ca.tln.w"], W[p + "ca.tln.b"] = f32(q + "text_norm.weight"), f32(q + "text_norm.bias")
+                W[p + "ca.q.w"], W[p + "ca.q.b"] = w16(q + "query.weight"), f32(q + "query.bias")
+                W[p + "ca.kv.w"], W[p + "ca.kv.b"] = r16(q + "key.weight", 2 * D, Dt), r32(q + "key.bias", 2 * D)
+            else:
+                W[p + name + ".qkv.w"] = r16(q + "query.weight", 3 * D, D)
+                W[p + name + ".qkv.b"] = r32(q + "query.bias", 3 * D)
+        q = mp + "ffn."
+        W[p + "ffn.w1"], W[p + "ffn.b1"] = w16(q + "linear1.weight"), f32(q + "linear1.bias")
+        W[p + "ffn.w2"], W[p + "ffn.b2"] = w16(q + "linear2.weight"), f32(q + "linear2.bias")
+        for name, sub in subs + [("ffn", "ffn")]:
+            q = mp + sub + ".proj_out."
+            W[p + name + ".po.ln.w"], W[p + name + ".po.ln.b"] = f32(q + "norm.weight"), f32(q + "norm.bias")
+            W[p + name + ".po.w"], W[p + name + ".po.b"] = w16(q + "out_layers.2.weight"), f32(q + "out_layers.2.bias")
+            W[p + name + ".ss"] = n_styl
+            n_styl += 1
+    first_w = fp.segments[-1][0]
+    first_b = fp.segments[-1][n_styl]
+    W["emb.w"] = r16(first_w, n_styl * 2 * D, E)
+    W["emb.b"] = r32(first_b, n_styl * 2 * D)
+    W["n_styl"] = n_styl
+    W["out.w"], W["out.b"] = w16("out.weight"), f32("out.bias")
+    W["out2.w"], W["out2.b"] = w16("out2.weight"), f32("out2.bias")
+    W["in.w"] = torch.zeros(D, eng.CP, device=dev, dtype=torch.bfloat16)
+    W["in.pos"] = torch.zeros(module.num_frames, D, device=dev, dtype=torch.float32)
+    W["zero.b"] = {}
+    return W
+
+
+def refresh_special(module, W, C):
+    """[joint_embed.W | joint_embed2.W] K-padded operand and the positional rows (:593-602), in place."""
+    with torch.no_grad():
+        W["in.w"][:, :C].copy_(module.joint_embed.weight)
+        W["in.w"][:, C:C + 4].copy_(module.joint_embed2.weight)
+        pos = W["in.pos"]
+        pos[0].copy_(module.joint_embed2.bias)
+        torch.add(module.sequence_embedding[:module.num_frames - 1], module.joint_embed.bias[None], out=pos[1:])
+
+
+# ====================================================================================================== one shape's plan
+class _Plan:
+    """Static buffers + captured graphs of one (S, T, N) training shape."""
+
+    def __init__(self, te, S, T, N):
+        self.te, self.S, self.T, self.N = te, S, T, N
+        eng, dev = te.eng, te.fp.param.device
+        self.x = torch.zeros(S, T, eng.C, device=dev)
+        self.t = torch.zeros(S, device=dev, dtype=torch.int64)
+        self.len = torch.zeros(S, device=dev, dtype=torch.int32)
+        self.xf_proj = torch.zeros(S, eng.E, device=dev)
+        self.xf_out = torch.zeros(S, N, te.module.text_latent_dim, device=dev)
+        self.d_eps = torch.zeros(S, T, eng.C, device=dev)
+        self.saved = None
+        self.fwd_graph = None
+        self.bwd_graphs = None
+        self.results = None
+        self.use_graph = os.environ.get("HIG_TRAIN_GRAPH", "1") != "0"
+        self.launches_fwd = self.launches_bwd = 0
+
+    # ------------------------------------------------------------------------------------------ forward schedule
+    def _forward(self):
+        te = self.te
+        eng, W = te.eng, te.W
+        S, T, N = self.S, self.T, self.N
+        D, F_, E, H, L = eng.D, eng.F, eng.E, eng.H, eng.L
+        dev, tok = self.x.device, S * T
+        bf, f32 = torch.bfloat16, torch.float32
+        new = lambda *shape, dtype=bf: torch.empty(*shape, device=dev, dtype=dtype)
+        G = ops.gemm
+        st = type("Saved", (), {})()
+        # ---- embedding MLP (:591) and every StylizationBlock's (scale | shift) (:88-90)
+        st.temb = ops.timestep_embed(self.t, W["freqs"], new(S, D))
+        st.h0 = new(S, E)
+        G(st.temb, W["te0.w"], bias=W["te0.b"], out_bf16=st.h0)
+        st.te_h = ops.act_fwd(st.h0, ops.ACT_SILU, new(S, E))
+        st.emb = new(S, E, dtype=f32)
+        G(st.te_h, W["te2.w"], bias=W["te2.b"], out_f32=st.emb, residual=self.xf_proj)
+        st.semb = ops.act_fwd(st.emb, ops.ACT_SILU, new(S, E))
+        st.ss = new(S, W["n_styl"] * 2 * D, dtype=f32)
+        G(st.semb, W["emb.w"], bias=W["emb.b"], out_f32=st.ss)
+        # ---- text K/V side of every layer's cross attention (:155-161)
+        Dt = self.xf_out.shape[2]
+        st.xf = self.xf_out.view(S * N, Dt)
+        st.tn, st.kv, st.a_text = [], [], []
+        for i in range(L):
+            p = f"l{i}.ca."
+            tn = ops.ln_film_silu(st.xf, W[p + "tln.w"], W[p + "tln.b"], new(S * N, Dt))
+            kv = new(S * N, 2 * D)
+            G(tn, W[p + "kv.w"], bias=W[p + "kv.b"], out_bf16=kv)
+            a = new(S, H, HEAD_DIM, HEAD_DIM)
+            ops.eff_attn(ops.ATTN_KV_ONLY, S, N, H, k=kv[:, :D], v=kv[:, D:], a_out=a)
+            st.tn.append(tn); st.kv.append(kv); st.a_text.append(a)
+        # ---- motion embedding (:593-602)
+        st.xa = torch.zeros(tok, eng.CP, device=dev, dtype=bf)
+        ops.pack_motion(self.x, st.xa)
+        xres = new(tok, D, dtype=f32)
+        G(st.xa, W["in.w"], residual=W["in.pos"], res_row_mod=T, out_f32=xres)
+        st.blocks = []
+
+        def stylize_project(blk, y, xres_in, p, want_xb):
+            i = W[p + ".ss"]
+            ss = st.ss[:, i * 2 * D:(i + 1) * 2 * D]
+            sact = ops.ln_film_silu(y, W[p + ".po.ln.w"], W[p + ".po.ln.b"], new(tok, D), rows_per_seq=T, scale_shift=ss,
+                                    silu=True)
+            xres_out = new(tok, D, dtype=f32)
+            xb = new(tok, D) if want_xb else None
+            G(sact, W[p + ".po.w"], bias=W[p + ".po.b"], residual=xres_in, out_f32=xres_out, out_bf16=xb)
+            blk.update(y=y, sact=sact, ss_index=i)
+            return xres_out, xb
+
+        xb = None
+        kinds = ["sa", "ca"] + (["ic"] if eng.has_ic else [])
+        for li in range(L):
+            p = f"l{li}."
+            for kind in kinds:
+                blk = {"kind": kind, "xres_in": xres, "li": li}
+                n = ops.ln_film_silu(xres, W[p + kind + ".ln.w"], W[p + kind + ".ln.b"], new(tok, D))
+                y = new(tok, D)
+                if kind == "ca":
+                    qc = new(tok, D)
+                    G(n, W[p + "ca.q.w"], bias=W[p + "ca.q.b"], out_bf16=qc)
+                    ops.eff_attn(ops.ATTN_Q_ONLY, S, T, H, q=qc, a_in=st.a_text[li], y=y)
+                    blk.update(n=n, q=qc)
+                else:
+                    qkv = new(tok, 3 * D)
+                    G(n, W[p + kind + ".qkv.w"], bias=W[p + kind + ".qkv.b"], out_bf16=qkv)
+                    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+                    if kind == "sa":
+                        ops.eff_attn(ops.ATTN_SELF, S, T, H, q=q, k=k, v=v, y=y, length=self.len, mask_v=True)
+                    else:
+                        ops.eff_attn(ops.ATTN_INTER, S, T, H, q=q, k=k, v=v, y=y, length=self.len, pair_shift=S // 2,
+                                     mask_v=False)
+                    blk.update(n=n, qkv=qkv)
+                xres, xb = stylize_project(blk, y, xres, p + kind, kind == kinds[-1])
+                st.blocks.append(blk)
+            # FFN (:261-264)
+            blk = {"kind": "ffn", "xres_in": xres, "li": li, "xb_in": xb}
+            h1 = new(tok, F_)
+            G(xb, W[p + "ffn.w1"], bias=W[p + "ffn.b1"], out_bf16=h1)
+            g = ops.act_fwd(h1, ops.ACT_GELU, new(tok, F_))
+            y = new(tok, D)
+            G(g, W[p + "ffn.w2"], bias=W[p + "ffn.b2"], out_bf16=y)
+            blk.update(h1=h1, g=g)
+            xres, xb = stylize_project(blk, y, xres, p + "ffn", True)
+            st.blocks.append(blk)
+        # ---- output heads (:613-616)
+        st.xb_final = xb
+        st.eps = new(tok, eng.LD_EPS, dtype=f32)
+        G(xb, W["out.w"], bias=W["out.b"], out_f32=st.eps[:, :eng.C])
+        G(xb.view(S, T * D)[:, :D], W["out2.w"], bias=W["out2.b"], out_f32=st.eps.view(S, T * eng.LD_EPS)[:, :eng.C])
+        return st
+
+    # ------------------------------------------------------------------------------------------ backward schedule
+    def _backward(self):
+        """Generator: runs the backward kernels and yields after each gradient segment is final (heads, layers L-1..0,
+        embeddings).  The last value (StopIteration.value) is (d_xf_proj, d_xf_out)."""
+        te, st = self.te, self.saved
+        eng, W, fp = te.eng, te.W, te.fp
+        S, T, N, C = self.S, self.T, self.N, eng.C
+        D, F_, E, H = eng.D, eng.F, eng.E, eng.H
+        dev, tok = self.x.device, S * T
+        bf, f32 = torch.bfloat16, torch.float32
+        new = lambda *shape, dtype=bf: torch.empty(*shape, device=dev, dtype=dtype)
+        gv = fp.gviews
+        greg = lambda first, count, shape: fp.region(fp.grad, first, count, shape)
+
+        def zero_bias(n):
+            zb = W["zero.b"].get(n)
+            if zb is None:
+                zb = W["zero.b"][n] = torch.zeros(n, device=dev, dtype=f32)
+            return zb
+
+        def dgrad(dy, w, out=None, out_f32=None, accumulate=False):
+            """dx[M,K] (+)= dy[M,N] . W[N,K] with W as stored (MN-major B operand)."""
+            ops.gemm_t(dy, w, trans_b=True, bias=zero_bias(w.shape[1]), residual=out_f32 if accumulate else None,
+                       out_f32=out_f32, out_bf16=out)
+
+        def wgrad(dy, x, w_grad, split=True):
+            """w_grad[N,K] += dy[M,N]^T . x[M,K]: both operands token-major as they lie; K = tokens split over CTA pairs
+            (fp32 atomics into the zeroed gradient buffer).  split=False: enough output tiles to fill the machine — plain
+            stores (the region has a single writer)."""
+            ops.gemm_t(dy, x, trans_a=True, trans_b=True, out_f32=w_grad, split_k=-1 if split else 0)
+
+        def bcast(region2w):
+            """[2W] parameter-gradient region as a stride-0 [S, 2W] view: ln_film_silu_bwd accumulates every sequence's
+            (dgamma | dbeta) partials straight into the parameter gradient."""
+            return region2w.view(1, -1).expand(S, -1)
+
+        fp.grad[:fp.n_den].zero_()
+        d_ss = torch.zeros_like(st.ss)
+        d_xf = torch.zeros(S * N, st.xf.shape[1], device=dev, dtype=f32)
+
+        # ---------------- output heads: eps = out(h[:,1:]) / out2(h[:,0])  (:613-616)
+        d_eps = self.d_eps.view(tok, C)
+        LDE = _rup(C, 8)
+        de_a = torch.zeros(tok, LDE, device=dev, dtype=bf)               # frames >= 1 (frame-0 rows zeroed)
+        ops.transpose(d_eps, copy=de_a, colsum=gv["out.bias"], rows_zero_mod=T)
+        de_0 = torch.zeros(S, LDE, device=dev, dtype=bf)                  # frame 0 of every sequence
+        ops.transpose(d_eps.view(S, T * C)[:, :C], copy=de_0, colsum=gv["out2.bias"])
+        dres = new(tok, D, dtype=f32)
+        ops.gemm_t(de_a[:, :C], W["out.w"], trans_b=True, out_f32=dres)
+        ops.gemm_t(de_0[:, :C], W["out2.w"], trans_b=True, out_f32=dres.view(S, T * D)[:, :D])
+        wgrad(de_a[:, :C], st.xb_final, gv["out.weight"])
+        wgrad(de_0[:, :C], st.xb_final.view(S, T * D)[:, :D], gv["out2.weight"])
+        yield 0
+
+        def stylize_project_bwd(blk, pfx, mp):
+            dres_c = new(tok, D)
+            ops.transpose(dres, copy=dres_c, colsum=gv[mp + "proj_out.out_layers.2.bias"])
+            d_sact = new(tok, D)
+            dgrad(dres_c, W[pfx + ".po.w"], out=d_sact)
+            wgrad(dres_c, blk["sact"], gv[mp + "proj_out.out_layers.2.weight"])
+            i = blk["ss_index"]
+            ss = st.ss[:, i * 2 * D:(i + 1) * 2 * D]
+            d_y = new(tok, D)
+            ops.ln_film_silu_bwd(blk["y"], W[pfx + ".po.ln.w"], W[pfx + ".po.ln.b"], d_sact, d_y, T, scale_shift=ss,
+                                 silu=True, d_ss=d_ss[:, i * 2 * D:(i + 1) * 2 * D],
+                                 d_gb=bcast(greg(mp + "proj_out.norm.weight", 2 * D, (2 * D,))))
+            return d_y
+
+        def linear_bwd(dy, x_saved, w, w_grad, b_grad, dx_into=None):
+            ops.colsum(dy, b_grad)
+            dx = None
+            if dx_into is not None:
+                dgrad(dy, w, out_f32=dx_into, accumulate=True)
+            else:
+                dx = new(dy.shape[0], w.shape[1])
+                dgrad(dy, w, out=dx)
+            wgrad(dy, x_saved, w_grad)
+            return dx
+
+        def pre_ln_bwd(blk, d_n, pfx, mp):
+            ops.ln_film_silu_bwd(blk["xres_in"], W[pfx + ".ln.w"], W[pfx + ".ln.b"], d_n, dres, T, dx_accumulate=True,
+                                 d_gb=bcast(greg(mp + "norm.weight", 2 * D, (2 * D,))))
+
+        modname = {"sa": "sa_block.", "ca": "ca_block.", "ic": "int_ca_block.", "ffn": "ffn."}
+        seg = 1
+        for blk in reversed(st.blocks):
+            li, kind = blk["li"], blk["kind"]
+            pfx = f"l{li}.{kind}"
+            mp = f"temporal_decoder_blocks.{li}.{modname[kind]}"
+            d_y = stylize_project_bwd(blk, pfx, mp)
+            if kind == "ffn":
+                d_g = linear_bwd(d_y, blk["g"], W[f"l{li}.ffn.w2"], gv[mp + "linear2.weight"], gv[mp + "linear2.bias"])
+                d_h1 = ops.act_bwd(blk["h1"], d_g, ops.ACT_GELU, new(tok, F_))
+                # no pre-norm in the FFN: d(xres_in) = dres (skip path) + d_h1 . W1, accumulated by the GEMM epilogue
+                linear_bwd(d_h1, blk["xb_in"], W[f"l{li}.ffn.w1"], gv[mp + "linear1.weight"], gv[mp + "linear1.bias"],
+                           dx_into=dres)
+            elif kind == "ca":
+                d_q = new(tok, D)
+                dA = new(S, H, HEAD_DIM, HEAD_DIM, dtype=f32)
+                ops.eff_attn_bwd(ops.ATTN_Q_ONLY, S, T, H, q=blk["q"], a_in=st.a_text[li], dy=d_y, dq=d_q, dA=dA)
+                d_n = linear_bwd(d_q, blk["n"], W[f"l{li}.ca.q.w"], gv[mp + "query.weight"], gv[mp + "query.bias"])
+                pre_ln_bwd(blk, d_n, pfx, mp)
+                kv = st.kv[li]
+                d_kv = new(S * N, 2 * D)
+                ops.eff_attn_bwd(ops.ATTN_KV_ONLY, S, N, H, k=kv[:, :D], v=kv[:, D:], dk=d_kv[:, :D], dv=d_kv[:, D:], dA=dA)
+                Dt = st.xf.shape[1]
+                d_tn = linear_bwd(d_kv, st.tn[li], W[f"l{li}.ca.kv.w"], greg(mp + "key.weight", 2 * D * Dt, (2 * D, Dt)),
+                                  greg(mp + "key.bias", 2 * D, (2 * D,)))
+                ops.ln_film_silu_bwd(st.xf, W[pfx + ".tln.w"], W[pfx + ".tln.b"], d_tn, d_xf, N, dx_accumulate=True,
+                                     d_gb=bcast(greg(mp + "text_norm.weight", 2 * Dt, (2 * Dt,))))
+            else:
+                qkv = blk["qkv"]
+                d_qkv = new(tok, 3 * D)
+                mode = ops.ATTN_SELF if kind == "sa" else ops.ATTN_INTER
+                ops.eff_attn_bwd(mode, S, T, H, q=qkv[:, :D], k=qkv[:, D:2 * D], v=qkv[:, 2 * D:], dy=d_y,
+                                 dq=d_qkv[:, :D], dk=d_qkv[:, D:2 * D], dv=d_qkv[:, 2 * D:], length=self.len,
+                                 pair_shift=S // 2 if kind == "ic" else 0)
+                d_n = linear_bwd(d_qkv, blk["n"], W[f"l{li}.{kind}.qkv.w"], greg(mp + "query.weight", 3 * D * D, (3 * D, D)),
+                                 greg(mp + "query.bias", 3 * D, (3 * D,)))
+                pre_ln_bwd(blk, d_n, pfx, mp)
+            if kind == "sa":
+                yield seg        # every parameter of layer li (except its emb-linears) is final
+                seg += 1
+
+        # ---------------- motion embedding (:593-602)
+        dres_c = new(tok, D)
+        ops.transpose(dres, copy=dres_c)
+        w_in = torch.zeros(D, eng.CP, device=dev, dtype=f32)
+        wgrad(dres_c, st.xa, w_in)
+        gv["joint_embed.weight"].copy_(w_in[:, :C])
+        gv["joint_embed2.weight"].copy_(w_in[:, C:C + 4])
+        dpos = torch.zeros(T * D, device=dev, dtype=f32)
+        ops.colsum(dres.view(S, T * D), dpos)
+        dpos = dpos.view(T, D)
+        gv["joint_embed2.bias"].copy_(dpos[0])
+        if T > 1:
+            gv["sequence_embedding"][:T - 1].copy_(dpos[1:])
+            ops.colsum(dpos[1:], gv["joint_embed.bias"])
+
+        # ---------------- stylization emb-linears + time-embedding MLP (:88-90, :474-478, :591)
+        n_styl = W["n_styl"]
+        first_w = fp.segments[-1][0]
+        first_b = fp.segments[-1][n_styl]
+        d_ss_c = new(S, n_styl * 2 * D)
+        ops.transpose(d_ss, copy=d_ss_c, colsum=greg(first_b, n_styl * 2 * D, (n_styl * 2 * D,)))
+        d_semb = torch.zeros(S, E, device=dev, dtype=f32)      # K = 4L * 1024 is long, the output 8 tiles: split-K
+        ops.gemm_t(d_ss_c, W["emb.w"], trans_b=True, out_f32=d_semb, split_k=-1)
+        wgrad(d_ss_c, st.semb, greg(first_w, n_styl * 2 * D * E, (n_styl * 2 * D, E)), split=False)
+        d_emb = ops.act_bwd(st.emb, d_semb, ops.ACT_SILU, new(S, E, dtype=f32))
+        d_emb_c = new(S, E)
+        ops.transpose(d_emb, copy=d_emb_c, colsum=gv["time_embed.2.bias"])
+        d_te_h = new(S, E)
+        dgrad(d_emb_c, W["te2.w"], out=d_te_h)
+        wgrad(d_emb_c, st.te_h, gv["time_embed.2.weight"])
+        d_h0 = ops.act_bwd(st.h0, d_te_h, ops.ACT_SILU, new(S, E))
+        ops.colsum(d_h0, gv["time_embed.0.bias"])
+        wgrad(d_h0, st.temb, gv["time_embed.0.weight"])
+        self.results = (d_emb, d_xf.view(S, N, -1))
+        yield seg
+
+    # ------------------------------------------------------------------------------------------ execution
+    def _pool(self):
+        return self.te.pool
+
+    def forward(self):
+        from . import _lib
+        if not self.use_graph:
+            self.saved = self._forward()
+            return self.saved.eps
+        if self.fwd_graph is None:
+            c0 = _lib.launch_count()
+            self.saved = self._forward()          # eager once: lazy initialisation (kernel attributes, tensor maps) + warm-up
+            self.launches_fwd = _lib.launch_count() - c0
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._pool()):
+                self.saved = self._forward()
+            self.fwd_graph = g
+        self.fwd_graph.replay()
+        return self.saved.eps
+
+    def backward(self, hook):
+        """Runs (replays) the backward; hook(segment index) is called as soon as a gradient segment is final."""
+        from . import _lib
+        if not self.use_graph:
+            for seg in self._backward():
+                hook(seg)
+            return self.results
+        if self.bwd_graphs is None:
+            c0 = _lib.launch_count()
+            for _ in self._backward():             # eager once (warm-up); its gradients are discarded by the replay below
+                pass
+            self.launches_bwd = _lib.launch_count() - c0
+            torch.cuda.synchronize()
+            graphs, gen = [], self._backward()
+            n_seg = len(self.te.fp.seg_bounds)
+            for _ in range(n_seg):                 # one graph per gradient segment (the generator yields after each)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self._pool()):
+                    seg = next(gen)
+                graphs.append((g, seg))
+            gen.close()
+            self.bwd_graphs = graphs
+        for g, seg in self.bwd_graphs:
+            g.replay()
+            hook(seg)
+        return self.results
+
+
+# ====================================================================================================== engine
+class TrainEngine:
+    def __init__(self, module):
+        self.module = module
+        self.eng = module.engine("bf16")
+        self.fp = flat_params(module)
+        self.W = build_operands(module, self.fp, self.eng)
+        self.plans = {}
+        self.pool = torch.cuda.graph_pool_handle()
+        self.last = None
+
+    def plan(self, S, T, N):
+        key = (S, T, N)
+        p = self.plans.get(key)
+        if p is None:
+            if len(self.plans) >= 3:      # each plan pins its saved activations: keep a few shapes only
+                self.plans.pop(next(iter(self.plans)))
+            p = self.plans[key] = _Plan(self, S, T, N)
+        return p
+
+    def refresh(self):
+        """Operand mirror up to date with the fp32 parameters (no-op after hig_adam_flat, one cast kernel after a third-party
+        optimizer step) + the two derived operands of the motion embedding."""
+        self.fp.refresh_mirror(self.module)
+        refresh_special(self.module, self.W, self.eng.C)
+
+
+def train_engine(module):
+    fp = flat_params(module)
+    te = getattr(module, "_hig_train_engine", None)
+    if te is None or te.fp is not fp:
+        te = module._hig_train_engine = TrainEngine(module)
+    return te
+
+
+class DenoiserGraphFn(torch.autograd.Function):
+    """eps = denoiser(x, t, length, xf_proj, xf_out; params) on the captured graphs.  Gradients: xf_proj, xf_out and every
+    denoiser parameter (views of the flat gradient buffer, or — FlatParams.direct — written in place and not returned)."""
+
+    @staticmethod
+    def forward(ctx, module, x, timesteps, length, xf_proj, xf_out, *params):
+        te = train_engine(module)
+        S, T, C = x.shape
+        if S % 2:
+            raise ValueError("the batch stacks person 1 and person 2 on dim 0: S must be even")
+        if T > module.num_frames:
+            raise ValueError(f"T={T} exceeds num_frames={module.num_frames}")
+        te.refresh()
+        plan = te.plan(S, T, xf_out.shape[1])
+        plan.x.copy_(x.detach())
+        plan.t.copy_(timesteps.detach().to(torch.int64))
+        plan.len.copy_(length.to(device=x.device, dtype=torch.int32).clamp(min=0, max=T))
+        plan.xf_proj.copy_(xf_proj.detach())
+        plan.xf_out.copy_(xf_out.detach())
+        eps = plan.forward()
+        ctx.plan, ctx.te = plan, te
+        te.last = plan
+        return eps.view(S, T, te.eng.LD_EPS)[:, :, :C].contiguous()
+
+    @staticmethod
+    def backward(ctx, d_eps):
+        plan, te = ctx.plan, ctx.te
+        fp, module = te.fp, te.module
+        named = dict(module.named_parameters())
+        first = named[fp.names[0]]
+        # a p.grad that aliases the flat gradient buffer (left by a previous backward) would be doubled by autograd's
+        # in-place accumulation: preserve accumulate semantics explicitly
+        carry = None
+        if not fp.direct and first.grad is not None and first.grad.data_ptr() == fp.gviews[fp.names[0]].data_ptr():
+            carry = fp.grad[:fp.n_den].clone()
+            for n in fp.names[:len(fp.names) - len(fp.other_names)]:
+                named[n].grad = None
+        plan.d_eps.copy_(d_eps.detach())
+        hook = getattr(module, "_grad_segment_hook", None)
+
+        def seg_done(k):
+            if hook is not None:
+                lo, hi = fp.seg_bounds[k]
+                hook(k, fp.grad[lo:hi])
+
+        d_xf_proj, d_xf_out = plan.backward(seg_done)
+        fin = getattr(module, "_grad_finish_hook", None)
+        if fin is not None:
+            fin()
+        if carry is not None:
+            fp.grad[:fp.n_den].add_(carry)
+        ctx.plan = None
+        n_den = len(fp.names) - len(fp.other_names)
+        if fp.direct:
+            grads = [None] * n_den
+        else:
+            grads = [fp._view(fp.grad, n) for n in fp.names[:n_den]]
+        return (None, None, None, None, d_xf_proj.clone(), d_xf_out.clone(), *grads)
+
+
+def denoiser_forward_graph(module, x, timesteps, length, xf_proj, xf_out):
+    if not x.is_cuda:
+        raise RuntimeError("hig_b200: the denoiser runs on CUDA only (no CPU fallback)")
+    fp = flat_params(module)
+    named = dict(module.named_parameters())
+    n_den = len(fp.names) - len(fp.other_names)
+    params = [named[n] for n in fp.names[:n_den]]
+    ln = torch.as_tensor(length).reshape(-1)
+    return DenoiserGraphFn.apply(module, x.float(), timesteps, ln, xf_proj.float(), xf_out.float(), *params).to(x.dtype)

@@ -242,6 +242,24 @@ int hig_eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void
                      const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
                      const int* length, int S, int T, int H, int pair_shift, int dtype, void* stream);
 
+/* The reference's training loss and its gradient — DDPMMulTrainer.backward_G, trainers/mul_ddpm_trainer.py:223-247:
+ * per frame the mean over features of (pred - tgt)^2 (frame 0: its first 4 features only; frames >= 1: all C), weighted by
+ * the length mask, normalised by the mask sum.  pit != 0 (unlabelled mode, S = 4B sequences stacked (m1,c1) (m1,c2) (m2,c2)
+ * (m2,c1)): the two persons of an assignment are summed and the cheaper assignment of each pair is kept (:235-242).
+ * rows [S] and w [S] are fp32 scratch (per-sequence loss sums / gradient weights), loss a device scalar,
+ * d_pred (nullable) = d loss / d pred, fp32 [S,T,C]. */
+int hig_masked_mse(const float* pred, const float* tgt, const int* length, int S, int T, int C, int pit, float* rows,
+                   float* w, float* loss, float* d_pred, void* stream);
+
+/* *out (double, caller-zeroed) += sum_i x[i]^2 — the global gradient norm of clip_grad_norm_ (mul_ddpm_trainer.py:253) */
+int hig_sumsq(const float* x, long long n, double* out, void* stream);
+
+/* clip-by-global-norm + torch.optim.Adam step (mul_ddpm_trainer.py:253-255, :291) over flat fp32 buffers in one pass;
+ * p_bf16 (nullable) receives the bf16 mirror of the updated parameters (the tcgen05 GEMM operands).  gnorm2 (nullable):
+ * device double holding the squared global gradient norm; the gradient is scaled by min(1, max_norm / (norm + 1e-6)). */
+int hig_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                  float beta2, float eps, int step, const double* gnorm2, float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,259 @@
+"""Round-2 training path on the B200: the graph-replayed training engine (train_engine.py), the fused loss / gradient-norm /
+Adam kernels (csrc/train_ops.cu) against their torch formulations, FusedAdam's torch.optim.Adam compatibility, and the
+reference's `tools/train.py` control flow (build_models -> DDPMMulTrainer -> train with --is_continue) on the drop-ins.
+Reference lines: codes/trainers/mul_ddpm_trainer.py:223-256 (loss, clip, Adam), :289-341 (train), tools/train.py:37-90."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _ops():
+    import hig_b200  # noqa: F401
+    from hig_b200 import ops
+    return ops
+
+
+def _model(cuda, layers=2, seed=0, cap_id=True):
+    import hig_b200  # noqa: F401
+    from hig_b200.interaction_transformer import MotionInteractionTransformer
+    torch.manual_seed(seed)
+    m = MotionInteractionTransformer(263, num_frames=196, num_layers=layers, latent_dim=512, cap_id=cap_id)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if p.abs().max() == 0 and "norm.bias" not in name:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    return m.to(cuda)
+
+
+def _ref_loss(pred, tgt, mask, with_label):
+    """DDPMMulTrainer.backward_G, :223-247, verbatim arithmetic."""
+    l0 = ((pred[:, 0, :4] - tgt[:, 0, :4]) ** 2).mean(dim=-1)
+    l1 = ((pred[:, 1:] - tgt[:, 1:]) ** 2).mean(dim=-1)
+    loss = torch.cat([l0.unsqueeze(1), l1], dim=1)
+    if with_label:
+        return (loss * mask).sum() / mask.sum()
+    n = loss.shape[0]
+    loss = (loss * mask).sum(dim=1).view(2, n // 2).sum(dim=0)
+    return loss.view(2, n // 4).min(dim=0).values.sum() / (mask.sum() / 2)
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("pit", [False, True])
+@pytest.mark.parametrize("S,T", [(8, 91), (256, 91), (4, 1), (12, 196)])
+def test_masked_mse_matches_backward_G(cuda, S, T, pit):
+    ops = _ops()
+    C = 263
+    g = torch.Generator(device=cuda).manual_seed(S + T)
+    pred = torch.randn(S, T, C, device=cuda, generator=g)
+    tgt = torch.randn(S, T, C, device=cuda, generator=g)
+    lens = torch.randint(1, T + 1, (S // 4 if pit else S // 2,), device=cuda, generator=g)
+    lens = torch.cat([lens] * (4 if pit else 2)).int()
+    mask = (torch.arange(T, device=cuda)[None] < lens[:, None]).float()
+    pr = pred.clone().requires_grad_(True)
+    want = _ref_loss(pr, tgt, mask, not pit)
+    want.backward()
+    loss, d_pred = ops.masked_mse(pred, tgt, lens, pit=pit)
+    assert abs(loss.item() - want.item()) < 1e-5 * max(1.0, abs(want.item()))
+    assert rel(d_pred, pr.grad) < 1e-6
+    assert (d_pred[pr.grad == 0] == 0).all()       # masked frames, frame-0 features >= 4, the losing PIT assignment
+
+
+def test_sumsq_and_adam_flat_match_torch(cuda):
+    """hig_adam_flat == clip_grad_norm_(0.5) + torch.optim.Adam.step() over several steps, and its bf16 mirror."""
+    ops = _ops()
+    n = 1_000_003
+    g = torch.Generator(device=cuda).manual_seed(5)
+    p0 = torch.randn(n + 5, device=cuda, generator=g)[:n]          # odd length: scalar tail of the kernels
+    p0 = p0.clone()
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=2e-4)
+    p, m, v = p0.clone(), torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    pb = torch.empty(n, device=cuda, dtype=torch.bfloat16)
+    gn2 = torch.zeros((), device=cuda, dtype=torch.float64)
+    for step in range(1, 5):
+        grad = torch.randn(n, device=cuda, generator=g) * (3.0 if step % 2 else 1e-4)   # clipped and unclipped steps
+        ref.grad = grad.clone()
+        total = torch.nn.utils.clip_grad_norm_([ref], 0.5)
+        opt.step()
+        gn2.zero_()
+        ops.sumsq(grad, gn2)
+        assert abs(gn2.sqrt().item() - total.item()) < 1e-5 * total.item()
+        ops.adam_flat(p, grad, m, v, step, 2e-4, p_bf16=pb, gnorm2=gn2, max_norm=0.5)
+        assert rel(p, ref.data) < 1e-6
+        assert rel(m, opt.state[ref]["exp_avg"]) < 1e-5 and rel(v, opt.state[ref]["exp_avg_sq"]) < 1e-4
+        assert torch.equal(pb, p.bfloat16())
+
+
+# ------------------------------------------------------------------------------------------------ engine
+def test_graph_engine_matches_eager_schedule_and_is_replayable(cuda):
+    """The captured-graph training engine against round 1's eager kernel schedule (autograd.py) on the same weights and
+    inputs (bf16; wgrad summation order differs: tolerance, not equality), replayed twice with different inputs."""
+    import weights
+    L, S, T = 2, 6, 40
+    m = _model(cuda, layers=L, cap_id=True)
+    m.cap_id = False
+    m.train()
+    outs = {}
+    for seed in (11, 12):
+        inp = weights.make_inputs(seed, S, T, n_text=77, lengths=[40, 33, 12, 40, 33, 12])
+        tgt = weights.make_noise(seed, 0, S, T)[0].to(cuda)
+        g = lambda k: inp[k].to(cuda)
+        for mode in ("1", "0"):
+            os.environ["HIG_TRAIN_ENGINE"] = mode
+            try:
+                m.zero_grad(set_to_none=True)
+                xfp, xfo = g("xf_proj").requires_grad_(True), g("xf_out").requires_grad_(True)
+                pred = m(g("x"), g("t"), length=g("length"), xf_proj=xfp, xf_out=xfo)
+                ((pred - tgt) ** 2).mean().backward()
+                outs[(seed, mode)] = (pred.detach().clone(), xfp.grad.clone(), xfo.grad.clone(),
+                                      {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+            finally:
+                os.environ.pop("HIG_TRAIN_ENGINE", None)
+        new, old = outs[(seed, "1")], outs[(seed, "0")]
+        assert rel(new[0], old[0]) < 2e-3
+        assert rel(new[1], old[1]) < 2e-2 and rel(new[2], old[2]) < 2e-2
+        assert set(new[3]) == set(old[3])
+        worst = max((rel(new[3][n], old[3][n]), n) for n in old[3] if old[3][n].norm() > 1e-7 and not n.endswith("key.bias"))
+        assert worst[0] < 3e-2, worst
+    assert rel(outs[(11, "1")][0], outs[(12, "1")][0]) > 1e-2      # the second replay really used the new inputs
+
+
+def test_gradient_accumulation_semantics_without_zero_grad(cuda):
+    """Two backward passes without zero_grad in between accumulate (p.grad aliases the engine's flat buffer)."""
+    import weights
+    L, S, T = 1, 4, 24
+    m = _model(cuda, layers=L)
+    m.cap_id = False
+    m.train()
+    inp = weights.make_inputs(3, S, T, n_text=1)
+    g = lambda k: inp[k].to(cuda)
+
+    def run():
+        pred = m(g("x"), g("t"), length=g("length"), xf_proj=g("xf_proj"), xf_out=g("xf_out"))
+        (pred ** 2).mean().backward()
+
+    m.zero_grad(set_to_none=True)
+    run()
+    once = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    run()
+    for n, p in m.named_parameters():
+        if n in once and once[n].norm() > 1e-6:
+            assert rel(p.grad, 2 * once[n]) < 2e-2, n
+
+
+def test_fused_update_matches_reference_update(cuda):
+    """DDPMMulTrainer.update on the fused path (hig_masked_mse -> graphs -> hig_adam_flat) against the reference sequence
+    (eager masked MSE -> autograd -> clip_grad_norm_ -> torch Adam) from the same state, labelled and PIT, with caption ids
+    in the dataloader's collated format ([LongTensor[B]])."""
+    from hig_b200.mul_ddpm_trainer import DDPMMulTrainer
+    from hig_b200.optim import FusedAdam
+    for label_path in ("labels.npy", None):
+        params = {}
+        for fused in (True, False):
+            m = _model(cuda, layers=2, seed=7)
+            opt = argparse.Namespace(device=cuda, multi=True, label_path=label_path, cap_id=True, diffusion_steps=1000,
+                                     is_train=True)
+            tr = DDPMMulTrainer(opt, m)
+            tr.opt_encoder = FusedAdam(m, lr=2e-4) if fused else torch.optim.Adam(m.parameters(), lr=2e-4)
+            tr.train_mode()
+            B, T = 4, 24
+            gen = torch.Generator().manual_seed(9)
+            batch = ([torch.tensor([1, 2, 3, 4])], [torch.tensor([5, 6, 7, 8])], torch.randn(B, T, 263, generator=gen),
+                     torch.randn(B, T, 263, generator=gen), torch.tensor([24, 20, 9, 24]), None)
+            losses = []
+            for it in range(3):
+                np.random.seed(it)
+                torch.manual_seed(it)
+                tr.forward(batch)
+                losses.append(tr.update()["loss_mot_rec"])
+            params[fused] = ({n: p.detach().clone() for n, p in m.named_parameters()}, losses)
+        (pf, lf), (pr, lr_) = params[True], params[False]
+        assert all(abs(a - b) < 2e-2 * abs(b) for a, b in zip(lf, lr_)), (lf, lr_)
+        for n in pr:
+            # three Adam steps move every weight by <= 3 lr; compare the DISPLACEMENTS' direction via the parameters
+            assert (pf[n] - pr[n]).abs().max().item() <= 2.5 * 3 * 2e-4, n
+
+
+def test_fused_adam_state_dict_is_torch_adam_compatible(cuda, tmp_path):
+    from hig_b200.optim import FusedAdam
+    import weights
+    m = _model(cuda, layers=1)
+    m.cap_id = False
+    m.train()
+    inp = weights.make_inputs(3, 4, 24, n_text=1)
+    g = lambda k: inp[k].to(cuda)
+    fo = FusedAdam(m, lr=1e-3)
+    for _ in range(2):
+        fo.zero_grad()
+        pred = m(g("x"), g("t"), length=g("length"), xf_proj=g("xf_proj"), xf_out=g("xf_out"))
+        (pred ** 2).mean().backward()
+        fo.step(clip_norm=0.5)
+    sd = fo.state_dict()
+    torch.save(sd, tmp_path / "opt.pt")
+    to = torch.optim.Adam(m.parameters(), lr=1e-3)
+    to.load_state_dict(torch.load(tmp_path / "opt.pt"))           # torch's Adam accepts it ...
+    p0 = dict(m.named_parameters())["temporal_decoder_blocks.0.ffn.linear1.weight"]
+    assert torch.equal(to.state[p0]["exp_avg"], fo.fp._view(fo.exp_avg, "temporal_decoder_blocks.0.ffn.linear1.weight"))
+    assert int(to.state[p0]["step"]) == 2
+    fo2 = FusedAdam(m, lr=1e-3)
+    fo2.load_state_dict(to.state_dict())                          # ... and its own state loads back
+    assert fo2.step_count == 2 and torch.equal(fo2.exp_avg, fo.exp_avg) and torch.equal(fo2.exp_avg_sq, fo.exp_avg_sq)
+
+
+def test_reference_train_py_control_flow(cuda, tmp_path):
+    """tools/train.py:37-51 (build_models incl. --pretrained -> load_my_state_dict) and :57-90 (trainer.train over a
+    dataset) on the drop-ins: two epochs of two batches, checkpoints written, --is_continue resumes epoch / iteration /
+    optimizer state, the loss log is JSON lines."""
+    from hig_b200.datasets import SyntheticText2MotionMulDataset
+    from hig_b200.interaction_transformer import MotionInteractionTransformer
+    from hig_b200.mul_ddpm_trainer import DDPMMulTrainer
+    pre = _model(cuda, layers=1, seed=21).state_dict()
+    pre["clip.fake.weight"] = torch.zeros(3)                      # keys of a text-conditioned checkpoint: skipped silently
+    opt = argparse.Namespace(device=cuda, multi=True, label_path="labels.npy", cap_id=True, diffusion_steps=1000,
+                             is_train=True, lr=2e-4, is_continue=False, model_dir=str(tmp_path), batch_size=8, num_epochs=2,
+                             log_every=2, save_latest=3, save_every_e=1, workers_per_gpu=0, only_language=False,
+                             only_motion=False, max_motion_length=196, num_layers=1, latent_dim=512)
+
+    def build_models(opt):
+        enc = MotionInteractionTransformer(input_feats=263, num_frames=opt.max_motion_length, num_layers=opt.num_layers,
+                                           latent_dim=opt.latent_dim, no_clip=False, no_eff=False, no_cross_attn=False,
+                                           cap_id=opt.cap_id)
+        enc.load_my_state_dict(pre, opt)
+        return enc
+
+    enc = build_models(opt).cuda()
+    assert all(torch.equal(v.cpu(), pre[k].cpu()) for k, v in enc.state_dict().items())
+    trainer = DDPMMulTrainer(opt, enc)
+    ds = SyntheticText2MotionMulDataset(n_items=16, cap_id=True, with_label=True, seed=1)
+    item = ds[0]
+    assert item[2].shape == (91, 263) and item[3].shape == (91, 263) and isinstance(item[0], list)
+    it = trainer.train(ds, 0, 1)
+    assert it == 4
+    assert os.path.exists(tmp_path / "latest.tar") and os.path.exists(tmp_path / "ckpt_e000.tar") and os.path.exists(tmp_path / "ckpt_e001.tar")
+    recs = [json.loads(l) for l in open(tmp_path / "train_log.jsonl")]
+    assert [r["it"] for r in recs] == [2, 4] and all(np.isfinite(r["loss_mot_rec"]) for r in recs)
+    # resume: --is_continue picks up epoch / iteration / Adam state and trains the remaining epoch
+    opt2 = argparse.Namespace(**{**vars(opt), "is_continue": True, "num_epochs": 3})
+    enc2 = build_models(opt2).cuda()
+    tr2 = DDPMMulTrainer(opt2, enc2)
+    it2 = tr2.train(ds, 0, 1)
+    assert it2 == 8, it2          # like the reference, the epoch the checkpoint was written in is run again (:294-296, :307)
+    assert tr2.opt_encoder.step_count == it2
+    ck = torch.load(tmp_path / "latest.tar", map_location="cpu")
+    assert ck["total_it"] == it2 and set(ck) == {"opt_encoder", "ep", "total_it", "encoder"}

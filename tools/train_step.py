@@ -24,6 +24,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--denoiser-only", action="store_true", help="cap_id model: no CLIP / text-encoder forward")
     ap.add_argument("--pit", action="store_true", help="unlabelled (PIT) mode: 4B sequences per iteration")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: hig_b200.optim.FusedAdam + fused loss (product path); torch: reference sequence on torch.optim.Adam")
+    ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the timed iterations (ncu --profile-from-start off)")
+    ap.add_argument("--no-reduce", action="store_true", help="DataParallel with the gradient all-reduce disabled (exposed-comm A/B)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -48,10 +52,17 @@ def main():
     if world > 1:
         from hig_b200.ddp import DataParallel
         enc = DataParallel(m)
+        if args.no_reduce:
+            m._grad_segment_hook = None
+            m._grad_finish_hook = None
     opt = argparse.Namespace(device=dev, multi=True, label_path=None if args.pit else "labels", cap_id=args.denoiser_only,
                              diffusion_steps=1000, is_train=True)
     tr = DDPMMulTrainer(opt, enc)
-    tr.opt_encoder = torch.optim.Adam(m.parameters(), lr=2e-4, fused=True)
+    if args.optimizer == "fused":
+        from hig_b200.optim import FusedAdam
+        tr.opt_encoder = FusedAdam(m, lr=2e-4)
+    else:
+        tr.opt_encoder = torch.optim.Adam(m.parameters(), lr=2e-4, fused=True)
     tr.train_mode()
     B, T = args.pairs, args.frames
     rs = np.random.RandomState(rank)
@@ -60,14 +71,16 @@ def main():
     else:
         c1 = [bench.CAPTIONS[(i + rank) % len(bench.CAPTIONS)][0] for i in range(B)]
         c2 = [bench.CAPTIONS[(i + rank) % len(bench.CAPTIONS)][1] for i in range(B)]
-    batch = (c1, c2, torch.randn(B, T, 263), torch.randn(B, T, 263), torch.from_numpy(rs.randint(20, 200, B)), None)
+    # pinned host memory, as hig_b200.datasets.build_dataloader hands the batches over
+    batch = (c1, c2, torch.randn(B, T, 263).pin_memory(), torch.randn(B, T, 263).pin_memory(),
+             torch.from_numpy(rs.randint(20, 200, B)), None)
 
     def it():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
         tr.forward(batch)
         ev[1].record()
-        logs = tr.update()
+        logs = tr.update_async()
         ev[2].record()
         return ev, logs
 
@@ -78,10 +91,14 @@ def main():
         dist.barrier()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     evs = [it() for _ in range(args.iters)]
     e1.record()
     torch.cuda.synchronize()
+    if args.profile:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1) / args.iters
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -95,7 +112,7 @@ def main():
         print(json.dumps({"workload": f"training step, {B} pairs/GPU x {T} frames, {'PIT' if args.pit else 'labelled'}, "
                                       f"{'denoiser only (cap_id)' if args.denoiser_only else 'with CLIP + text encoder'}",
                           "n_gpus": world, "ms_per_iter": ms, "pairs_per_s": world * B / ms * 1e3,
-                          "forward_ms": fwd, "backward_plus_adam_ms": bwd, "loss": evs[-1][1]["loss_mot_rec"],
+                          "forward_ms": fwd, "backward_plus_adam_ms": bwd, "loss": float(evs[-1][1]["loss_mot_rec"]), "optimizer": args.optimizer,
                           "hig_launches_per_iter": (_lib.launch_count() - l0) / args.iters,
                           "denoiser_fwd_bwd_tflops": fl / (ms * 1e-3) / 1e12,
                           "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
