@@ -210,24 +210,216 @@ def cpu_reference_arm(state_dict, B, T, n_denoiser_steps, warm):
     return sum(times) / len(times), times
 
 
+def gpu_eager_reference(model, device, B, T, n_steps=3):
+    """The reference's own formulation on this GPU: the oracle port (plain eager PyTorch, fp32, TF32 off — what running
+    line/Human-Interaction-Generation's denoiser + posterior step unmodified on a B200 costs), `n_steps` denoiser steps at the
+    bench shape, CUDA events.  It is a comparator, not the product: nothing of hig_b200's kernels is on this path."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import denoiser_oracle as DO
+    import diffusion_oracle as DF
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        S = 2 * B
+        g = torch.Generator(device=device).manual_seed(0)
+        sd = {k: v.detach().float() for k, v in model.state_dict().items()
+              if not k.startswith(("clip.", "textTrans", "text_pre", "text_ln"))}
+        x = torch.randn(S, T, CFG["feats"], device=device, generator=g)
+        xf_proj = torch.randn(S, 4 * CFG["latent"], device=device, generator=g) * 0.5
+        xf_out = torch.randn(S, CFG["text_tokens"], CFG["text_dim"], device=device, generator=g)
+        length = torch.full((S,), T, dtype=torch.long, device=device)
+        sch = DF.Schedule(CFG["diffusion_steps"])
+        ev = []
+        with torch.no_grad():
+            for i in range(n_steps + 1):
+                t = torch.full((S,), CFG["diffusion_steps"] - 1 - i, dtype=torch.long, device=device)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                eps = DO.denoiser_forward(sd, x, t, length, xf_proj, xf_out)
+                x = DF.p_sample_step(sch, x, eps, t, torch.randn(x.shape, device=device, generator=g))
+                e1.record()
+                ev.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in ev[1:])[len(ev[1:]) // 2]
+        return {"us_per_denoiser_step": ms * 1e3, "interactions_per_s": B / (ms * 1e-3 * CFG["diffusion_steps"]),
+                "what": f"oracle port of the reference denoiser + posterior step, eager PyTorch fp32 (TF32 off) on this GPU, "
+                        f"median of {n_steps} steps at {B} pairs x {T} frames, extrapolated to {CFG['diffusion_steps']} steps; "
+                        f"the reference's per-step host mask loop (0.5 s at S=1024) and its text encoder are not included"}
+    except Exception as ex:  # noqa
+        return {"error": f"{type(ex).__name__}: {ex}"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+
+
+def train_block(device, rank, world, iters, pk):
+    """BASELINE configs[3]: the DDP training step — 128 pairs per GPU x 91 frames (the rows the dataset produces,
+    datasets/mul_dataset.py:186-201), labelled mode, caption ids (cap_id: denoiser only), through
+    DDPMMulTrainer.forward / update_async on the graph-replayed engine with the fused loss / clip / Adam kernels.
+    N > 1: NCCL gradient-equality check first, then the same loop with the all-reduce disabled (exposed communication) and
+    the all-reduce of the flat gradient buffer alone."""
+    import numpy as np
+    import torch.distributed as dist
+    from hig_b200 import ops
+    from hig_b200.interaction_transformer import MotionInteractionTransformer
+    from hig_b200.mul_ddpm_trainer import DDPMMulTrainer
+    from hig_b200.optim import FusedAdam
+    B, T = 128, 91
+    torch.manual_seed(0)
+    m = MotionInteractionTransformer(CFG["feats"], num_frames=CFG["frames"], num_layers=CFG["layers"], latent_dim=CFG["latent"],
+                                     cap_id=True)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if p.abs().max() == 0 and "norm.bias" not in name:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    m = m.to(device)
+    enc = m
+    if world > 1:
+        from hig_b200.ddp import DataParallel
+        enc = DataParallel(m)
+    opt = argparse.Namespace(device=device, multi=True, label_path="labels", cap_id=True, diffusion_steps=1000, is_train=True)
+    tr = DDPMMulTrainer(opt, enc)
+    tr.opt_encoder = FusedAdam(m, lr=2e-4)
+    tr.train_mode()
+    rs = np.random.RandomState(100 + rank)
+    gen = torch.Generator().manual_seed(100 + rank)
+    batch = (list(rs.randint(0, 43, B)), list(rs.randint(0, 43, B)), torch.randn(B, T, CFG["feats"], generator=gen).pin_memory(),
+             torch.randn(B, T, CFG["feats"], generator=gen).pin_memory(), torch.from_numpy(rs.randint(20, 200, B)), None)
+    hooks = (getattr(m, "_grad_segment_hook", None), getattr(m, "_grad_finish_hook", None))
+
+    def set_hooks(on):
+        m._grad_segment_hook, m._grad_finish_hook = hooks if on else (None, None)
+
+    from hig_b200.datasets import DevicePrefetcher
+
+    class _Repeat:        # the same pinned batch through the prefetcher DDPMMulTrainer.train uses (H2D on a side stream)
+        def __iter__(self):
+            while True:
+                yield batch
+    feed = iter(DevicePrefetcher(_Repeat(), device))
+
+    def run(n):
+        for _ in range(3):
+            tr.forward(next(feed))
+            tr.update_async()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            tr.forward(next(feed))
+            loss = tr.update_async()["loss_mot_rec"]
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            tt = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = tt.item()
+        return ms, float(loss)
+
+    out = {"workload": f"configs[3]: DDP training step, {B} pairs/GPU x {T} frames, labelled, caption ids (denoiser + loss + "
+                       f"clip + Adam; text encoder not on this path)", "iters": iters, "optimizer": "hig_b200.optim.FusedAdam"}
+    fp = tr.opt_encoder.fp
+    # ---- gradient equality across ranks (what tools/ddp_check.py asserts), on the production engine
+    if world > 1:
+        def grads(on):
+            set_hooks(on)
+            np.random.seed(7); torch.manual_seed(7)
+            tr.forward(batch)
+            tr.opt_encoder.zero_grad()
+            _, d_pred = ops.masked_mse(tr.fake_noise.detach().float().contiguous(), tr.real_noise.float().contiguous(),
+                                       tr.cur_len.to(torch.int32))
+            tr.fake_noise.backward(d_pred)
+            torch.cuda.synchronize()
+            return fp.grad[:fp.n_den].clone()
+        local = grads(False)
+        want = local.clone()
+        dist.all_reduce(want)
+        want /= world
+        got = grads(True)
+        err = ((got - want).norm() / want.norm().clamp_min(1e-20)).item()
+        same = got.clone()
+        dist.broadcast(same, src=0)
+        identical = bool(torch.equal(same, got))
+        flags = torch.tensor([1.0 if (err < 2e-3 and identical) else 0.0], device=device)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        out["ddp_check"] = {"ok": bool(flags.item() > 0), "rel_err_vs_mean_of_local_grads": err,
+                            "identical_on_all_ranks": identical,
+                            "what": "flat denoiser gradient after the overlapped NCCL all-reduce vs the all-reduced mean of the "
+                                    "ranks' local gradients (bf16 split-K atomics reorder fp32 sums between two backward runs: "
+                                    "tolerance 2e-3, not equality)"}
+        set_hooks(True)
+    else:
+        out["ddp_check"] = None
+    ms, loss = run(iters)
+    fl = flops_per_denoiser_step(2 * B, T) * 3
+    tf = fl / (ms * 1e-3) / 1e12
+    out.update({"ms_per_iter": ms, "pairs_per_s": world * B / ms * 1e3, "loss": loss, "denoiser_fwd_bwd_tflops": tf,
+                "roofline_frac": tf / pk["bf16_tflops_sustained"],
+                "roofline_basis": f"3 x {fl / 3e9:.1f} algorithmic GFLOP (forward + 2x backward, SURVEY §8d) per iteration and GPU "
+                                  f"over the CUDA-event time, against the {pk['source']} sustained bf16 peak",
+                "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30})
+    if world > 1:
+        red = enc.reducer
+        b0, c0 = red.bytes_reduced, red.calls
+        ms1, _ = run(max(2, iters // 4))
+        n_it = max(2, iters // 4) + 3
+        out["allreduce_bytes"] = (red.bytes_reduced - b0) / n_it
+        out["allreduce_calls_per_iter"] = (red.calls - c0) / n_it
+        set_hooks(False)
+        ms_off, _ = run(iters)
+        set_hooks(True)
+        # the all-reduce alone, same buffer, same collective
+        flat = fp.grad[:fp.n_den]
+        for _ in range(2):
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ar = e0.elapsed_time(e1) / 5
+        exposed = max(ms - ms_off, 0.0)
+        out.update({"ms_per_iter_allreduce_off": ms_off, "exposed_allreduce_ms": exposed, "allreduce_alone_ms": ms_ar,
+                    "overlap_frac": max(0.0, min(1.0, 1.0 - exposed / ms_ar)) if ms_ar > 0 else None,
+                    "allreduce_busbw_gbs": 2 * (world - 1) / world * flat.numel() * 4 / (ms_ar * 1e-3) / 1e9})
+    else:
+        out.update({"allreduce_bytes": 0, "overlap_frac": None})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=CFG["pairs"])
+    ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU (default: 64 at N=1 = configs[1]; 512 / N at N>1 = configs[2])")
+    ap.add_argument("--train-iters", type=int, default=20, help="timed iterations of the configs[3] training block (0 = skip)")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-formulation-on-this-GPU comparator")
     ap.add_argument("--diffusion-steps", type=int, default=CFG["diffusion_steps"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    CFG["pairs"], CFG["diffusion_steps"] = args.pairs, args.diffusion_steps
-    B, T, C, NS = CFG["pairs"], CFG["frames"], CFG["feats"], CFG["diffusion_steps"]
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    workload = {"workload": f"configs[1]: full {NS}-step DDPM sampling, {B} pairs/GPU x {T} frames x {C} feats, "
+    ngpu = max(world, args.gpus if args.impl == "reference" else world)
+    # N = 1: configs[1] (64 pairs).  N > 1: configs[2], a fixed batch of 512 pairs split over the N GPUs (strong scaling).
+    strong = ngpu > 1 and args.pairs is None
+    CFG["pairs"] = args.pairs if args.pairs is not None else (512 // ngpu if ngpu > 1 else 64)
+    CFG["diffusion_steps"] = args.diffusion_steps
+    B, T, C, NS = CFG["pairs"], CFG["frames"], CFG["feats"], CFG["diffusion_steps"]
+    which = f"configs[2]: batch of {B * ngpu} pairs sharded over {ngpu} GPUs ({B} per GPU)" if ngpu > 1 else "configs[1]"
+    workload = {"workload": f"{which}: full {NS}-step DDPM sampling, {B} pairs/GPU x {T} frames x {C} feats, "
                             f"8-layer role-aware denoiser, random-init CLIP-shaped text encoder",
-                "pairs_per_gpu": B, "frames": T, "diffusion_steps": NS, "parallelism": f"batch-shard x{world}",
+                "pairs_per_gpu": B, "total_pairs": B * ngpu, "frames": T, "diffusion_steps": NS,
+                "parallelism": f"batch-shard x{ngpu}",
                 "l2": "working set per denoiser step (~1.5 GB of activations + 214 MB weights) exceeds the 126 MB L2"}
     unit = "interactions/s"
 
@@ -250,11 +442,13 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": "interactions/sec (full DDPM sample, 196f)", "value": val, "unit": unit,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per * NS * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload,
-            "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} of {NS} denoiser+posterior steps at {B} pairs x {T} frames "
-                                       f"({s_per:.3f} s each), extrapolated x{NS}/{1}"},
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload, "extrapolated": True,
+            "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "extrapolated": True,
+                             "sample": f"{args.steps} of {NS} denoiser + posterior-update steps at {B} pairs x {T} frames "
+                                       f"({s_per:.3f} s each, oracle port of the reference, torch fp32, {cores} host threads), "
+                                       f"extrapolated x{NS}; excluded: the text encoder (once per sample) and the reference's "
+                                       f"per-step host mask loop — both would make the reference slower"},
             "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -312,15 +506,22 @@ def main():
     value = world * B * args.steps / dt
 
     # ---------------- end-to-end arm: host captions + host lengths in, host motions out ----------------
+    # N > 1: the whole batch's captions / lengths go to hig_b200.ddp.generate_sharded, every rank samples its slice and
+    # copies it (asynchronous DMA) into ONE host buffer shared by the ranks (ddp.HostGather: /dev/shm mapping registered with
+    # CUDA) — no gather collective, no single-rank D2H funnel; rank 0 holds all samples in host memory after the barrier.
+    hg = None
+    if world > 1:
+        from hig_b200.ddp import HostGather, generate_sharded
+        all1 = [CAPTIONS[i % len(CAPTIONS)][0] for i in range(B * world)]
+        all2 = [CAPTIONS[i % len(CAPTIONS)][1] for i in range(B * world)]
+        all_lens = torch.full((B * world,), T, dtype=torch.long)
+        hg = HostGather(B * world, T, C, tag="bench")
+
     def e2e_step():
+        if world > 1:
+            return generate_sharded(trainer, all1, all2, all_lens, C, batch_size=512, host_gather=hg)
         out = trainer.generate(caps1, caps2, m_lens_host, C)
         res = torch.stack([torch.stack(p) for p in out])          # [B, 2, T, C] on device
-        if world > 1:
-            gl = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
-            dist.gather(res, gl, dst=0)
-            if rank == 0:
-                return torch.cat(gl).cpu()
-            return None
         return res.cpu()
 
     e2e_step()
@@ -335,15 +536,27 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt_e2e = tt.item()
     e2e_val = world * B * args.steps / dt_e2e
-    h2d = S * 77 * 8 + B * 8                      # token ids [S,77] int64 + lengths [B] int64
-    d2h = B * 2 * T * C * 4 * (world if world > 1 else 1)
+    if hg is not None:
+        hg.close()
+    h2d = (S * 77 * 8 + B * 8) * world            # token ids [S,77] int64 + lengths [B] int64, per rank
+    d2h = B * 2 * T * C * 4 * world               # every rank's samples, each by its own DMA
+
+    # ---------------- configs[3]: the DDP training step (all ranks take part) ----------------
+    pk = peaks()
+    train = None
+    if args.train_iters > 0:
+        try:
+            torch.cuda.empty_cache()
+            train = train_block(device, rank, world, args.train_iters, pk)
+        except Exception as ex:  # noqa
+            import traceback
+            train = {"error": f"{type(ex).__name__}: {ex}", "trace": traceback.format_exc()[-1500:]}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    pk = peaks()
     f_step = flops_per_denoiser_step(S, T)
     ach = f_step * NS * args.steps / dt / 1e12      # per GPU: each rank runs the same per-GPU workload
     roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -357,22 +570,32 @@ def main():
     except Exception as ex:  # noqa
         roof["kernel"] = {"error": str(ex)}
 
+    gpu_eager = None
+    if not args.no_gpu_eager:
+        gpu_eager = gpu_eager_reference(model, device, B, T)
+
     cpu = None
     if not args.no_cpu_baseline:
         sd = {k: v for k, v in model.state_dict().items()}
         s_per, _ = cpu_reference_arm(sd, B, T, 2, 1)
         cpu = {"value": B / (s_per * NS), "unit": unit, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": f"2 of {NS} denoiser+posterior steps at {B} pairs x {T} frames on the host CPU "
-                         f"({s_per:.2f} s each, oracle port, torch fp32, all threads), extrapolated to {NS} steps"}
+                         f"({s_per:.2f} s each, oracle port, torch fp32, all threads), extrapolated to {NS} steps",
+               "extrapolated": True}
 
     print(json.dumps({
         "metric": "interactions/sec (full DDPM sample, 196f)", "value": value, "unit": unit, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload,
-        "us_per_denoiser_step": dt / (args.steps * NS) * 1e6,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload, "us_per_denoiser_step": dt / (args.steps * NS) * 1e6,
         "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "DDPMMulTrainer.generate(caption strings, host lengths) -> host tensors"},
-        "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}))
+                "api": ("hig_b200.ddp.generate_sharded(trainer, caption strings, host lengths) -> one pinned host tensor shared "
+                        "by the ranks (per-rank D2H DMA, no gather collective)") if world > 1 else
+                       "DDPMMulTrainer.generate(caption strings, host lengths) -> host tensors",
+                "text_cache": "the frozen-CLIP feature cache is warm (same captions as the warm-up call): the timed text work "
+                              "is tokenisation + the 4-layer text encoder + text_proj, not the 12-layer CLIP stack"},
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "train": train,
+        "reference_gpu_eager": gpu_eager}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -22,6 +22,7 @@ SIGNATURES = {
     "hig_last_error": [],
     "hig_launch_count": [],
     "hig_debug_trace": [c_void_p, c_int],
+    "hig_debug_saturation": [c_void_p],
     "hig_l2_persist": [c_void_p, c_ull, ctypes.c_float, c_void_p],
     "hig_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                       c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
@@ -63,6 +64,7 @@ SIGNATURES = {
                              c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
     "hig_eff_attn_bwd": [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                          c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "hig_mha_attention": [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "hig_masked_mse": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                        c_void_p],
     "hig_sumsq": [c_void_p, ctypes.c_longlong, c_void_p, c_void_p],

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libhig_b200.so")
 SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemm2_tcgen05.cu", "gemm_stream.cu", "gemm_simt.cu", "ln_film.cu", "eff_attn.cu", "attn_apply.cu", "attn_apply_tc.cu", "diffusion_ops.cu",
-           "joints.cu", "bwd_ops.cu", "eff_attn_bwd.cu", "eff_attn_bwd_tc.cu", "train_ops.cu"]
+           "joints.cu", "bwd_ops.cu", "eff_attn_bwd.cu", "eff_attn_bwd_tc.cu", "train_ops.cu", "text_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -207,24 +207,30 @@ attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int sw2 = (lane >> 1) & 3;
     const bool silu = (apply_silu & 1) != 0;
     const float hs = silu ? 0.5f : 1.0f;     // SiLU(x) = h + h tanh(h), h = x / 2: the affine carries the 1/2
+    // folded FiLM affine of a tile's sequence: out = n_hat * G + B,  G = gamma (1 + scale),  B = beta (1 + scale) + shift.
+    // Written one tile AHEAD (double-buffered by tile parity) so that its global loads never sit on a tile's critical path.
+    auto stage_affine = [&](int tile, uint32_t par) {
+      const int s = tile_seq(tile);
+      float* sG = sGB + par * 1024;
+      float* sB = sG + 512;
+      const int c = et;
+      float gg = __ldg(gamma + c), bb = __ldg(beta + c);
+      if (scale_shift != nullptr) {
+        const float m1 = 1.0f + __ldg(scale_shift + (size_t)s * ss_stride + c);
+        gg *= m1;
+        bb = fmaf(bb, m1, __ldg(scale_shift + (size_t)s * ss_stride + 512 + c));
+      }
+      sG[c] = gg * hs;
+      sB[c] = bb * hs;
+    };
+    pdl_wait();          // scale_shift comes from this step's FiLM GEMM
+    if ((int)blockIdx.x < num_tiles) stage_affine(blockIdx.x, 0);
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int s = tile_seq(tile), r0 = tile_row0(tile);
       const uint32_t par = lt & 1u;
-      // folded FiLM affine of this sequence: out = n_hat * G + B,  G = gamma (1 + scale),  B = beta (1 + scale) + shift
       float* sG = sGB + par * 1024;
       float* sB = sG + 512;
-      {
-        const int c = et;
-        float gg = __ldg(gamma + c), bb = __ldg(beta + c);
-        if (scale_shift != nullptr) {
-          const float m1 = 1.0f + __ldg(scale_shift + (size_t)s * ss_stride + c);
-          gg *= m1;
-          bb = fmaf(bb, m1, __ldg(scale_shift + (size_t)s * ss_stride + 512 + c));
-        }
-        sG[c] = gg * hs;
-        sB[c] = bb * hs;
-      }
       named_bar(5, 32 * EPI_WARPS);
       const int qrow0 = r0 + q * 32;
       const bool live = qrow0 < T;       // warp-uniform: this quarter holds at least one valid row
@@ -310,6 +316,9 @@ attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar);
       }
+      // next tile's affine into the other parity buffer: every warp passed this tile's named barrier, i.e. finished the
+      // previous tile, the last reader of that buffer
+      if (tile + (int)gridDim.x < num_tiles) stage_affine(tile + gridDim.x, par ^ 1u);
     }
     if (lane == 0) bulk_wait_g<0>();
   }

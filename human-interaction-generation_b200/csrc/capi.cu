@@ -141,6 +141,11 @@ int hig_debug_trace(unsigned long long* buf, int max_launches) {
   return HIG_OK;
 }
 
+int hig_debug_saturation(unsigned long long* counter) {
+  hig::set_saturation_counter(counter);
+  return HIG_OK;
+}
+
 int hig_recover_joints(const float* x, int S, int T, int C, int init_row, const float* mean, const float* std_,
                        const float* init_mean, const float* init_std, const int* length, int joints_num, float* joints,
                        void* stream) {
@@ -218,6 +223,11 @@ int hig_eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void
                      const int* length, int S, int T, int H, int pair_shift, int dtype, void* stream) {
   return hig::eff_attn_bwd(mode, q, ldq, k, v, ldkv, a_in, dy, lddy, dq, lddq, dk, dv, lddkv, dA, length, S, T, H,
                            pair_shift, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int hig_mha_attention(const void* q, const void* k, const void* v, int ld, void* out, int ldo, int B, int N, int H,
+                      int causal, int dtype, void* stream) {
+  return hig::mha_attention(q, k, v, ld, out, ldo, B, N, H, causal, dtype, static_cast<cudaStream_t>(stream));
 }
 
 int hig_masked_mse(const float* pred, const float* tgt, const int* length, int S, int T, int C, int pit, float* rows,

@@ -15,6 +15,7 @@
 // chunks are XOR-swizzled with row & 7 (conflict-free ldmatrix, plain and transposed), A and dA as [64, 64] bf16.
 // The round-1 kernel did these contractions as per-thread fp32 dot products out of padded fp32 shared memory:
 // 512 us per launch at the C4 shape (S = 256, T = 91) against ~26 us of HBM traffic.
+#include <cstdlib>
 #include <string>
 #include "hig_common.cuh"
 #include "hig_internal.h"
@@ -86,7 +87,9 @@ HIG_DEVICE void frag_b_nk(uint32_t tile, int n0, int kc, int lane, uint32_t (&b)
 }  // namespace tcb
 using namespace tcb;
 
-__global__ void __launch_bounds__(TC_THREADS)
+// MINB: resident CTAs per SM the register allocation aims for (2: 127 registers, no spills; 3: 80 registers, ~350 B spilled)
+template <int MINB>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
 eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k,
                        const __nv_bfloat16* __restrict__ v, int ldkv, const __nv_bfloat16* __restrict__ a_in,
                        const __nv_bfloat16* __restrict__ dy, int lddy, __nv_bfloat16* __restrict__ dq, int lddq,
@@ -245,28 +248,63 @@ eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, c
     }
   }
   if (do_q) {
-    // feature softmax of Q (rows): one warp per row, lane owns columns 2 lane, 2 lane + 1
-    for (int t = warp; t < T; t += TC_WARPS) {
-      const uint32_t addr = sQ + swz_el(t, 2 * lane);
-      const float2 f = unpack_bf16x2(lds32(addr));
-      const float m = warp_max(fmaxf(f.x, f.y));
-      const float e0 = __expf(f.x - m), e1 = __expf(f.y - m);
-      const float inv = 1.0f / warp_sum(e0 + e1);
-      sts32(addr, pack_bf16x2(e0 * inv, e1 * inv));
+    // feature softmax of Q (rows): four lanes per row (16 columns = two 16-byte chunks each), a warp takes 8 rows at a
+    // time; the row maximum / sum are two quad shuffles instead of two full-warp reductions
+    const int qr = lane >> 2, qc = lane & 3;
+    // (warp-uniform trip count: the quad shuffles below are full-mask; rows t >= T are padding rows of the tile — they exist
+    //  in shared memory, hold zeros and are simply not written back)
+    for (int tb = warp * 8; tb < T; tb += TC_WARPS * 8) {
+      const int t = tb + qr;
+      float f[16];
+      uint32_t w[8];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4 * c]), "=r"(w[4 * c + 1]), "=r"(w[4 * c + 2]), "=r"(w[4 * c + 3])
+                     : "r"(sQ + swz(t, 2 * qc + c)));
+      }
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 p = unpack_bf16x2(w[j]);
+        f[2 * j] = p.x;
+        f[2 * j + 1] = p.y;
+        m = fmaxf(m, fmaxf(p.x, p.y));
+      }
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        f[j] = __expf(f[j] - m);
+        sum += f[j];
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(f[2 * j] * inv, f[2 * j + 1] * inv);
+      if (t < T) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sQ + swz(t, 2 * qc + c)), "r"(w[4 * c]), "r"(w[4 * c + 1]),
+                       "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
+      }
     }
   }
   __syncthreads();
 
   // ---------------------------------------------------------------- A = Ks^T V,  dA = Qs^T dY   (64 x 64 each)
-  // warp -> rows d in [dw, dw+16), columns l in [lw, lw+32)
+  // warp -> rows d in [dw, dw+16), columns l in [lw, lw+32).  The column sums the K-side softmax backward needs,
+  //   cs[d] = sum_t dKs[t,d] Ks[t,d] = sum_t Ks[t,d] sum_l V[t,l] dA[d,l] = sum_l dA[d,l] A[d,l],
+  // are row dot products of the two 64 x 64 matrices this phase holds in registers: no per-tile reduction later.
   {
     const int dw = (warp & 3) * 16, lw = (warp >> 2) * 32;
-    if (do_kv && do_q) {
-      float acc[4][4];
+    float accA[4][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < 4; ++j) accA[i][j] = 0.f;
+    if (do_kv) {
       const int kend = (len + 15) & ~15;
       for (int kt = 0; kt < kend; kt += 16) {
         uint32_t a[4], b[4];
@@ -274,17 +312,20 @@ eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, c
 #pragma unroll
         for (int np = 0; np < 2; ++np) {
           frag_b_kn(sV, kt, lw + np * 16, lane, b);
-          mma16816(acc[2 * np], a, b[0], b[1]);
-          mma16816(acc[2 * np + 1], a, b[2], b[3]);
+          mma16816(accA[2 * np], a, b[0], b[1]);
+          mma16816(accA[2 * np + 1], a, b[2], b[3]);
         }
       }
+      if (do_q) {
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int col = lw + nt * 8 + 2 * tg;
-        sts32(sA + swz_el(dw + g, col), pack_bf16x2(acc[nt][0], acc[nt][1]));
-        sts32(sA + swz_el(dw + g + 8, col), pack_bf16x2(acc[nt][2], acc[nt][3]));
+        for (int nt = 0; nt < 4; ++nt) {
+          const int col = lw + nt * 8 + 2 * tg;
+          sts32(sA + swz_el(dw + g, col), pack_bf16x2(accA[nt][0], accA[nt][1]));
+          sts32(sA + swz_el(dw + g + 8, col), pack_bf16x2(accA[nt][2], accA[nt][3]));
+        }
       }
     }
+    uint32_t dAb[4][2];   // bf16 pairs of dA at this thread's fragment positions (rows dw+g / dw+g+8)
     if (do_q) {
       float acc[4][4];
 #pragma unroll
@@ -301,6 +342,11 @@ eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, c
           mma16816(acc[2 * np + 1], a, b[2], b[3]);
         }
       }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        dAb[nt][0] = pack_bf16x2(acc[nt][0], acc[nt][1]);
+        dAb[nt][1] = pack_bf16x2(acc[nt][2], acc[nt][3]);
+      }
       if (mode == 3) {
         float* og = dA_g + ((size_t)s * H + h) * TC_HD * TC_HD;
 #pragma unroll
@@ -313,20 +359,38 @@ eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, c
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int col = lw + nt * 8 + 2 * tg;
-          sts32(sdA + swz_el(dw + g, col), pack_bf16x2(acc[nt][0], acc[nt][1]));
-          sts32(sdA + swz_el(dw + g + 8, col), pack_bf16x2(acc[nt][2], acc[nt][3]));
+          sts32(sdA + swz_el(dw + g, col), dAb[nt][0]);
+          sts32(sdA + swz_el(dw + g + 8, col), dAb[nt][1]);
         }
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int col = lw + nt * 8 + 2 * tg;
+        dAb[nt][0] = lds32(sdA + swz_el(dw + g, col));
+        dAb[nt][1] = lds32(sdA + swz_el(dw + g + 8, col));
+      }
+    }
+    if (do_kv) {
+      float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float2 d0 = unpack_bf16x2(dAb[nt][0]), d1 = unpack_bf16x2(dAb[nt][1]);
+        c0 = fmaf(d0.x, accA[nt][0], fmaf(d0.y, accA[nt][1], c0));
+        c1 = fmaf(d1.x, accA[nt][2], fmaf(d1.y, accA[nt][3], c1));
+      }
+      c0 += __shfl_xor_sync(0xffffffffu, c0, 1); c0 += __shfl_xor_sync(0xffffffffu, c0, 2);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, 1); c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
+      if (tg == 0) {          // the two column halves (warp >> 2) of a row meet in shared memory
+        atomicAdd(&fcs[dw + g], c0);
+        atomicAdd(&fcs[dw + g + 8], c1);
       }
     }
   }
   __syncthreads();
 
   // ---------------------------------------------------------------- per 16-row tile of t (a warp owns its tiles' rows)
-  float dks[2][8][4];
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const int tt = warp + it * TC_WARPS;
-    if (tt >= ntiles) break;
+  for (int tt = warp; tt < ntiles; tt += TC_WARPS) {
     const int t0 = tt * 16;
     if (do_q) {
       // dQs[t, d] = sum_l dY[t, l] A[d, l]
@@ -376,11 +440,11 @@ eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, c
     }
     if (do_kv) {
       // dKs[t, d] = sum_l V[t, l] dA[d, l]       dV[t, l] = sum_d Ks[t, d] dA[d, l]
-      float dvv[8][4];
+      float dks[8][4], dvv[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { dks[it][i][j] = 0.f; dvv[i][j] = 0.f; }
+        for (int j = 0; j < 4; ++j) { dks[i][j] = 0.f; dvv[i][j] = 0.f; }
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
         uint32_t av[4], ak[4], b[4];
@@ -389,55 +453,24 @@ eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, c
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
           frag_b_nk(sdA, np * 16, kc, lane, b);
-          mma16816(dks[it][2 * np], av, b[0], b[1]);
-          mma16816(dks[it][2 * np + 1], av, b[2], b[3]);
+          mma16816(dks[2 * np], av, b[0], b[1]);
+          mma16816(dks[2 * np + 1], av, b[2], b[3]);
           frag_b_kn(sdA, kc * 16, np * 16, lane, b);
           mma16816(dvv[2 * np], ak, b[0], b[1]);
           mma16816(dvv[2 * np + 1], ak, b[2], b[3]);
         }
       }
-      __syncwarp();   // all V fragments of this tile are in registers before its rows become dV
-      float cs[16];
+      __syncwarp();   // all K / V fragments of this tile are in registers before its rows become dK / dV
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int col = nt * 8 + 2 * tg;
         sts32(sV + swz_el(t0 + g, col), pack_bf16x2(dvv[nt][0], dvv[nt][1]));
         sts32(sV + swz_el(t0 + g + 8, col), pack_bf16x2(dvv[nt][2], dvv[nt][3]));
-        const float2 k0 = unpack_bf16x2(lds32(sK + swz_el(t0 + g, col)));
-        const float2 k1 = unpack_bf16x2(lds32(sK + swz_el(t0 + g + 8, col)));
-        cs[2 * nt] = fmaf(dks[it][nt][0], k0.x, dks[it][nt][2] * k1.x);
-        cs[2 * nt + 1] = fmaf(dks[it][nt][1], k0.y, dks[it][nt][3] * k1.y);
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 4);
-        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
-        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
-      }
-      if (g == 0) {
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          atomicAdd(&fcs[nt * 8 + 2 * tg], cs[2 * nt]);
-          atomicAdd(&fcs[nt * 8 + 2 * tg + 1], cs[2 * nt + 1]);
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (do_kv) {
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int tt = warp + it * TC_WARPS;
-      if (tt >= ntiles) break;
-      const int t0 = tt * 16;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = nt * 8 + 2 * tg;
         const float c0 = fcs[col], c1 = fcs[col + 1];
         const uint32_t a0 = sK + swz_el(t0 + g, col), a1 = sK + swz_el(t0 + g + 8, col);
         const float2 k0 = unpack_bf16x2(lds32(a0)), k1 = unpack_bf16x2(lds32(a1));
-        sts32(a0, pack_bf16x2(k0.x * (dks[it][nt][0] - c0), k0.y * (dks[it][nt][1] - c1)));
-        sts32(a1, pack_bf16x2(k1.x * (dks[it][nt][2] - c0), k1.y * (dks[it][nt][3] - c1)));
+        sts32(a0, pack_bf16x2(k0.x * (dks[nt][0] - c0), k0.y * (dks[nt][1] - c1)));
+        sts32(a1, pack_bf16x2(k1.x * (dks[nt][2] - c0), k1.y * (dks[nt][3] - c1)));
       }
     }
   }
@@ -481,12 +514,16 @@ int eff_attn_bwd_tc(int mode, const void* q, int ldq, const void* k, const void*
   const size_t smem = (size_t)((do_kv ? 2 : 0) + (do_q ? 2 : 0)) * TP * 128 + 2 * TC_HD * 128 + (TC_WARPS * 64 + 128) * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(eff_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(eff_attn_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(eff_attn_bwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("eff_attn_bwd_tc attr: ") + cudaGetErrorString(e));
     configured = smem;
   }
   using bf = __nv_bfloat16;
-  eff_attn_bwd_tc_kernel<<<dim3(H, S), TC_THREADS, smem, stream>>>(
+  // three CTAs per SM when their shared memory fits (T <= 96 at 4 tiles): HIG_ATTN_BWD_OCC=2 keeps the 127-register build
+  static const int occ = []() { const char* ev = getenv("HIG_ATTN_BWD_OCC"); return ev ? atoi(ev) : 3; }();
+  auto kern = (occ >= 3 && smem * 3 <= 227 * 1024) ? eff_attn_bwd_tc_kernel<3> : eff_attn_bwd_tc_kernel<2>;
+  kern<<<dim3(H, S), TC_THREADS, smem, stream>>>(
       mode, (const bf*)q, ldq, (const bf*)k, (const bf*)v, ldkv, (const bf*)a_in, (const bf*)dy, lddy, (bf*)dq, lddq,
       (bf*)dk, (bf*)dv, lddkv, dA, length, S, T, pair_shift);
   cudaError_t e = cudaGetLastError();

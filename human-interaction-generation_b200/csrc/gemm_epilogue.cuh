@@ -205,7 +205,9 @@ HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const EpiLane& L, uint32
         if (w32) {
           float* o = L.o32 + (size_t)(4 * i) * ep.ldo_f32 + col0;
           if (KIND == EPI_GENERIC && ep.atomic) {
-            atomicAdd(o, v[i].x); atomicAdd(o + 1, v[i].y); atomicAdd(o + 2, v[i].z); atomicAdd(o + 3, v[i].w);
+            // one 16-byte vector reduction instead of four scalar atomics (split-K weight gradients)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[i].x), "f"(v[i].y), "f"(v[i].z),
+                         "f"(v[i].w) : "memory");
           } else {
             *reinterpret_cast<float4*>(o) = v[i];
           }

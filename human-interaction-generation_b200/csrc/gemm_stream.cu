@@ -58,6 +58,8 @@ struct StreamEpi {
   float* stats_out;        // [M, 8] or null ST_RES_H
   float inv_width;         // 1 / (LayerNorm width)
   float ln_eps;
+  unsigned long long* sat_count;   // debug (hig_debug_saturation): counts fp16 stream stores that hit +-65504; normally null
+  int gelu_erf;            // ST_BF16_GELU: 1 = erf-form GELU (|err| <= 1.5e-7 vs torch's exact GELU), 0 = tanh form (<= 5e-4)
 };
 
 HIG_DEVICE void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
@@ -118,8 +120,13 @@ HIG_DEVICE void stream_chunk(const uint32_t (&r)[32], uint32_t slab_row, int cb,
       for (int i = 0; i < 8; ++i) v[i] += bb[i];
     }
     if (KIND == ST_BF16_GELU) {
+      if (ep.gelu_erf) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = gelu_fast_f(v[i]);
+        for (int i = 0; i < 8; ++i) v[i] = gelu_as_f(v[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gelu_fast_f(v[i]);
+      }
     }
     if (KIND == ST_RES_H) {
       const uint4 h = ld_shared_u4(addr);
@@ -128,6 +135,12 @@ HIG_DEVICE void stream_chunk(const uint32_t (&r)[32], uint32_t slab_row, int cb,
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
       st_shared_u4(addr, pack_h2_sat(v[0], v[1]), pack_h2_sat(v[2], v[3]), pack_h2_sat(v[4], v[5]), pack_h2_sat(v[6], v[7]));
+      if (ep.sat_count != nullptr) {
+        int n = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) n += fabsf(v[i]) > 65504.f;
+        if (n) atomicAdd(ep.sat_count, (unsigned long long)n);
+      }
     } else {
       st_shared_u4(addr, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
@@ -493,8 +506,17 @@ HIG_DEVICE void wres_chunk(const uint32_t (&r)[32], const uint32_t (&res)[32], u
       for (int i = 0; i < 4; ++i) v[i] = f2_add(v[i], bb[i]);
     }
     if (KIND == ST_BF16_GELU) {
+      if (ep.gelu_erf) {      // warp-uniform: exact-GELU semantics (FFN.forward :257/:262) at ~2x the epilogue instructions
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = f2_gelu(v[i]);
+        for (int i = 0; i < 4; ++i) {
+          float a, b;
+          f2_unpack(v[i], a, b);
+          v[i] = f2_pack(gelu_as_f(a), gelu_as_f(b));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = f2_gelu(v[i]);
+      }
     }
     const uint32_t addr = sub_row + ((g ^ sw2) << 4);
     float lo[4], hi[4];
@@ -508,6 +530,12 @@ HIG_DEVICE void wres_chunk(const uint32_t (&r)[32], const uint32_t (&res)[32], u
         f2_unpack(v[i], lo[i], hi[i]);
       }
       st_shared_u4(addr, pack_h2_sat(lo[0], hi[0]), pack_h2_sat(lo[1], hi[1]), pack_h2_sat(lo[2], hi[2]), pack_h2_sat(lo[3], hi[3]));
+      if (ep.sat_count != nullptr) {     // debug only (hig_debug_saturation): a saturating store would otherwise be silent
+        int n = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) n += (fabsf(lo[i]) > 65504.f) + (fabsf(hi[i]) > 65504.f);
+        if (n) atomicAdd(ep.sat_count, (unsigned long long)n);
+      }
     } else if (KIND == ST_F16) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) f2_unpack(v[i], lo[i], hi[i]);
@@ -799,6 +827,14 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// debug: device counter of saturating fp16 stream stores (hig_debug_saturation); null = off
+static unsigned long long* g_sat_count = nullptr;
+void set_saturation_counter(unsigned long long* p) { g_sat_count = p; }
+static bool gelu_erf_enabled() {
+  const char* e = getenv("HIG_GELU");
+  return e && (e[0] == 'e' || e[0] == 'E');
+}
+
 // debug: set through hig_debug_trace(buf, max_launches); every traced launch takes the next block of 74 * 32 slots
 static unsigned long long* g_trace = nullptr;
 static int g_trace_left = 0;
@@ -892,6 +928,8 @@ int gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op
   ep.bias = bias; ep.wsum = wsum; ep.stats_in = stats_in; ep.stats_out = stats_out;
   ep.inv_width = ln_width > 0 ? 1.0f / (float)ln_width : 0.f;
   ep.ln_eps = 1e-5f;
+  ep.sat_count = g_sat_count;
+  ep.gelu_erf = gelu_erf_enabled() ? 1 : 0;      // read per call: HIG_GELU=erf / tanh (default) can be A/B-toggled
   const int f16 = op_dtype == HIG_F16;
   const int tm_f16 = f16;
   CUtensorMap tmA, tmB, tmC;

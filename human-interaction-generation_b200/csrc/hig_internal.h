@@ -48,6 +48,7 @@ int gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op
                 void* out, int ldo, cudaStream_t stream);
 
 void set_gemm_trace(unsigned long long* buf, int max_launches);
+void set_saturation_counter(unsigned long long* counter);
 
 int row_stats(const void* x, int x_dtype, int rows, int width, float* stats, cudaStream_t stream);
 
@@ -122,6 +123,10 @@ int ln_film_silu_bwd(const void* x, int x_dtype, int rows, int width, int rows_p
 int eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
                  const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
                  const int* length, int S, int T, int H, int pair_shift, int dtype, cudaStream_t stream);
+
+// ---- text conditioning path (text_ops.cu) ----
+int mha_attention(const void* q, const void* k, const void* v, int ld, void* out, int ldo, int B, int N, int H, int causal,
+                  int dtype, cudaStream_t stream);
 
 // ---- training step around the denoiser (train_ops.cu) ----
 int masked_mse(const float* pred, const float* tgt, const int* length, int S, int T, int C, int pit, float* rows, float* w,

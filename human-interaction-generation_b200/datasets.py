@@ -79,3 +79,43 @@ def build_dataloader(dataset, rank, world_size, samples_per_gpu, drop_last=True,
     return data.DataLoader(dataset, batch_size=samples_per_gpu, sampler=sampler, num_workers=workers_per_gpu,
                            pin_memory=torch.cuda.is_available(), shuffle=shuffle, drop_last=drop_last,
                            persistent_workers=workers_per_gpu > 0)
+
+
+class DevicePrefetcher:
+    """Iterates a loader one batch ahead of the training step: the two motion tensors and the lengths of batch i+1 travel
+    host -> device on a side stream (pinned memory, asynchronous DMA) while batch i trains, so the copy (24 MB at the C4
+    batch) never sits between two iterations' kernels.  Captions stay on the host (strings / small id tensors)."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.sampler = getattr(loader, "sampler", None)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _stage(self, it):
+        try:
+            batch = next(it)
+        except StopIteration:
+            return None
+        c1, c2, m1, m2, lens, fid = batch
+        with torch.cuda.stream(self.stream):
+            m1 = torch.as_tensor(m1).to(self.device, non_blocking=True)
+            m2 = torch.as_tensor(m2).to(self.device, non_blocking=True)
+            lens = torch.as_tensor(lens).to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return (c1, c2, m1, m2, lens, fid), ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        nxt = self._stage(it)
+        while nxt is not None:
+            batch, ev = nxt
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            for t in batch[2:5]:
+                t.record_stream(cur)
+            nxt = self._stage(it)
+            yield batch

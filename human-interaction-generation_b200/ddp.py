@@ -282,7 +282,7 @@ def gather_indexed(local, indices, n_pairs, dim_pose, group=None, dst=0):
     return out
 
 
-def generate_bucketed(trainer, caption1, caption2, m_lens, dim_pose, batch_size=512, group=None, dst=0):
+def generate_bucketed(trainer, caption1, caption2, m_lens, dim_pose, batch_size=512, group=None, dst=0, pair_noise=None):
     """Length-bucketed, rank-sharded `DDPMMulTrainer.generate`: same arguments, returns (on `dst`; everywhere when
     torch.distributed is not initialised) the list of [motion1, motion2] in the callers' order, each trimmed to its own
     length — what the evaluator keeps anyway (datasets/evaluator.py:94-97)."""
@@ -296,7 +296,8 @@ def generate_bucketed(trainer, caption1, caption2, m_lens, dim_pose, batch_size=
     local, indices = [], []
     for T_b, idx in plan[rank]:
         ml = lens[idx]
-        out = trainer.generate_batch([caption1[i] for i in idx], [caption2[i] for i in idx], ml, dim_pose)
+        out = trainer.generate_batch([caption1[i] for i in idx], [caption2[i] for i in idx], ml, dim_pose,
+                                     pair_noise=None if pair_noise is None else pair_noise[idx])
         B = len(idx)
         for k, i in enumerate(idx):
             n = max(1, min(int(ml[k]), out.shape[1]))

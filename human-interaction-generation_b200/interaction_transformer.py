@@ -141,17 +141,35 @@ class MotionInteractionTransformer(nn.Module):
         the FROZEN CLIP features of a caption are cached across calls (invalidated when a CLIP parameter changes)."""
         text = list(text)
         uniq = list(dict.fromkeys(text))
-        feats = self._clip_features(uniq, device)               # [77, U, 512]
-        x = self.text_pre_proj(feats)
-        xf_out = self.text_ln(self.textTransEncoder(x))
-        eot = self._eot_index(uniq, device)
-        xf_proj = self.text_proj(xf_out[eot, torch.arange(xf_out.shape[1], device=device)])
-        xf_out = xf_out.permute(1, 0, 2)
+        if self._text_on_kernels(device):
+            # no-grad paths (sampling, evaluation): the whole text stack on the library's kernels (text_engine.py)
+            feats = self._clip_features(uniq, device)           # [77, U, 512], frozen CLIP cached per caption
+            eot = self._eot_index(uniq, device)
+            xf_proj, xf_out = self.text_engine().encode(feats.permute(1, 0, 2).contiguous(), eot)
+        else:
+            feats = self._clip_features(uniq, device)           # [77, U, 512]
+            x = self.text_pre_proj(feats)
+            xf_out = self.text_ln(self.textTransEncoder(x))
+            eot = self._eot_index(uniq, device)
+            xf_proj = self.text_proj(xf_out[eot, torch.arange(xf_out.shape[1], device=device)])
+            xf_out = xf_out.permute(1, 0, 2)
         if len(uniq) != len(text):
             where = {c: i for i, c in enumerate(uniq)}
             idx = torch.tensor([where[c] for c in text], device=device, dtype=torch.long)
             xf_proj, xf_out = xf_proj.index_select(0, idx), xf_out.index_select(0, idx)
         return xf_proj, xf_out
+
+    def text_engine(self):
+        eng = getattr(self, "_text_engine", None)
+        if eng is None:
+            from .text_engine import TextEncoderEngine
+            eng = self._text_engine = TextEncoderEngine(self)
+        return eng
+
+    def _text_on_kernels(self, device):
+        import os
+        return (not torch.is_grad_enabled()) and torch.device(device).type == "cuda" and \
+            os.environ.get("HIG_TEXT_ENGINE", "1") != "0" and self.text_latent_dim in (256, 512)
 
     def _eot_index(self, captions, device):
         return self._tokenize(captions, truncate=True).to(device).argmax(dim=-1)
@@ -162,6 +180,8 @@ class MotionInteractionTransformer(nn.Module):
 
         def run(caps):
             tokens = self._tokenize(caps, truncate=True).to(device)
+            if self._text_on_kernels(device):
+                return self.text_engine().clip_features(tokens).permute(1, 0, 2)      # LND like the reference
             dt = self._clip_dtype
             x = clip.token_embedding(tokens).type(dt)
             x = x + clip.positional_embedding.type(dt)

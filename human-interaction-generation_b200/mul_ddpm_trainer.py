@@ -72,10 +72,15 @@ class DDPMMulTrainer(object):
             opt.step()
 
     # ------------------------------------------------------------------------------------------ sampling (:164-221)
-    def generate_batch(self, caption1, caption2, m_lens, dim_pose, noise=None, noise_seq=None):
+    def generate_batch(self, caption1, caption2, m_lens, dim_pose, noise=None, noise_seq=None, pair_noise=None):
+        """pair_noise ([pairs, 2, >= T, dim_pose], optional): x_T given PER PAIR (rows beyond the batch's T are dropped) instead
+        of one th.randn over the padded batch (:176,192) — makes a pair's sample independent of how pairs are batched."""
         net = self._net()
         m_lens = torch.cat([m_lens, m_lens], dim=0)
         T = int(min(int(m_lens.max()), net.num_frames))
+        if pair_noise is not None:
+            pn = pair_noise.to(self.device)
+            noise = torch.cat([pn[:, 0, :T], pn[:, 1, :T]], dim=0).contiguous()
         if self.cap_id:
             kw = {"text": [torch.as_tensor(caption1).reshape(-1), torch.as_tensor(caption2).reshape(-1)],
                   "length": m_lens}
@@ -89,7 +94,7 @@ class DDPMMulTrainer(object):
         return self.diffusion.p_sample_loop(self.encoder, (B, T, dim_pose), noise=noise, clip_denoised=False,
                                             progress=False, model_kwargs=kw, noise_seq=noise_seq)
 
-    def generate(self, caption1, caption2, m_lens, dim_pose, batch_size=512, reference_chunk_bug=False):
+    def generate(self, caption1, caption2, m_lens, dim_pose, batch_size=512, reference_chunk_bug=False, pair_noise=None):
         N = len(caption1)
         self.encoder.eval()
         all_output = []
@@ -97,7 +102,8 @@ class DDPMMulTrainer(object):
             hi = min(lo + batch_size, N)
             c1 = caption1[lo:hi]
             c2 = caption1[lo:hi] if (reference_chunk_bug and hi < N) else caption2[lo:hi]
-            output = self.generate_batch(c1, c2, m_lens[lo:hi], dim_pose)
+            output = self.generate_batch(c1, c2, m_lens[lo:hi], dim_pose,
+                                         pair_noise=None if pair_noise is None else pair_noise[lo:hi])
             B = hi - lo
             all_output.extend([output[i], output[B + i]] for i in range(B))
         return all_output
@@ -208,7 +214,7 @@ class DDPMMulTrainer(object):
         """The reference's epoch loop (:289-341).  The optimizer is the flat fused Adam (same hyper-parameters and the same
         state_dict format as `optim.Adam(self.encoder.parameters(), lr=self.opt.lr)`); losses are accumulated on the device
         and read back every `log_every` iterations only."""
-        from .datasets import build_dataloader
+        from .datasets import DevicePrefetcher, build_dataloader
         from .optim import FusedAdam
         opt = self.opt
         self.to(self.device)
@@ -220,6 +226,8 @@ class DDPMMulTrainer(object):
         loader = train_dataset if hasattr(train_dataset, "__iter__") and not hasattr(train_dataset, "__getitem__") else \
             build_dataloader(train_dataset, rank, world_size, samples_per_gpu=opt.batch_size, drop_last=True,
                              workers_per_gpu=getattr(opt, "workers_per_gpu", 4), shuffle=True)
+        if torch.device(self.device).type == "cuda":
+            loader = DevicePrefetcher(loader, self.device)      # host -> device copies of batch i+1 overlap iteration i
         log_path = getattr(opt, "log_file", None) or os.path.join(getattr(opt, "model_dir", "."), "train_log.jsonl")
         max_iters = getattr(opt, "max_iters", None)
         acc, n_acc = None, 0

@@ -7,7 +7,7 @@ import torch
 from . import _lib
 
 BF16, F32, F16 = 0, 1, 2
-ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_SILU, ACT_QUICKGELU = 0, 1, 2, 3
 ATTN_SELF, ATTN_INTER, ATTN_KV_ONLY, ATTN_Q_ONLY = 0, 1, 2, 3
 
 
@@ -314,6 +314,14 @@ def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, out=None):
     return out
 
 
+def debug_saturation(counter):
+    """counter: int64 / uint64 device scalar that counts saturating fp16 stream stores (None switches the counter off)."""
+    lib = _lib.load()
+    if counter is not None and (not counter.is_cuda or counter.element_size() != 8):
+        raise ValueError("hig_b200.debug_saturation: an 8-byte CUDA scalar is required")
+    _lib.check(lib.hig_debug_saturation(_ptr(counter)), "hig_debug_saturation")
+
+
 def l2_persist(t, hit_ratio=1.0):
     """Pin tensor `t` in L2 for kernels launched/captured on the current stream (None clears the window)."""
     lib = _lib.load()
@@ -439,6 +447,18 @@ def eff_attn_bwd(mode, S, T, H, q=None, k=None, v=None, a_in=None, dy=None, dq=N
                               _ptr(dk), _ptr(dv), dk.stride(0) if dk is not None else 0, _ptr(dA), _ptr(length), S, T,
                               H, pair_shift, _dt(ref), _stream())
     _lib.check(rc, "hig_eff_attn_bwd")
+
+
+def mha_attention(qkv, out, B, N, H, causal=False):
+    """Softmax MHA over rows [B*N, 3*H*64] laid out (q | k | v); out [B*N, H*64].  bf16 or fp32 storage."""
+    lib = _lib.load()
+    D = H * 64
+    if qkv.shape != (B * N, 3 * D) or out.shape != (B * N, D) or qkv.dtype != out.dtype:
+        raise ValueError("hig_b200.mha_attention: qkv [B*N, 3*H*64], out [B*N, H*64] of one dtype")
+    rc = lib.hig_mha_attention(_ptr(qkv[:, :D]), _ptr(qkv[:, D:2 * D]), _ptr(qkv[:, 2 * D:]), _rowmajor(qkv, "qkv"), _ptr(out),
+                               _rowmajor(out, "out"), B, N, H, 1 if causal else 0, _dt(qkv), _stream())
+    _lib.check(rc, "hig_mha_attention")
+    return out
 
 
 def masked_mse(pred, target, length, pit=False, want_grad=True):

@@ -25,17 +25,16 @@ class FusedAdam(torch.optim.Adam):
         self.exp_avg_sq = torch.zeros_like(self.fp.param)
         self.gnorm2 = torch.zeros((), device=dev, dtype=torch.float64)
         self.step_count = 0
-        self._n_den = len(self.fp.names) - len(self.fp.other_names)
-        self._others = [named[n] for n in self.fp.other_names]
+        self._n_den = self.fp.n_den_params
+        self._others = self.fp.params[self._n_den:]
         self._other_gviews = [self.fp.gviews[n] for n in self.fp.other_names]
         self._attach()
 
     def _attach(self):
         """Denoiser gradients are written in place by the backward graphs: expose them as persistent p.grad views."""
         self.fp.direct = True
-        named = dict(self.net.named_parameters())
-        for n in self.fp.names[:self._n_den]:
-            named[n].grad = self.fp.gviews[n]
+        for n, p in zip(self.fp.names[:self._n_den], self.fp.params):
+            p.grad = self.fp.gviews[n]
 
     def _check_layout(self):
         fp = flat_params(self.net)
@@ -51,8 +50,7 @@ class FusedAdam(torch.optim.Adam):
                 p.grad = None
             elif p.grad is not None:
                 p.grad.zero_()
-        named = dict(self.net.named_parameters())
-        first = named[self.fp.names[0]]
+        first = self.fp.params[0]
         if first.grad is None or first.grad.data_ptr() != self.fp.gviews[self.fp.names[0]].data_ptr():
             self._attach()
 

@@ -71,6 +71,9 @@ class FlatParams:
                 v.copy_(p.data)
                 p.data = v
         self.gviews = {n: self._view(self.grad, n) for n in self.names}
+        self.params = [named[n] for n in self.names]          # the Parameter objects, in flat order (identity is stable)
+        self.n_den_params = len(den)
+        self._all_trainable = [p for p in module.parameters() if p.requires_grad]
         self._mirror_key = None
         self.direct = False          # True: gradients are exposed as persistent p.grad views (FusedAdam path)
 
@@ -93,18 +96,19 @@ class FlatParams:
         return flat[o:o + count].view(shape)
 
     def owns(self, module):
-        named = dict(module.named_parameters())
-        for n in (self.names[0], self.names[-1]):
-            p = named.get(n)
-            if p is None or p.data_ptr() != self.param.data_ptr() + 4 * self.offsets[n] or tuple(p.shape) != self.shapes[n]:
+        """True while the module's parameters are still the views this object created (a later .to() / .cuda() / re-creation
+        of a parameter breaks that)."""
+        base = self.param.data_ptr()
+        for i in (0, self.n_den_params - 1, len(self.names) - 1):
+            n, p = self.names[i], self.params[i]
+            if p.data_ptr() != base + 4 * self.offsets[n] or tuple(p.shape) != self.shapes[n]:
                 return False
-        return True
+        return getattr(module, "_hig_flat", None) is self
 
     def refresh_mirror(self, module, force=False):
         """bf16 operand mirror <- fp32 parameters (one cast kernel) when a parameter changed behind our back (a third-party
         optimizer, load_state_dict, ...).  hig_adam_flat writes the mirror itself and calls mark_mirror_fresh()."""
-        key = (getattr(module, "_hig_param_generation", 0),
-               sum(p._version for p in module.parameters() if p.requires_grad))
+        key = (getattr(module, "_hig_param_generation", 0), sum(p._version for p in self._all_trainable))
         if force or key != self._mirror_key:
             ops.act_fwd(self.param[:self.n_den], ops.ACT_NONE, self.mirror)
             self._mirror_key = key
@@ -113,8 +117,7 @@ class FlatParams:
 
     def mark_mirror_fresh(self, module):
         module._hig_param_generation = getattr(module, "_hig_param_generation", 0) + 1
-        self._mirror_key = (module._hig_param_generation,
-                            sum(p._version for p in module.parameters() if p.requires_grad))
+        self._mirror_key = (module._hig_param_generation, sum(p._version for p in self._all_trainable))
 
 
 def flat_params(module):
@@ -574,15 +577,14 @@ class DenoiserGraphFn(torch.autograd.Function):
     def backward(ctx, d_eps):
         plan, te = ctx.plan, ctx.te
         fp, module = te.fp, te.module
-        named = dict(module.named_parameters())
-        first = named[fp.names[0]]
+        first = fp.params[0]
         # a p.grad that aliases the flat gradient buffer (left by a previous backward) would be doubled by autograd's
         # in-place accumulation: preserve accumulate semantics explicitly
         carry = None
         if not fp.direct and first.grad is not None and first.grad.data_ptr() == fp.gviews[fp.names[0]].data_ptr():
             carry = fp.grad[:fp.n_den].clone()
-            for n in fp.names[:len(fp.names) - len(fp.other_names)]:
-                named[n].grad = None
+            for p in fp.params[:fp.n_den_params]:
+                p.grad = None
         plan.d_eps.copy_(d_eps.detach())
         hook = getattr(module, "_grad_segment_hook", None)
 
@@ -598,7 +600,7 @@ class DenoiserGraphFn(torch.autograd.Function):
         if carry is not None:
             fp.grad[:fp.n_den].add_(carry)
         ctx.plan = None
-        n_den = len(fp.names) - len(fp.other_names)
+        n_den = fp.n_den_params
         if fp.direct:
             grads = [None] * n_den
         else:
@@ -610,8 +612,6 @@ def denoiser_forward_graph(module, x, timesteps, length, xf_proj, xf_out):
     if not x.is_cuda:
         raise RuntimeError("hig_b200: the denoiser runs on CUDA only (no CPU fallback)")
     fp = flat_params(module)
-    named = dict(module.named_parameters())
-    n_den = len(fp.names) - len(fp.other_names)
-    params = [named[n] for n in fp.names[:n_den]]
+    params = fp.params[:fp.n_den_params]
     ln = torch.as_tensor(length).reshape(-1)
     return DenoiserGraphFn.apply(module, x.float(), timesteps, ln, xf_proj.float(), xf_out.float(), *params).to(x.dtype)

@@ -28,6 +28,7 @@ extern "C" {
 #define HIG_ACT_NONE 0
 #define HIG_ACT_GELU 1 /* exact erf GELU, nn.GELU() */
 #define HIG_ACT_SILU 2
+#define HIG_ACT_QUICKGELU 3 /* x sigmoid(1.702 x): CLIP text transformer MLP (hig_act_fwd only) */
 
 #define HIG_ATTN_SELF 0    /* LinearTemporalSelfAttention              models/interaction_transformer.py:112-130 */
 #define HIG_ATTN_INTER 1   /* LinearTemporalInteractionCrossAttention  models/interaction_transformer.py:181-207 */
@@ -45,6 +46,12 @@ unsigned long long hig_launch_count(void);
  * max_launches launches (buf holds max_launches * 74 * 32 entries) — tile-by-tile timeline read by tools/gemm_trace.py;
  * NULL or max_launches <= 0 disables. */
 int hig_debug_trace(unsigned long long* buf, int max_launches);
+
+/* Debug aid (no reference counterpart): while `counter` (a device unsigned long long) is non-NULL, every fp16 residual-stream
+ * store of hig_gemm_stream (HIG_GS_RES_H) whose fp32 value exceeds +-65504 — i.e. that the saturating conversion clamps —
+ * adds 1 to *counter.  The reference's stream is fp32 (models/interaction_transformer.py:129,164,203,263): a non-zero count
+ * means this checkpoint does not fit the fp16 stream and `precision="fp32"` must be used.  NULL disables (default). */
+int hig_debug_saturation(unsigned long long* counter);
 
 /* L2 residency hint (no reference counterpart): pins [ptr, ptr+bytes) — the fp32 residual stream — in the 126 MB L2
  * through an access-policy window on `stream`; ptr == NULL clears it. */
@@ -241,6 +248,13 @@ int hig_ln_film_silu_bwd(const void* x, int x_dtype, int rows, int width, int ro
 int hig_eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
                      const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
                      const int* length, int S, int T, int H, int pair_shift, int dtype, void* stream);
+
+/* Softmax multi-head attention of the text transformers in MotionInteractionTransformer.encode_text
+ * (models/interaction_transformer.py:533-559: CLIP's causal 8-head text transformer, and the 4-head nn.TransformerEncoder of
+ * :446-455): out[b,i,h,:] = softmax_j(q_i . k_j / 8 (+ causal mask)) v_j, head dim 64, rows [B*N, ld] with q/k/v pointing at
+ * head 0 of their blocks, N <= 128 tokens, storage dtype bf16 or fp32 (fp32 arithmetic). */
+int hig_mha_attention(const void* q, const void* k, const void* v, int ld, void* out, int ldo, int B, int N, int H,
+                      int causal, int dtype, void* stream);
 
 /* The reference's training loss and its gradient — DDPMMulTrainer.backward_G, trainers/mul_ddpm_trainer.py:223-247:
  * per frame the mean over features of (pred - tgt)^2 (frame 0: its first 4 features only; frames >= 1: all C), weighted by

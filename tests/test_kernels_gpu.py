@@ -687,3 +687,53 @@ def test_launch_counter(cuda):
     a = torch.randn(128, 64, device=cuda).bfloat16()
     ops.gemm(a, a)
     assert _lib.launch_count() == before + 1
+
+
+# ------------------------------------------------------------------------------------------------ text path
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,N,H,causal", [(3, 77, 8, True), (5, 77, 4, False), (2, 1, 4, False), (1, 128, 2, True)])
+def test_mha_attention_matches_torch(cuda, B, N, H, causal, dtype):
+    ops = _ops()
+    D = H * 64
+    g = torch.Generator(device=cuda).manual_seed(B * 100 + N)
+    qkv = torch.randn(B * N, 3 * D, device=cuda, generator=g).to(dtype)
+    out = ops.mha_attention(qkv, torch.empty(B * N, D, device=cuda, dtype=dtype), B, N, H, causal=causal)
+    q, k, v = [qkv[:, i * D:(i + 1) * D].float().view(B, N, H, 64).transpose(1, 2) for i in range(3)]
+    ref = F.scaled_dot_product_attention(q, k, v, is_causal=causal).transpose(1, 2).reshape(B * N, D)
+    assert _rel(out.float(), ref) < (2e-6 if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_encode_text_on_kernels_matches_torch_path(cuda, precision, monkeypatch):
+    """MotionInteractionTransformer.encode_text (:533-559) on the library's kernels (text_engine.py: CLIP-shaped 12-layer
+    causal transformer, text_pre_proj, 4-layer post-norm encoder, text_ln, text_proj) against the PyTorch modules it
+    replaces, on identical (random-init) weights; captions repeat to exercise the de-duplication + cache."""
+    import hig_b200  # noqa: F401
+    from hig_b200.interaction_transformer import MotionInteractionTransformer
+    monkeypatch.setenv("HIG_CLIP_STUB", "1")
+    torch.manual_seed(0)
+    m = MotionInteractionTransformer(263, num_frames=196, num_layers=1, cap_id=False, precision=precision).to(cuda).eval()
+    caps = ["a person pushes the other person", "a person is pushed by the other person", "two people shake hands",
+            "a person pushes the other person", "a person walks towards the other person , slowly", "two people shake hands"]
+    with torch.no_grad():
+        monkeypatch.setenv("HIG_TEXT_ENGINE", "0")
+        p_ref, o_ref = m.encode_text(caps, cuda)
+        m._clip_cache_key = None                      # drop the torch-computed CLIP features
+        monkeypatch.setenv("HIG_TEXT_ENGINE", "1")
+        before = _lib_count()
+        p, o = m.encode_text(caps, cuda)
+        assert _lib_count() - before > 100            # the kernels really ran (12 + 4 layers)
+    assert p.shape == p_ref.shape == (6, 2048) and o.shape == o_ref.shape == (6, 77, 256)
+    tol = 2e-4 if precision == "fp32" else 3e-2
+    assert _rel(o, o_ref) < tol, _rel(o, o_ref)
+    assert _rel(p, p_ref) < tol, _rel(p, p_ref)
+    assert torch.equal(o[0], o[3]) and torch.equal(o[2], o[5])
+    # with autograd on (training), the trainable encoder stays on torch.autograd and receives gradients
+    p2, o2 = m.encode_text(caps[:2], cuda)
+    (p2.sum() + o2.sum()).backward()
+    assert m.textTransEncoder.layers[0].linear1.weight.grad is not None
+
+
+def _lib_count():
+    from hig_b200 import _lib
+    return _lib.launch_count()

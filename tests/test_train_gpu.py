@@ -53,6 +53,23 @@ def test_transpose_copy_colsum(cuda, M, N, in_dt, out_dt):
     assert rel(cs, (x * keep).float().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("in_dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N", [(23296, 512), (1000, 1536), (37, 8), (256, 32768)])
+def test_cast_and_colsum_without_transposition(cuda, M, N, in_dt):
+    """hig_transpose with no transposed output = the vectorised cast (+ column sums) kernel of the training backward."""
+    ops = _ops()
+    x = torch.randn(M, N + 8, device=cuda).to(in_dt)[:, :N]
+    cp = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
+    cs = torch.randn(N, device=cuda)
+    base = cs.clone()
+    ops.transpose(x, copy=cp, colsum=cs)
+    assert torch.equal(cp, x.to(torch.bfloat16))
+    assert rel(cs - base, x.float().sum(0)) < 2e-5
+    cp2 = torch.zeros_like(cp)
+    ops.transpose(x, copy=cp2)
+    assert torch.equal(cp2, cp)
+
+
 def test_colsum(cuda):
     ops = _ops()
     for M, N, dt in [(256, 91 * 512, torch.float32), (4, 1024, torch.float32), (3000, 77, torch.bfloat16)]:
@@ -207,7 +224,7 @@ def test_eff_attn_bwd_self_and_inter(cuda, dtype, S, T, H):
         for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
             if T == 1 and name != "dv":
                 # one key row: Ks == 1, A has identical rows, so dQ and dK are exactly zero analytically
-                assert (d[:, sl].float() - want[:, sl]).abs().max().item() < 1e-5
+                assert (d[:, sl].float() - want[:, sl]).abs().max().item() < 2e-5
                 continue
             e = rel(d[:, sl], want[:, sl])
             assert e < tol, (mode, name, e)
@@ -243,7 +260,7 @@ def test_eff_attn_bwd_text(cuda, dtype, N):
     if N > 1:   # a single token has softmax == 1 and a zero key gradient
         assert rel(dkv[:, :D], kvr.grad[:, :, 0].reshape(S * N, D)) < tol
     else:
-        assert dkv[:, :D].float().abs().max().item() < 1e-6
+        assert dkv[:, :D].float().abs().max().item() < 2e-5     # analytically zero: rounding noise of two summation orders
 
 
 # ------------------------------------------------------------------------------------------------ model level

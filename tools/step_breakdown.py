@@ -58,9 +58,15 @@ def time_graph(label, disabled=()):
 
 
 full = time_graph("full denoiser step")
-for label, dis in [("without GEMMs", ("gemm",)), ("without eff_attn (K/V half)", ("eff_attn",)),
-                   ("without attn_apply_stylize", ("attn_apply_stylize",)), ("without ln_film_silu", ("ln_film_silu",)),
-                   ("only GEMMs", ("eff_attn", "attn_apply_stylize", "ln_film_silu", "timestep_embed"))]:
+# classes of the PRODUCT schedule (DenoiserEngine.layers_stream): every call of a class is replaced by a no-op at capture
+for label, dis in [("without the token-sized projections (hig_gemm_stream)", ("gemm_stream",)),
+                   ("without the general GEMM (FiLM linears, M = S)", ("gemm",)),
+                   ("without the K/V half (attn_kv / eff_attn)", ("attn_kv", "eff_attn")),
+                   ("without attention-apply + stylize", ("attn_apply_stylize", "attn_apply_stylize_tc")),
+                   ("without ln_film_silu (FFN branch)", ("ln_film_silu",)),
+                   ("without time table / tile_rows", ("time_table_silu", "tile_rows", "timestep_embed")),
+                   ("only the projections", ("gemm", "attn_kv", "eff_attn", "attn_apply_stylize", "attn_apply_stylize_tc",
+                                             "ln_film_silu", "time_table_silu", "tile_rows", "timestep_embed"))]:
     tt = time_graph(label, dis)
     print(f"    -> class cost {full - tt:8.1f} us ({100 * (full - tt) / full:4.1f}%)")
 
@@ -83,7 +89,7 @@ def time_fn(label, fn):
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / n * 1e3)
-    print(f"{label:34s} {best:8.1f} us")
+    print(f"{label:46s} {best:8.1f} us")
 
 
 from hig_b200.gaussian_diffusion import GaussianDiffusion, LossType, ModelMeanType, ModelVarType, get_named_beta_schedule  # noqa: E402
@@ -91,18 +97,29 @@ diff = GaussianDiffusion(betas=get_named_beta_schedule("linear", 1000), model_me
                          model_var_type=ModelVarType.FIXED_SMALL, loss_type=LossType.MSE)
 coef = diff._tables(dev)["coef"]
 W = eng.packed()
-time_fn("embed (time MLP + 32 FiLM linears)", lambda: eng.embed(ws, t, xf_proj, S))
-time_fn("embed_motion", lambda: eng.embed_motion(ws, T))
-time_fn("heads (out / out2)", lambda: eng.heads(ws, S, T))
-time_fn("ddpm_step + pack + t--", lambda: ops.ddpm_step(x, ws["eps16"] if eng.heads16 else ws["eps"], t, coef, noise=None, seed=1, packed=ws["xa"], t_next=None))
 D = 512
-qkv = ws["qkv"]
-time_fn("1 x qkv GEMM", lambda: eng._gemm(ws["n"], W["l0.sa.qkv.w"], W["l0.sa.qkv.b"], out=qkv))
-time_fn("1 x q GEMM", lambda: eng._gemm(ws["n"], W["l0.ca.q.w"], W["l0.ca.q.b"], out=qkv.view(-1)[:S * T * D].view(S * T, D)))
-time_fn("1 x ffn1 GEMM (+GELU)", lambda: eng._gemm(ws["xb"], W["l0.ffn.w1"], W["l0.ffn.b1"], out=ws["g"], act=ops.ACT_GELU))
-time_fn("1 x ffn2 GEMM", lambda: eng._gemm(ws["g"], W["l0.ffn.w2"], W["l0.ffn.b2"], out=ws["y"]))
-time_fn("1 x out-proj GEMM (res fp16)", lambda: eng._project(ws, W, "l0.sa", False))
-time_fn("1 x out-proj GEMM (res fp16 + xb)", lambda: eng._project(ws, W, "l0.ffn", True))
-time_fn("1 x pre-LN (fp16 -> bf16)", lambda: ops.ln_film_silu(ws["xres"], W["l0.sa.ln.w"], W["l0.sa.ln.b"], ws["n"]))
-time_fn("1 x attn K/V half", lambda: ops.eff_attn(ops.ATTN_KV_ONLY, S, T, 8, k=qkv[:, D:2 * D], v=qkv[:, 2 * D:], a_out=ws["a_blk"], length=ws["len"]))
-time_fn("1 x attn apply + stylize", lambda: eng._attend(ws, W, "l0.ca", S, T, qkv[:, :D], a_in=ws["a_blk"]))
+tok = S * T
+qkv, xres, sact, stats = ws["qkv"], ws["xres"], ws["sact"], ws["stats"]
+q_ca = qkv.view(-1)[:tok * D].view(tok, D)
+gs = ops.gemm_stream
+ln_kind = ops.GS_LN_QSM if eng.qsm else ops.GS_LN_BF16
+# single kernels of the product path, replayed back to back (operands stay L2-warm: compare with the in-graph classes above)
+time_fn("embed (time MLP + 32 FiLM linears)", lambda: eng.embed(ws, t, xf_proj, S))
+time_fn("embed_motion (tile_rows + in-place projection)", lambda: eng.embed_motion(ws, T))
+time_fn("heads (out / out2, fp16 eps)", lambda: eng.heads(ws, S, T))
+time_fn("ddpm_step + pack + t--", lambda: ops.ddpm_step(x, ws["eps16"] if eng.heads16 else ws["eps"], t, coef, noise=None, seed=1,
+                                                        packed=ws["xa"], t_next=None))
+time_fn("Q|K|V projection (LN folded, query softmax)", lambda: gs(ln_kind, xres, W["l0.sa.qkv.wg"], W["l0.sa.qkv.bg"], qkv,
+                                                                  wsum=W["l0.sa.qkv.wsum"], stats_in=stats, ln_width=D))
+time_fn("Q projection (text CA)", lambda: gs(ln_kind, xres, W["l0.ca.q.wg"], W["l0.ca.q.bg"], q_ca, wsum=W["l0.ca.q.wsum"],
+                                             stats_in=stats, ln_width=D))
+time_fn("out-projection + fp16 residual + row stats", lambda: gs(ops.GS_RES_H, sact, W["l0.sa.po.w"], W["l0.sa.po.b"], xres,
+                                                                 stats_out=stats))
+time_fn("FFN linear1 + GELU", lambda: gs(ops.GS_BF16_GELU, xres, W["l0.ffn.w1h"], W["l0.ffn.b1"], ws["g"]))
+time_fn("FFN linear2 (streamed, K = 1024)", lambda: gs(ops.GS_BF16, ws["g"], W["l0.ffn.w2"], W["l0.ffn.b2"], ws["y"]))
+time_fn("FFN LayerNorm + FiLM + SiLU", lambda: ops.ln_film_silu(ws["y"], W["l0.ffn.po.ln.w"], W["l0.ffn.po.ln.b"], sact, rows_per_seq=T,
+                                                                scale_shift=eng._ss(ws, W, "l0.ffn"), silu=True))
+time_fn("K/V half (A or A^T)", lambda: ops.attn_kv(qkv[:, D:2 * D], qkv[:, 2 * D:], ws["a_blk"], S, T, 8, length=ws["len"],
+                                                   transposed=eng.apply_tc))
+time_fn("attention apply + stylize (product kernel)", lambda: eng._attend(ws, W, "l0.ca", S, T, q_ca, a_in=ws["a_blk"],
+                                                                           q_softmaxed=eng.qsm))
