@@ -389,8 +389,10 @@ def train_block(device, rank, world, iters, pk):
         out.update({"ms_per_iter_allreduce_off": ms_off, "exposed_allreduce_ms": exposed, "allreduce_alone_ms": ms_ar,
                     "overlap_frac": max(0.0, min(1.0, 1.0 - exposed / ms_ar)) if ms_ar > 0 else None,
                     "allreduce_busbw_gbs": 2 * (world - 1) / world * flat.numel() * 4 / (ms_ar * 1e-3) / 1e9})
+        out["nccl_reserved_sms"] = int(os.environ.get("HIG_DDP_NCCL_SMS", "0"))
     else:
         out.update({"allreduce_bytes": 0, "overlap_frac": None})
+    ops.set_sm_limit(0)      # DataParallel reserved SMs for NCCL: give them back to whatever runs after this block
     return out
 
 

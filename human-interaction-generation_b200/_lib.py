@@ -23,6 +23,7 @@ SIGNATURES = {
     "hig_launch_count": [],
     "hig_debug_trace": [c_void_p, c_int],
     "hig_debug_saturation": [c_void_p],
+    "hig_set_sm_limit": [c_int],
     "hig_l2_persist": [c_void_p, c_ull, ctypes.c_float, c_void_p],
     "hig_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                       c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],

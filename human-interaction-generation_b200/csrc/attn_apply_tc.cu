@@ -14,12 +14,13 @@
 // active at 16 warps per SM; profiles/r01e_ncu_full_summary.txt).  Y never exists outside TMEM.
 //
 // Operands: Qs = softmax_feat(Q) as the Q / Q|K|V projection's epilogue leaves it (bf16, HIG_GS_LN_QSM), streamed
-// head by head (128 rows x 64 columns = 16 KB, K-major, 128B swizzle) through a 5-stage TMA ring; A^T[s, h] ([l][d],
-// i.e. the K-major B operand; written in that layout by attn_kv_kernel / the text precompute) resident for the tile
-// (8 x 8 KB).  3-D tensor maps [S][T][cols] clip rows >= T on load (zero fill) and on store.
-// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 epilogue (TMEM lane quarter = warp % 4,
-// column half = (warp - 2) / 4): pass 1 row statistics, one 64-thread named barrier per quarter to swap the two column
-// halves' partials, pass 2 normalise + FiLM + SiLU -> bf16 -> 128B-swizzled 32 x 64 slabs -> TMA store.
+// head by head (128 rows x 64 columns = 16 KB, K-major, 128B swizzle) together with that head's A^T ([l][d], 8 KB: the
+// K-major B operand, written in that layout by attn_kv_kernel / the text precompute) through a 6-stage TMA ring.
+// 3-D tensor maps [S][T][cols] clip rows >= T on load (zero fill) and on store.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..17 epilogue (TMEM lane quarter = warp % 4, column
+// quarter = (warp - 2) / 4): pass 1 row statistics with the next tcgen05.ld always in flight, one 128-thread named barrier
+// per lane quarter to combine the four column quarters' partials, pass 2 normalise + FiLM + SiLU -> bf16 -> 64B-swizzled
+// 32 x 32 sub-slabs -> TMA store.
 #include <cuda.h>
 #include <cstdlib>
 #include <mutex>
@@ -33,15 +34,16 @@ namespace hig {
 namespace atc {
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;   // warp 0 producer, warp 1 MMA, warps 2..17 epilogue
-constexpr int STAGES = 5;
-constexpr int Q_BYTES = 128 * 64 * 2;          // one head block of the tile
-constexpr int A_BYTES = 8 * 64 * 64 * 2;       // A^T of the 8 heads
+constexpr int STAGES = 6;
+constexpr int Q_BYTES = 128 * 64 * 2;          // one head block of the tile (128 rows x 64 columns)
+constexpr int AH_BYTES = 64 * 64 * 2;          // A^T of one head
+constexpr int STAGE_BYTES = Q_BYTES + AH_BYTES;   // a ring stage carries BOTH operands of one head's MMAs
 constexpr int SUB = 32 * 64;                   // staging sub-slab: 32 rows x 32 bf16 columns (64-byte rows, 64B swizzle)
 constexpr int EPI_BYTES = EPI_WARPS * 2 * SUB; // two sub-slabs per epilogue warp
 constexpr int GB_BYTES = 2 * 2 * 512 * 4;      // (G, B) x two tile parities
 constexpr int RED_BYTES = EPI_WARPS * 32 * 8;
-constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-constexpr int SMEM = STAGES * Q_BYTES + A_BYTES + EPI_BYTES + GB_BYTES + RED_BYTES + BAR_BYTES + 1024;
+constexpr int BAR_BYTES = (2 * STAGES + 2) * 8 + 16;
+constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + GB_BYTES + RED_BYTES + BAR_BYTES + 1024;
 static_assert(SMEM <= 232448, "shared memory budget");
 
 HIG_DEVICE void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
@@ -112,16 +114,13 @@ attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      int S, int T) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sAT = sQ + STAGES * Q_BYTES;
-  uint8_t* sEpi = sAT + A_BYTES;
+  uint8_t* sQ = smem;                                   // ring: stage s = [Q block 16 KB | A^T head 8 KB]
+  uint8_t* sEpi = sQ + STAGES * STAGE_BYTES;
   float* sGB = reinterpret_cast<float*>(sEpi + EPI_BYTES);            // [parity][G | B][512]
   float2* sRed = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(sGB) + GB_BYTES);   // [16 warps][32 lanes]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sRed) + RED_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* afull_bar = empty_bar + STAGES;
-  uint64_t* afree_bar = afull_bar + 1;
-  uint64_t* tfull_bar = afree_bar + 1;
+  uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
 
@@ -134,8 +133,6 @@ attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmO);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    mbar_init(afull_bar, 1);
-    mbar_init(afree_bar, 1);
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, EPI_WARPS);
     fence_mbar_init();
@@ -155,18 +152,18 @@ attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (lane == 0) {
       pdl_wait();        // Qs and A^T are the outputs of the two previous kernels
       pdl_trigger();
-      uint32_t it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      // the ring runs ahead of the MMA warp across tile boundaries: while the epilogue drains tile i, the operands of the
+      // first STAGES heads of tile i+1 are already landing (the first cut kept A^T in a single buffer gated on the previous
+      // tile's MMAs and had 5 of 8 query blocks in flight: the next tile's MMAs then waited on L2 latency)
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int s = tile_seq(tile), r0 = tile_row0(tile);
-        if (lt > 0) mbar_wait(afree_bar, (lt - 1u) & 1u);     // the previous tile's MMAs have read A^T
-        mbar_arrive_expect_tx(afull_bar, A_BYTES);
-#pragma unroll
-        for (int h = 0; h < 8; ++h) tma_load_2d(sAT + h * 8192, &tmA, afull_bar, 0, (s * 8 + h) * 64);
         for (int h = 0; h < 8; ++h, ++it) {
           const uint32_t stage = it % STAGES, phase = (it / STAGES) & 1u;
           mbar_wait(empty_bar + stage, phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar + stage, Q_BYTES);
-          tma_load_3d(sQ + stage * Q_BYTES, &tmQ, full_bar + stage, h * 64, r0, s);
+          mbar_arrive_expect_tx(full_bar + stage, STAGE_BYTES);
+          tma_load_3d(sQ + stage * STAGE_BYTES, &tmQ, full_bar + stage, h * 64, r0, s);
+          tma_load_2d(sQ + stage * STAGE_BYTES + Q_BYTES, &tmA, full_bar + stage, 0, (s * 8 + h) * 64);
         }
       }
     }
@@ -176,21 +173,19 @@ attn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
       uint32_t it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-        mbar_wait(afull_bar, lt & 1u);
         mbar_wait(tempty_bar, (lt & 1u) ^ 1u);     // the epilogue has drained the previous tile's accumulator
         tc_fence_after();
         for (int h = 0; h < 8; ++h, ++it) {
           const uint32_t stage = it % STAGES, phase = (it / STAGES) & 1u;
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
-          const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + stage * Q_BYTES));
-          const uint64_t db = umma_desc_k_sw128(smem_u32(sAT + h * 8192));
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + stage * STAGE_BYTES));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sQ + stage * STAGE_BYTES + Q_BYTES));
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(tmem_base + h * 64, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);
           umma_commit(empty_bar + stage);
         }
         umma_commit(tfull_bar);
-        umma_commit(afree_bar);
       }
     }
     __syncwarp();

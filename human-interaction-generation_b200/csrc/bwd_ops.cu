@@ -126,6 +126,7 @@ cast_colsum_kernel(const TIn* __restrict__ in, int M, int N, int ld_in, TOut* __
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (grp < groups) {
+#pragma unroll 4
     for (int m = m0 + ri; m < m1; m += rpt) {
       float v[8];
       Vec8<TIn>::load(in + (size_t)m * ld_in + grp * 8, v);
@@ -221,7 +222,8 @@ colsum_vec_kernel(const TIn* __restrict__ in, int M, int N, int ld, int rows_per
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (grp < groups && ri < rpt) {
-    for (int m = m0 + ri; m < m1; m += rpt) {
+#pragma unroll 4
+    for (int m = m0 + ri; m < m1; m += rpt) {     // unrolled: four independent 16 / 32-byte loads in flight per thread
       float v[8];
       Vec8<TIn>::load(in + (size_t)m * ld + grp * 8, v);
 #pragma unroll
@@ -286,20 +288,21 @@ int colsum(const void* in, int dtype, int M, int N, int ld, float* out, cudaStre
 //   fwd: out = act(x)            bwd: dx = dy * act'(x)   (x = the saved pre-activation)
 // ------------------------------------------------------------------------------------------------
 HIG_DEVICE float act_fwd_f(float v, int act) {
-  if (act == 1) return gelu_erf_f(v);
-  if (act == 2) return v / (1.0f + expf(-v));
+  if (act == 1) return gelu_as_f(v);                     // erf to 1.5e-7 absolute (Abramowitz & Stegun 7.1.26): exact-GELU semantics
+  if (act == 2) return __fdividef(v, 1.0f + __expf(-v));
   if (act == 3) return v / (1.0f + expf(-1.702f * v));   // QuickGELU of CLIP's text transformer MLP: x sigmoid(1.702 x)
   return v;
 }
 HIG_DEVICE float act_grad_f(float v, int act) {
   if (act == 1) {
-    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
-    const float pdf = 0.3989422804014327f * expf(-0.5f * v * v);
-    return cdf + v * pdf;
+    // the kernel was instruction-bound on erff + expf (84 % issue-active, 40 us for 143 MB): A&S erf + fast exp
+    const float cdf = 0.5f * (1.0f + erf_as_f(v * 0.70710678118654752440f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
+    return fmaf(v, pdf, cdf);
   }
   if (act == 2) {
-    const float s = 1.0f / (1.0f + expf(-v));
-    return s * (1.0f + v * (1.0f - s));
+    const float s = __fdividef(1.0f, 1.0f + __expf(-v));
+    return s * fmaf(v, 1.0f - s, 1.0f);
   }
   return 1.0f;
 }
@@ -424,16 +427,20 @@ ln_film_silu_bwd_kernel(const TX* __restrict__ x, int rows, int rows_per_seq, in
                         int apply_silu, const TG* __restrict__ dout, TDX* __restrict__ dx, int dx_accumulate,
                         float* __restrict__ d_ss, int dss_stride, float* __restrict__ d_gb, int dgb_stride) {
   constexpr int CH = WIDTH / 256;
+  // per-column vectors in a lane-major layout: column c*256 + lane*8 + j lives at ((c*2 + j/4)*32 + lane)*4 + j%4, so a
+  // warp's 16-byte accesses are contiguous (the natural layout put the lanes 32 B apart: 2-way bank conflicts, 1.7 M per launch)
   __shared__ __align__(16) float par[4][WIDTH];   // gamma, beta, 1 + scale, shift
   __shared__ __align__(16) float red[2][WIDTH];   // X = sum dt n_hat, Y = sum dt
+  auto perm = [](int col) { const int c = col >> 8, l = (col & 255) >> 3, j = col & 7; return ((c * 2 + (j >> 2)) * 32 + l) * 4 + (j & 3); };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int seq = blockIdx.x / slices, slice = blockIdx.x - seq * slices;
   for (int i = threadIdx.x; i < WIDTH; i += LNB_WARPS * 32) {
-    par[0][i] = gamma[i];
-    par[1][i] = beta[i];
-    par[2][i] = scale_shift ? 1.0f + scale_shift[(size_t)seq * ss_stride + i] : 1.0f;
-    par[3][i] = scale_shift ? scale_shift[(size_t)seq * ss_stride + WIDTH + i] : 0.f;
-    red[0][i] = red[1][i] = 0.f;
+    const int p = perm(i);
+    par[0][p] = gamma[i];
+    par[1][p] = beta[i];
+    par[2][p] = scale_shift ? 1.0f + scale_shift[(size_t)seq * ss_stride + i] : 1.0f;
+    par[3][p] = scale_shift ? scale_shift[(size_t)seq * ss_stride + WIDTH + i] : 0.f;
+    red[0][p] = red[1][p] = 0.f;
   }
   __syncthreads();
 
@@ -504,17 +511,17 @@ ln_film_silu_bwd_kernel(const TX* __restrict__ x, int rows, int rows_per_seq, in
     float m1 = 0.f, m2 = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      const int col = c * 256 + lane * 8;
+      const int p0 = (c * 64 + lane) * 4, p1 = p0 + 128;   // lane-major positions of columns j = 0..3 / 4..7
       float G[8], Bt[8], S1[8], SH[8];
-      *reinterpret_cast<float4*>(G) = *reinterpret_cast<const float4*>(&par[0][col]);
-      *reinterpret_cast<float4*>(G + 4) = *reinterpret_cast<const float4*>(&par[0][col + 4]);
-      *reinterpret_cast<float4*>(S1) = *reinterpret_cast<const float4*>(&par[2][col]);
-      *reinterpret_cast<float4*>(S1 + 4) = *reinterpret_cast<const float4*>(&par[2][col + 4]);
+      *reinterpret_cast<float4*>(G) = *reinterpret_cast<const float4*>(&par[0][p0]);
+      *reinterpret_cast<float4*>(G + 4) = *reinterpret_cast<const float4*>(&par[0][p1]);
+      *reinterpret_cast<float4*>(S1) = *reinterpret_cast<const float4*>(&par[2][p0]);
+      *reinterpret_cast<float4*>(S1 + 4) = *reinterpret_cast<const float4*>(&par[2][p1]);
       if (need_u) {
-        *reinterpret_cast<float4*>(Bt) = *reinterpret_cast<const float4*>(&par[1][col]);
-        *reinterpret_cast<float4*>(Bt + 4) = *reinterpret_cast<const float4*>(&par[1][col + 4]);
-        *reinterpret_cast<float4*>(SH) = *reinterpret_cast<const float4*>(&par[3][col]);
-        *reinterpret_cast<float4*>(SH + 4) = *reinterpret_cast<const float4*>(&par[3][col + 4]);
+        *reinterpret_cast<float4*>(Bt) = *reinterpret_cast<const float4*>(&par[1][p0]);
+        *reinterpret_cast<float4*>(Bt + 4) = *reinterpret_cast<const float4*>(&par[1][p1]);
+        *reinterpret_cast<float4*>(SH) = *reinterpret_cast<const float4*>(&par[3][p0]);
+        *reinterpret_cast<float4*>(SH + 4) = *reinterpret_cast<const float4*>(&par[3][p1]);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -562,28 +569,29 @@ ln_film_silu_bwd_kernel(const TX* __restrict__ x, int rows, int rows_per_seq, in
     if (warp == w) {
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        const int col = c * 256 + lane * 8;
+        const int p0 = (c * 64 + lane) * 4;
         auto add8 = [&](float* dst, const float (&a)[8]) {
-          float4 p = *reinterpret_cast<float4*>(dst), q = *reinterpret_cast<float4*>(dst + 4);
+          float4 p = *reinterpret_cast<float4*>(dst), q = *reinterpret_cast<float4*>(dst + 128);
           p.x += a[0]; p.y += a[1]; p.z += a[2]; p.w += a[3]; q.x += a[4]; q.y += a[5]; q.z += a[6]; q.w += a[7];
           *reinterpret_cast<float4*>(dst) = p;
-          *reinterpret_cast<float4*>(dst + 4) = q;
+          *reinterpret_cast<float4*>(dst + 128) = q;
         };
-        add8(&red[0][col], aX[c]);
-        add8(&red[1][col], aY[c]);
+        add8(&red[0][p0], aX[c]);
+        add8(&red[1][p0], aY[c]);
       }
     }
     __syncthreads();
   }
   for (int i = threadIdx.x; i < WIDTH; i += LNB_WARPS * 32) {
-    const float X = red[0][i], Y = red[1][i];
+    const int p = perm(i);
+    const float X = red[0][p], Y = red[1][p];
     if (d_ss) {
-      atomicAdd(d_ss + (size_t)seq * dss_stride + i, fmaf(par[0][i], X, par[1][i] * Y));
+      atomicAdd(d_ss + (size_t)seq * dss_stride + i, fmaf(par[0][p], X, par[1][p] * Y));
       atomicAdd(d_ss + (size_t)seq * dss_stride + WIDTH + i, Y);
     }
     if (d_gb) {
-      atomicAdd(d_gb + (size_t)seq * dgb_stride + i, par[2][i] * X);
-      atomicAdd(d_gb + (size_t)seq * dgb_stride + WIDTH + i, par[2][i] * Y);
+      atomicAdd(d_gb + (size_t)seq * dgb_stride + i, par[2][p] * X);
+      atomicAdd(d_gb + (size_t)seq * dgb_stride + WIDTH + i, par[2][p] * Y);
     }
   }
 }

@@ -141,6 +141,11 @@ int hig_debug_trace(unsigned long long* buf, int max_launches) {
   return HIG_OK;
 }
 
+int hig_set_sm_limit(int n) {
+  hig::set_sm_limit(n);
+  return HIG_OK;
+}
+
 int hig_debug_saturation(unsigned long long* counter) {
   hig::set_saturation_counter(counter);
   return HIG_OK;

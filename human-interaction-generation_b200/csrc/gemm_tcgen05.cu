@@ -267,6 +267,11 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int 
 
 int device_num_sms();
 static int num_sms() { return device_num_sms(); }
+// SMs the persistent kernels (GEMMs, attention apply) size their grids for.  hig_set_sm_limit(n) caps it: the data-parallel
+// training path leaves a few SMs to NCCL so that the gradient all-reduce of a segment runs BESIDE the next segment's backward
+// kernels instead of waiting behind persistent grids that own every SM.
+static int g_sm_limit = 0;
+void set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
 int device_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -275,6 +280,7 @@ int device_num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
+  if (g_sm_limit > 0 && g_sm_limit < n) return g_sm_limit & ~1;   // CTA pairs: even
   return n;
 }
 
@@ -339,7 +345,9 @@ static int gemm_bf16_impl(const void* A, int lda, const void* W, int ldw, int M,
   const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
   auto pick_splits = [&](int mn_tiles, int workers) {
     if (!split_k) return 1;
-    int want = split_k > 0 ? split_k : (workers + mn_tiles - 1) / mn_tiles;
+    // floor, not ceil: tiles x slices must fit ONE wave of CTA pairs (ceil gave 76 / 84 / 80 units on 74 pairs for the
+    // 512x512 / 1536x512 / 1024x512 weight gradients: a second, nearly empty wave doubled their time)
+    int want = split_k > 0 ? split_k : workers / mn_tiles;
     if (want > k_blocks) want = k_blocks;
     if (want < 1) want = 1;
     const int per = (k_blocks + want - 1) / want;
@@ -426,7 +434,7 @@ int gemm_bf16_t(int trans_a, int trans_b, const void* A, int lda, const void* W,
   int ks = 1;
   if (split_k) {
     const int workers = num_sms() / 2;
-    int want = split_k > 0 ? split_k : (workers + mn - 1) / mn;
+    int want = split_k > 0 ? split_k : workers / mn;      // one wave of CTA pairs (see gemm_bf16_impl)
     if (want > k_blocks) want = k_blocks;
     if (want < 1) want = 1;
     const int per = (k_blocks + want - 1) / want;

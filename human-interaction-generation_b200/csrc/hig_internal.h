@@ -49,6 +49,7 @@ int gemm_stream(int kind, const void* A, int lda, const void* W, int ldw, int op
 
 void set_gemm_trace(unsigned long long* buf, int max_launches);
 void set_saturation_counter(unsigned long long* counter);
+void set_sm_limit(int n);
 
 int row_stats(const void* x, int x_dtype, int rows, int width, float* stats, cudaStream_t stream);
 

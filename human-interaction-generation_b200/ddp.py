@@ -85,9 +85,19 @@ class DataParallel(nn.Module):
             with torch.no_grad():
                 for p in module.parameters():
                     dist.broadcast(p.data, src=0, group=process_group)
-        # the denoiser's flat gradient segments (autograd.py)
+        # the denoiser's flat gradient segments (autograd.py / train_engine.py)
         module._grad_segment_hook = self.reducer.segment_ready
         module._grad_finish_hook = self.reducer.finish
+        # Persistent GEMM grids own every SM, so an NCCL kernel launched beside them only runs in the gaps between kernels
+        # (measured at N = 2: 0.70 ms of a 0.82 ms all-reduce exposed).  Reserve a few SMs for NCCL while training in parallel:
+        # HIG_DDP_NCCL_SMS=n (default 0 = no reservation: measured at N = 2, reserving 8 or 16 SMs changed nothing — 16.42 / 16.47 / 16.50 ms).  Graphs captured afterwards use the reduced grids.
+        import os
+        reserve = int(os.environ.get("HIG_DDP_NCCL_SMS", "0"))
+        if self.reducer.world > 1 and reserve > 0 and torch.cuda.is_available() and next(module.parameters()).is_cuda:
+            from . import ops
+            sms = torch.cuda.get_device_properties(next(module.parameters()).device).multi_processor_count
+            ops.set_sm_limit(max(2, sms - reserve))
+            self.sm_limit = sms - reserve
         # everything torch.autograd differentiates outside the denoiser kernels
         self._other = []
         if hasattr(module, "temporal_decoder_blocks"):

@@ -314,6 +314,11 @@ def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, out=None):
     return out
 
 
+def set_sm_limit(n):
+    """Persistent kernels size their grids for n SMs (0 = all): leaves SMs to concurrent NCCL kernels."""
+    _lib.check(_lib.load().hig_set_sm_limit(int(n)), "hig_set_sm_limit")
+
+
 def debug_saturation(counter):
     """counter: int64 / uint64 device scalar that counts saturating fp16 stream stores (None switches the counter off)."""
     lib = _lib.load()

@@ -59,6 +59,23 @@ class FlatParams:
         self.n_den = self.seg_bounds[len(self.segments) - 1][1]
         self.n_total = off
         self.other_bounds = self.seg_bounds.pop()
+        # What leaves with each gradient segment (data-parallel all-reduce ranges).  The emb-linears of the StylizationBlocks
+        # live in the LAST segment's region (one contiguous forward operand), but a layer's share of them is final when the
+        # layer's backward is: it is handed out with that layer (train_engine._Plan._backward).
+        L = module.num_layers
+        last = self.segments[-1]
+        n_styl = sum(1 for n in last if n.endswith("emb_layers.1.weight"))
+        npl = n_styl // L
+        per_w = named[last[0]].numel()                    # 2D * E
+        per_b = named[last[n_styl]].numel()               # 2D
+        w0, b0 = self.offsets[last[0]], self.offsets[last[n_styl]]
+        rest0 = self.offsets[last[2 * n_styl]]
+        self.seg_ranges = [[self.seg_bounds[0]]]
+        for k in range(1, L + 1):
+            li = L - k
+            self.seg_ranges.append([self.seg_bounds[k], (w0 + li * npl * per_w, w0 + (li + 1) * npl * per_w),
+                                    (b0 + li * npl * per_b, b0 + (li + 1) * npl * per_b)])
+        self.seg_ranges.append([(rest0, self.seg_bounds[-1][1])])
         self.param = torch.zeros(self.n_total, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(self.n_total, device=dev, dtype=torch.float32)
         self.mirror = torch.zeros(self.n_den, device=dev, dtype=torch.bfloat16)
@@ -389,6 +406,11 @@ class _Plan:
                                  d_gb=bcast(greg(mp + "norm.weight", 2 * D, (2 * D,))))
 
         modname = {"sa": "sa_block.", "ca": "ca_block.", "ic": "int_ca_block.", "ffn": "ffn."}
+        n_styl = W["n_styl"]
+        npl = n_styl // eng.L                                      # StylizationBlocks per layer (sa, ca, [ic], ffn)
+        emb_w_grad = greg(fp.segments[-1][0], n_styl * 2 * D * E, (n_styl * 2 * D, E))
+        emb_b_grad = greg(fp.segments[-1][n_styl], n_styl * 2 * D, (n_styl * 2 * D,))
+        d_ss_c = new(S, n_styl * 2 * D)
         seg = 1
         for blk in reversed(st.blocks):
             li, kind = blk["li"], blk["kind"]
@@ -426,7 +448,13 @@ class _Plan:
                                  greg(mp + "query.bias", 3 * D, (3 * D,)))
                 pre_ln_bwd(blk, d_n, pfx, mp)
             if kind == "sa":
-                yield seg        # every parameter of layer li (except its emb-linears) is final
+                # every parameter of layer li is final — including its StylizationBlocks' emb-linears: their (scale | shift)
+                # gradient slabs receive nothing from the layers below, so their weight / bias gradients are taken now and
+                # leave with this segment instead of waiting for the end of backward (a third of all parameters)
+                lo_c, hi_c = li * npl * 2 * D, (li + 1) * npl * 2 * D
+                ops.transpose(d_ss[:, lo_c:hi_c], copy=d_ss_c[:, lo_c:hi_c], colsum=emb_b_grad[lo_c:hi_c])
+                wgrad(d_ss_c[:, lo_c:hi_c], st.semb, emb_w_grad[lo_c:hi_c], split=False)
+                yield seg
                 seg += 1
 
         # ---------------- motion embedding (:593-602)
@@ -445,14 +473,8 @@ class _Plan:
             ops.colsum(dpos[1:], gv["joint_embed.bias"])
 
         # ---------------- stylization emb-linears + time-embedding MLP (:88-90, :474-478, :591)
-        n_styl = W["n_styl"]
-        first_w = fp.segments[-1][0]
-        first_b = fp.segments[-1][n_styl]
-        d_ss_c = new(S, n_styl * 2 * D)
-        ops.transpose(d_ss, copy=d_ss_c, colsum=greg(first_b, n_styl * 2 * D, (n_styl * 2 * D,)))
         d_semb = torch.zeros(S, E, device=dev, dtype=f32)      # K = 4L * 1024 is long, the output 8 tiles: split-K
         ops.gemm_t(d_ss_c, W["emb.w"], trans_b=True, out_f32=d_semb, split_k=-1)
-        wgrad(d_ss_c, st.semb, greg(first_w, n_styl * 2 * D * E, (n_styl * 2 * D, E)), split=False)
         d_emb = ops.act_bwd(st.emb, d_semb, ops.ACT_SILU, new(S, E, dtype=f32))
         d_emb_c = new(S, E)
         ops.transpose(d_emb, copy=d_emb_c, colsum=gv["time_embed.2.bias"])
@@ -590,8 +612,8 @@ class DenoiserGraphFn(torch.autograd.Function):
 
         def seg_done(k):
             if hook is not None:
-                lo, hi = fp.seg_bounds[k]
-                hook(k, fp.grad[lo:hi])
+                for lo, hi in fp.seg_ranges[k]:
+                    hook(k, fp.grad[lo:hi])
 
         d_xf_proj, d_xf_out = plan.backward(seg_done)
         fin = getattr(module, "_grad_finish_hook", None)

@@ -47,6 +47,12 @@ unsigned long long hig_launch_count(void);
  * NULL or max_launches <= 0 disables. */
 int hig_debug_trace(unsigned long long* buf, int max_launches);
 
+/* Grid sizing (no reference counterpart): the persistent kernels (tcgen05 GEMMs, attention apply) launch one CTA (pair) per SM.
+ * n > 0 makes them size their grids for n SMs instead of all of them — data-parallel training leaves a few SMs to the NCCL
+ * all-reduce kernels (tools/train.py:78-82 is where the reference's DDP reducer would run) so that a gradient segment's
+ * exchange overlaps the next segment's backward; n <= 0 restores the device's SM count. */
+int hig_set_sm_limit(int n);
+
 /* Debug aid (no reference counterpart): while `counter` (a device unsigned long long) is non-NULL, every fp16 residual-stream
  * store of hig_gemm_stream (HIG_GS_RES_H) whose fp32 value exceeds +-65504 — i.e. that the saturating conversion clamps —
  * adds 1 to *counter.  The reference's stream is fp32 (models/interaction_transformer.py:129,164,203,263): a non-zero count

@@ -178,6 +178,24 @@ def test_heavy_tailed_residual_stream_bf16(cuda):
     err = valid_rel(out, ref, inp["length"])
     print(f"heavy tail bf16: rel-L2 {err:.3e}")
     assert err < 1e-2, err
+    # (B) rows whose mean sits >= 50 standard deviations from zero, without outlier channels to inflate sigma: a common
+    # offset of 60 on four positional rows of an otherwise O(1) stream.  LayerNorm is shift invariant, the fp16 stream is
+    # not: its ulp at 60 is 0.03, i.e. ~3 % of those rows' sigma per rounding — the error is confined to those rows.
+    sdb = {k: v.clone() for k, v in weights.make_state_dict(seed=0, num_layers=L).items()}
+    sdb["sequence_embedding"][5:9] += 60.0
+    m.load_state_dict(sdb, strict=True)
+    with torch.no_grad():
+        ref_b = DO.denoiser_forward(sdb, inp["x"], inp["t"], inp["length"], inp["xf_proj"], inp["xf_out"])
+    out_b = run(m, inp, "text", cuda)
+    torch.cuda.synchronize()
+    stream_b = eng.workspace(S, T)["xres"].float()
+    ratio = (stream_b.mean(1).abs() / stream_b.std(1)).view(S, T)
+    err_b = valid_rel(out_b, ref_b, inp["length"])
+    rows_b = valid_rel(out_b[:, 6:10], ref_b[:, 6:10], inp["length"].clamp(max=4))
+    print(f"heavy tail (B): max |mu|/sigma of the final stream {ratio.max().item():.1f} (rows 6..9: {ratio[:, 6:10].mean().item():.1f}), "
+          f"rel-L2 {err_b:.3e}, on the offset rows {rows_b:.3e}")
+    assert ratio.max().item() >= 20
+    assert err_b < 1e-2, err_b
     # and the counter does count: push the stream over the fp16 range
     sd2 = {k: v.clone() for k, v in sd.items()}
     for k in sd2:
