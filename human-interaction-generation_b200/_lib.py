@@ -43,6 +43,8 @@ SIGNATURES = {
     "hig_attn_kv": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "hig_attn_apply_stylize_tc": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                   c_int, c_int, c_void_p],
+    "hig_attn_apply_stylize_y": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
+                                 c_int, c_int, c_void_p],
     "hig_timestep_embed": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_time_table_silu": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "hig_tile_rows": [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p],

@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(AP_THREADS, 2)
 attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ a_in,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           const float* __restrict__ scale_shift, int ss_stride, int apply_silu,
-                          __nv_bfloat16* __restrict__ out, int S, int T) {
+                          __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ y_out, int S, int T) {
+  // y_out (nullable, training forward): the attention output itself, bf16 [S*T, 512] — the LayerNorm backward needs it
   extern __shared__ __align__(128) uint8_t ap_smem[];
   const uint32_t sA = smem_u32(ap_smem);
   const uint32_t sQ = sA + AP_SMEM_A;
@@ -205,6 +206,29 @@ attn_apply_stylize_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
         ap_mma(acc[2 * np], af[kk], b0, b1);
         ap_mma(acc[2 * np + 1], af[kk], b2, b3);
       }
+    }
+    if (y_out != nullptr) {
+      // attention output before the LayerNorm, staged through this warp's consumed Q buffer like the final result
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQt + ap_swz(g, nt) + 4 * tg), "r"(pack_bf16x2(acc[nt][0], acc[nt][1])) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQt + ap_swz(g + 8, nt) + 4 * tg), "r"(pack_bf16x2(acc[nt][2], acc[nt][3])) : "memory");
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = i * 32 + lane;
+        const int r = idx >> 3, c = idx & 7;
+        const int t = tile * 16 + r;
+        if (t < T) {
+          uint4 val;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                       : "r"(sQt + ap_swz(r, c)) : "memory");
+          *reinterpret_cast<uint4*>(y_out + ((size_t)s * T + t) * AP_D + w * AP_HD + c * 8) = val;
+        }
+      }
+      __syncwarp();
     }
     // ---- LayerNorm over the 512 columns of a row = 8 warps x 64 columns: (sum, sum of squares) partials of every warp
     //      meet in shared memory behind ONE barrier per tile (the partial buffer alternates between tiles)
@@ -479,13 +503,14 @@ int attn_kv(const void* k, const void* v, int ldkv, void* a_out, const int* leng
 }
 
 int attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
-                       const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
+                       const float* scale_shift, int ss_stride, int apply_silu, void* out, void* y_out, int S, int T, int H,
                        cudaStream_t stream) {
   if (!q || !a_in || !gamma || !beta || !out || S <= 0 || T <= 0)
     return set_error(HIG_ERR_INVALID, "attn_apply_stylize: bad arguments");
   if (H != 8) return set_error(HIG_ERR_UNSUPPORTED, "attn_apply_stylize: built for 8 heads x 64 (latent_dim 512)");
   if (ldq % 8) return set_error(HIG_ERR_INVALID, "attn_apply_stylize: ldq must be a multiple of 8");
-  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(a_in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(a_in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(y_out) & 15))
     return set_error(HIG_ERR_INVALID, "attn_apply_stylize: pointers must be 16-byte aligned");
   static bool attr = false;
   if (!attr) {
@@ -500,7 +525,7 @@ int attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* ga
   if (ctas > (long long)S * n_tiles) ctas = (long long)S * n_tiles;
   cudaError_t e = launch_pdl(attn_apply_stylize_kernel, dim3((int)ctas), dim3(AP_THREADS), AP_SMEM, stream,
                              (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)a_in, gamma, beta, scale_shift, ss_stride,
-                             apply_silu, (__nv_bfloat16*)out, S, T);
+                             apply_silu, (__nv_bfloat16*)out, (__nv_bfloat16*)y_out, S, T);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("attn_apply_stylize launch: ") + cudaGetErrorString(e));
   count_launch();

@@ -161,7 +161,7 @@ int transpose(const void* in, int in_dtype, int M, int N, int ld_in, void* outT,
     int chunks = (148 * 4 + xb - 1) / xb;
     const int max_chunks = (M + rpt * 4 - 1) / (rpt * 4);
     if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks < 1) chunks = 1;
+    if (chunks < 1 || (colsum != nullptr && deterministic())) chunks = 1;
     const int rpc = (M + chunks - 1) / chunks;
     dim3 grid(xb, (M + rpc - 1) / rpc);
     using bf = __nv_bfloat16;
@@ -258,7 +258,7 @@ int colsum(const void* in, int dtype, int M, int N, int ld, float* out, cudaStre
       int chunks = (148 * 4 + xb - 1) / xb;
       const int max_chunks = (M + rpt * 4 - 1) / (rpt * 4);    // at least ~4 rows per thread
       if (chunks > max_chunks) chunks = max_chunks;
-      if (chunks < 1) chunks = 1;
+      if (chunks < 1 || deterministic()) chunks = 1;          // one CTA per column group: a single atomicAdd per column
       const int rpc = (M + chunks - 1) / chunks;
       dim3 grid(xb, (M + rpc - 1) / rpc);
       if (dtype == HIG_BF16) colsum_vec_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)in, M, N, ld, rpc, out);
@@ -272,7 +272,7 @@ int colsum(const void* in, int dtype, int M, int N, int ld, float* out, cudaStre
   const int xb = (N + 255) / 256;
   int chunks = (148 * 8 + xb - 1) / xb;
   if (chunks > M) chunks = M;
-  if (chunks < 1) chunks = 1;
+  if (chunks < 1 || deterministic()) chunks = 1;
   const int rpc = (M + chunks - 1) / chunks;
   dim3 grid(xb, (M + rpc - 1) / rpc);
   if (dtype == HIG_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)in, M, N, ld, rpc, out);
@@ -611,7 +611,7 @@ int ln_film_silu_bwd(const void* x, int x_dtype, int rows, int width, int rows_p
   int slices = (148 * 2) / n_seq;
   const int max_slices = (rows_per_seq + LNB_WARPS - 1) / LNB_WARPS;
   if (slices > max_slices) slices = max_slices;
-  if (slices < 1) slices = 1;
+  if (slices < 1 || deterministic()) slices = 1;      // one CTA per sequence: every (scale | shift) gradient has one contributor
   const int blocks = n_seq * slices;
   using bf = __nv_bfloat16;
 #define HIG_LNB(W, TX, TG, TD)                                                                                        \

@@ -17,6 +17,13 @@ int set_error(int code, const std::string& msg) {
   return code;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+// HIG_DETERMINISTIC=1 (read at every call, so a test can toggle it): reductions that are normally combined with floating-point
+// atomics across CTAs (column sums, the gradient norm) run with ONE contributor per address, in a fixed order
+bool deterministic() {
+  const char* e = getenv("HIG_DETERMINISTIC");
+  return e != nullptr && e[0] != '\0' && e[0] != '0';
+}
+
 bool pdl_enabled() {
   static const bool on = []() { const char* e = getenv("HIG_PDL"); return !(e && e[0] == '0'); }();
   return on;
@@ -166,7 +173,14 @@ int hig_q_sample(const float* x0, const float* noise, const long long* t, const 
 int hig_attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
                            const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
                            void* stream) {
-  return hig::attn_apply_stylize(q, ldq, a_in, gamma, beta, scale_shift, ss_stride, apply_silu, out, S, T, H,
+  return hig::attn_apply_stylize(q, ldq, a_in, gamma, beta, scale_shift, ss_stride, apply_silu, out, nullptr, S, T, H,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int hig_attn_apply_stylize_y(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
+                             const float* scale_shift, int ss_stride, int apply_silu, void* out, void* y_out, int S, int T,
+                             int H, void* stream) {
+  return hig::attn_apply_stylize(q, ldq, a_in, gamma, beta, scale_shift, ss_stride, apply_silu, out, y_out, S, T, H,
                                  static_cast<cudaStream_t>(stream));
 }
 

@@ -10,6 +10,8 @@ namespace hig {
 
 // HIG_PDL=0 disables programmatic dependent launch (default on)
 bool pdl_enabled();
+// HIG_DETERMINISTIC=1: cross-CTA floating-point atomics are replaced by single-contributor reductions (bit-reproducible gradients)
+bool deterministic();
 
 // kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute: consecutive
 // kernels of the denoiser step overlap prologue and tail (also inside CUDA-graph capture: programmatic edges)
@@ -90,8 +92,9 @@ int q_sample(const float* x0, const float* noise, const long long* t, const floa
 int attn_kv(const void* k, const void* v, int ldkv, void* a_out, const int* length, int S, int T, int H,
             int pair_shift, int transposed, cudaStream_t stream);
 
+// y_out (nullable): also write the attention output itself (bf16 [S*T, 512]) — saved by the training forward
 int attn_apply_stylize(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
-                       const float* scale_shift, int ss_stride, int apply_silu, void* out, int S, int T, int H,
+                       const float* scale_shift, int ss_stride, int apply_silu, void* out, void* y_out, int S, int T, int H,
                        cudaStream_t stream);
 
 // tcgen05 / TMEM variant (attn_apply_tc.cu): q holds softmax_feat(Q) already, a_t = A^T [S, 8, 64 (l), 64 (d)]

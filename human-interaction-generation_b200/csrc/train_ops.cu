@@ -160,7 +160,7 @@ int sumsq(const float* x, long long n, double* out, cudaStream_t stream) {
   if (reinterpret_cast<uintptr_t>(x) & 15) return set_error(HIG_ERR_INVALID, "sumsq: x must be 16-byte aligned");
   long long blocks = (n / 4 + 511) / 512;
   if (blocks > 148 * 4) blocks = 148 * 4;
-  if (blocks < 1) blocks = 1;
+  if (blocks < 1 || deterministic()) blocks = 1;      // HIG_DETERMINISTIC: one block, fixed summation order
   sumsq_kernel<<<(unsigned)blocks, 512, 0, stream>>>(x, n, out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("sumsq launch: ") + cudaGetErrorString(e));

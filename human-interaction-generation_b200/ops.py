@@ -164,7 +164,7 @@ def eff_attn(mode, S, T, H, q=None, k=None, v=None, a_in=None, a_out=None, y=Non
     return y if y is not None else a_out
 
 
-def attn_apply_stylize(q, a_in, gamma, beta, out, S, T, H, scale_shift=None, silu=True, q_softmaxed=False):
+def attn_apply_stylize(q, a_in, gamma, beta, out, S, T, H, scale_shift=None, silu=True, q_softmaxed=False, y_out=None):
     """out = [SiLU](LN(concat_h softmax_feat(q_h) @ a_in[s,h]) * (1 + scale) + shift), bf16; q is a [S*T, ld] view.
     q_softmaxed: q already holds softmax_feat(Q) (written by a GS_LN_QSM projection)."""
     lib = _lib.load()
@@ -177,8 +177,15 @@ def attn_apply_stylize(q, a_in, gamma, beta, out, S, T, H, scale_shift=None, sil
         if scale_shift.dtype != torch.float32 or scale_shift.stride(1) != 1:
             raise ValueError("hig_b200.attn_apply_stylize: scale_shift must be fp32 with unit inner stride")
         ss_stride = scale_shift.stride(0)
-    rc = lib.hig_attn_apply_stylize(_ptr(q), q.stride(0), _ptr(a_in), _ptr(gamma), _ptr(beta), _ptr(scale_shift),
-                                    ss_stride, (1 if silu else 0) | (2 if q_softmaxed else 0), _ptr(out), S, T, H, _stream())
+    flags = (1 if silu else 0) | (2 if q_softmaxed else 0)
+    if y_out is not None:
+        if y_out.dtype != torch.bfloat16 or not y_out.is_contiguous() or y_out.shape != out.shape:
+            raise ValueError("hig_b200.attn_apply_stylize: y_out must be a contiguous bf16 tensor shaped like out")
+        rc = lib.hig_attn_apply_stylize_y(_ptr(q), q.stride(0), _ptr(a_in), _ptr(gamma), _ptr(beta), _ptr(scale_shift),
+                                          ss_stride, flags, _ptr(out), _ptr(y_out), S, T, H, _stream())
+    else:
+        rc = lib.hig_attn_apply_stylize(_ptr(q), q.stride(0), _ptr(a_in), _ptr(gamma), _ptr(beta), _ptr(scale_shift),
+                                        ss_stride, flags, _ptr(out), S, T, H, _stream())
     _lib.check(rc, "hig_attn_apply_stylize")
     return out
 

@@ -269,17 +269,18 @@ class _Plan:
         G(st.xa, W["in.w"], residual=W["in.pos"], res_row_mod=T, out_f32=xres)
         st.blocks = []
 
-        def stylize_project(blk, y, xres_in, p, want_xb):
-            i = W[p + ".ss"]
-            ss = st.ss[:, i * 2 * D:(i + 1) * 2 * D]
-            sact = ops.ln_film_silu(y, W[p + ".po.ln.w"], W[p + ".po.ln.b"], new(tok, D), rows_per_seq=T, scale_shift=ss,
-                                    silu=True)
+        def project(blk, sact, xres_in, p, want_xb):
+            """x += out_layers(sact) (:92-97 + the block's residual add); xb = bf16 copy for the next block's GEMM operand."""
             xres_out = new(tok, D, dtype=f32)
             xb = new(tok, D) if want_xb else None
             G(sact, W[p + ".po.w"], bias=W[p + ".po.b"], residual=xres_in, out_f32=xres_out, out_bf16=xb)
-            blk.update(y=y, sact=sact, ss_index=i)
             return xres_out, xb
 
+        def ss_of(p):
+            i = W[p + ".ss"]
+            return i, st.ss[:, i * 2 * D:(i + 1) * 2 * D]
+
+        fused_attn = os.environ.get("HIG_TRAIN_FUSED_ATTN", "1") != "0"
         xb = None
         kinds = ["sa", "ca"] + (["ic"] if eng.has_ic else [])
         for li in range(L):
@@ -287,23 +288,39 @@ class _Plan:
             for kind in kinds:
                 blk = {"kind": kind, "xres_in": xres, "li": li}
                 n = ops.ln_film_silu(xres, W[p + kind + ".ln.w"], W[p + kind + ".ln.b"], new(tok, D))
-                y = new(tok, D)
+                y, sact = new(tok, D), new(tok, D)
+                i_ss, ss = ss_of(p + kind)
                 if kind == "ca":
-                    qc = new(tok, D)
-                    G(n, W[p + "ca.q.w"], bias=W[p + "ca.q.b"], out_bf16=qc)
-                    ops.eff_attn(ops.ATTN_Q_ONLY, S, T, H, q=qc, a_in=st.a_text[li], y=y)
-                    blk.update(n=n, q=qc)
+                    qv = new(tok, D)
+                    G(n, W[p + "ca.q.w"], bias=W[p + "ca.q.b"], out_bf16=qv)
+                    a_blk = st.a_text[li]
+                    blk.update(n=n, q=qv)
                 else:
                     qkv = new(tok, 3 * D)
                     G(n, W[p + kind + ".qkv.w"], bias=W[p + kind + ".qkv.b"], out_bf16=qkv)
-                    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
-                    if kind == "sa":
-                        ops.eff_attn(ops.ATTN_SELF, S, T, H, q=q, k=k, v=v, y=y, length=self.len, mask_v=True)
-                    else:
-                        ops.eff_attn(ops.ATTN_INTER, S, T, H, q=q, k=k, v=v, y=y, length=self.len, pair_shift=S // 2,
-                                     mask_v=False)
+                    qv, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
                     blk.update(n=n, qkv=qkv)
-                xres, xb = stylize_project(blk, y, xres, p + kind, kind == kinds[-1])
+                    a_blk = None
+                if fused_attn:
+                    # K/V half, then the query half fused with LayerNorm + FiLM + SiLU (the sampling path's kernels); the
+                    # attention output y is written too — the LayerNorm backward reads it
+                    if a_blk is None:
+                        a_blk = new(S, H, HEAD_DIM, HEAD_DIM)
+                        ops.attn_kv(k, v, a_blk, S, T, H, length=self.len, pair_shift=S // 2 if kind == "ic" else 0)
+                    ops.attn_apply_stylize(qv, a_blk, W[p + kind + ".po.ln.w"], W[p + kind + ".po.ln.b"], sact, S, T, H,
+                                           scale_shift=ss, silu=True, y_out=y)
+                else:
+                    if kind == "ca":
+                        ops.eff_attn(ops.ATTN_Q_ONLY, S, T, H, q=qv, a_in=a_blk, y=y)
+                    elif kind == "sa":
+                        ops.eff_attn(ops.ATTN_SELF, S, T, H, q=qv, k=k, v=v, y=y, length=self.len, mask_v=True)
+                    else:
+                        ops.eff_attn(ops.ATTN_INTER, S, T, H, q=qv, k=k, v=v, y=y, length=self.len, pair_shift=S // 2,
+                                     mask_v=False)
+                    ops.ln_film_silu(y, W[p + kind + ".po.ln.w"], W[p + kind + ".po.ln.b"], sact, rows_per_seq=T,
+                                     scale_shift=ss, silu=True)
+                blk.update(y=y, sact=sact, ss_index=i_ss)
+                xres, xb = project(blk, sact, xres, p + kind, kind == kinds[-1])
                 st.blocks.append(blk)
             # FFN (:261-264)
             blk = {"kind": "ffn", "xres_in": xres, "li": li, "xb_in": xb}
@@ -312,8 +329,11 @@ class _Plan:
             g = ops.act_fwd(h1, ops.ACT_GELU, new(tok, F_))
             y = new(tok, D)
             G(g, W[p + "ffn.w2"], bias=W[p + "ffn.b2"], out_bf16=y)
-            blk.update(h1=h1, g=g)
-            xres, xb = stylize_project(blk, y, xres, p + "ffn", True)
+            i_ss, ss = ss_of(p + "ffn")
+            sact = ops.ln_film_silu(y, W[p + "ffn.po.ln.w"], W[p + "ffn.po.ln.b"], new(tok, D), rows_per_seq=T, scale_shift=ss,
+                                    silu=True)
+            blk.update(h1=h1, g=g, y=y, sact=sact, ss_index=i_ss)
+            xres, xb = project(blk, sact, xres, p + "ffn", True)
             st.blocks.append(blk)
         # ---- output heads (:613-616)
         st.xb_final = xb
@@ -335,6 +355,10 @@ class _Plan:
         new = lambda *shape, dtype=bf: torch.empty(*shape, device=dev, dtype=dtype)
         gv = fp.gviews
         greg = lambda first, count, shape: fp.region(fp.grad, first, count, shape)
+        # HIG_DETERMINISTIC=1 (bit-reproducible gradients, a debugging / regression mode): weight gradients in ONE pass per
+        # output tile instead of K-slices combined with fp32 atomics, column sums and the gradient norm with one contributor
+        # per address (the C side reads the same variable), LayerNorm parameter gradients through per-sequence partials.
+        det = os.environ.get("HIG_DETERMINISTIC", "0") not in ("", "0")
 
         def zero_bias(n):
             zb = W["zero.b"].get(n)
@@ -351,12 +375,24 @@ class _Plan:
             """w_grad[N,K] += dy[M,N]^T . x[M,K]: both operands token-major as they lie; K = tokens split over CTA pairs
             (fp32 atomics into the zeroed gradient buffer).  split=False: enough output tiles to fill the machine — plain
             stores (the region has a single writer)."""
-            ops.gemm_t(dy, x, trans_a=True, trans_b=True, out_f32=w_grad, split_k=-1 if split else 0)
+            ops.gemm_t(dy, x, trans_a=True, trans_b=True, out_f32=w_grad, split_k=-1 if (split and not det) else 0)
+
+        pending_gb = []
 
         def bcast(region2w):
             """[2W] parameter-gradient region as a stride-0 [S, 2W] view: ln_film_silu_bwd accumulates every sequence's
-            (dgamma | dbeta) partials straight into the parameter gradient."""
-            return region2w.view(1, -1).expand(S, -1)
+            (dgamma | dbeta) partials straight into the parameter gradient.  Deterministic mode: per-sequence partials,
+            column-summed in a fixed order by flush_gb()."""
+            if not det:
+                return region2w.view(1, -1).expand(S, -1)
+            part = torch.zeros(S, region2w.numel(), device=dev, dtype=f32)
+            pending_gb.append((part, region2w))
+            return part
+
+        def flush_gb():
+            for part, region in pending_gb:
+                ops.colsum(part, region)
+            pending_gb.clear()
 
         fp.grad[:fp.n_den].zero_()
         d_ss = torch.zeros_like(st.ss)
@@ -366,9 +402,15 @@ class _Plan:
         d_eps = self.d_eps.view(tok, C)
         LDE = _rup(C, 8)
         de_a = torch.zeros(tok, LDE, device=dev, dtype=bf)               # frames >= 1 (frame-0 rows zeroed)
-        ops.transpose(d_eps, copy=de_a, colsum=gv["out.bias"], rows_zero_mod=T)
         de_0 = torch.zeros(S, LDE, device=dev, dtype=bf)                  # frame 0 of every sequence
-        ops.transpose(d_eps.view(S, T * C)[:, :C], copy=de_0, colsum=gv["out2.bias"])
+        if det:
+            ops.transpose(d_eps, copy=de_a, rows_zero_mod=T)
+            ops.transpose(d_eps.view(S, T * C)[:, :C], copy=de_0)
+            ops.colsum(de_a[:, :C], gv["out.bias"])
+            ops.colsum(de_0[:, :C], gv["out2.bias"])
+        else:
+            ops.transpose(d_eps, copy=de_a, colsum=gv["out.bias"], rows_zero_mod=T)
+            ops.transpose(d_eps.view(S, T * C)[:, :C], copy=de_0, colsum=gv["out2.bias"])
         dres = new(tok, D, dtype=f32)
         ops.gemm_t(de_a[:, :C], W["out.w"], trans_b=True, out_f32=dres)
         ops.gemm_t(de_0[:, :C], W["out2.w"], trans_b=True, out_f32=dres.view(S, T * D)[:, :D])
@@ -454,6 +496,7 @@ class _Plan:
                 lo_c, hi_c = li * npl * 2 * D, (li + 1) * npl * 2 * D
                 ops.transpose(d_ss[:, lo_c:hi_c], copy=d_ss_c[:, lo_c:hi_c], colsum=emb_b_grad[lo_c:hi_c])
                 wgrad(d_ss_c[:, lo_c:hi_c], st.semb, emb_w_grad[lo_c:hi_c], split=False)
+                flush_gb()
                 yield seg
                 seg += 1
 
@@ -474,7 +517,7 @@ class _Plan:
 
         # ---------------- stylization emb-linears + time-embedding MLP (:88-90, :474-478, :591)
         d_semb = torch.zeros(S, E, device=dev, dtype=f32)      # K = 4L * 1024 is long, the output 8 tiles: split-K
-        ops.gemm_t(d_ss_c, W["emb.w"], trans_b=True, out_f32=d_semb, split_k=-1)
+        ops.gemm_t(d_ss_c, W["emb.w"], trans_b=True, out_f32=d_semb, split_k=0 if det else -1)
         d_emb = ops.act_bwd(st.emb, d_semb, ops.ACT_SILU, new(S, E, dtype=f32))
         d_emb_c = new(S, E)
         ops.transpose(d_emb, copy=d_emb_c, colsum=gv["time_embed.2.bias"])
@@ -548,7 +591,8 @@ class TrainEngine:
         self.last = None
 
     def plan(self, S, T, N):
-        key = (S, T, N)
+        # the kernel-selection knobs are baked into the captured graphs
+        key = (S, T, N) + tuple(os.environ.get(k, "") for k in ("HIG_DETERMINISTIC", "HIG_TRAIN_FUSED_ATTN", "HIG_TRAIN_GRAPH"))
         p = self.plans.get(key)
         if p is None:
             if len(self.plans) >= 3:      # each plan pins its saved activations: keep a few shapes only

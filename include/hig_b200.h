@@ -191,6 +191,13 @@ int hig_recover_joints(const float* x, int S, int T, int C, int init_row, const 
 int hig_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
                  const float* sqrt_1mac, int S, int TC, float* out, void* stream);
 
+/* hig_attn_apply_stylize that also writes y_out (bf16 [S*T, 512], 16-byte aligned) = concat_h softmax_feat(Q_h) . A[s,h], the
+ * attention output before the StylizationBlock (models/interaction_transformer.py:128,162,201): the training forward keeps it
+ * for the LayerNorm backward, so the unfused attention kernel + a separate LayerNorm pass are not needed there either. */
+int hig_attn_apply_stylize_y(const void* q, int ldq, const void* a_in, const float* gamma, const float* beta,
+                             const float* scale_shift, int ss_stride, int apply_silu, void* out, void* y_out, int S, int T,
+                             int H, void* stream);
+
 /* K/V half of the efficient attention, bf16: a_out[s,h] = softmax_time(K_masked)^T (V mask) (64 x 64 per head;
  * models/interaction_transformer.py:121-127 / :194-200), K/V of sequence (s + pair_shift) % S, rows >= length[s] masked.
  * transposed != 0 writes A^T ([l][d]), the K-major B operand hig_attn_apply_stylize_tc consumes. */

@@ -126,12 +126,45 @@ def test_graph_engine_matches_eager_schedule_and_is_replayable(cuda):
             finally:
                 os.environ.pop("HIG_TRAIN_ENGINE", None)
         new, old = outs[(seed, "1")], outs[(seed, "0")]
-        assert rel(new[0], old[0]) < 2e-3
+        assert rel(new[0], old[0]) < 6e-3      # fused attention + tanh-form SiLU in the new forward vs the unfused exact-SiLU kernels
         assert rel(new[1], old[1]) < 2e-2 and rel(new[2], old[2]) < 2e-2
         assert set(new[3]) == set(old[3])
         worst = max((rel(new[3][n], old[3][n]), n) for n in old[3] if old[3][n].norm() > 1e-7 and not n.endswith("key.bias"))
         assert worst[0] < 3e-2, worst
     assert rel(outs[(11, "1")][0], outs[(12, "1")][0]) > 1e-2      # the second replay really used the new inputs
+
+
+def test_deterministic_mode_gives_bit_identical_gradients(cuda, monkeypatch):
+    """HIG_DETERMINISTIC=1: no cross-CTA floating-point atomics anywhere on the training path — two backward passes from the same
+    state give bit-identical flat gradients (and the same gradient norm); they agree with the default (split-K atomics) mode to
+    summation-order noise."""
+    import weights
+    from hig_b200 import ops
+    from hig_b200.train_engine import flat_params
+    L, S, T = 2, 8, 91
+    m = _model(cuda, layers=L)
+    m.cap_id = False
+    m.train()
+    inp = weights.make_inputs(5, S, T, n_text=77, lengths=[91, 60, 33, 91, 91, 60, 33, 91])
+    tgt = weights.make_noise(5, 0, S, T)[0].to(cuda)
+    g = lambda k: inp[k].to(cuda)
+
+    def run():
+        m.zero_grad(set_to_none=True)
+        pred = m(g("x"), g("t"), length=g("length"), xf_proj=g("xf_proj"), xf_out=g("xf_out"))
+        ((pred - tgt) ** 2).mean().backward()
+        fp = flat_params(m)
+        n2 = torch.zeros((), device=cuda, dtype=torch.float64)
+        ops.sumsq(fp.grad, n2)
+        return fp.grad[:fp.n_den].clone(), n2.item()
+
+    monkeypatch.setenv("HIG_DETERMINISTIC", "1")
+    g1, n1 = run()
+    g2, n2 = run()
+    assert torch.equal(g1, g2) and n1 == n2
+    monkeypatch.setenv("HIG_DETERMINISTIC", "0")
+    g3, _ = run()
+    assert rel(g3, g1) < 1e-4 and g1.abs().sum() > 0
 
 
 def test_gradient_accumulation_semantics_without_zero_grad(cuda):
