@@ -392,8 +392,83 @@ def train_block(device, rank, world, iters, pk):
         out["nccl_reserved_sms"] = int(os.environ.get("HIG_DDP_NCCL_SMS", "0"))
     else:
         out.update({"allreduce_bytes": 0, "overlap_frac": None})
+    # ---- the same step with captions as TEXT: (random-init) CLIP features cached per caption, the trainable 4-layer text
+    # encoder through torch.autograd (forward / backward each one CUDA graph), 77 text tokens per caption on the K/V side of
+    # every layer's text cross attention, shared between the sequences that carry the same caption
+    try:
+        out["with_captions"] = train_with_captions(device, rank, world, max(5, iters // 2), B, T)
+    except Exception as e:  # noqa: BLE001 — reported, the caption-id numbers above stand on their own
+        out["with_captions"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     ops.set_sm_limit(0)      # DataParallel reserved SMs for NCCL: give them back to whatever runs after this block
     return out
+
+
+# the 26 two-person classes of NTU RGB+D 120 (the reference's dataset, datasets/evaluator.py:133 `range(26)`): one caption per
+# role, so a batch of 128 pairs carries at most 52 distinct captions
+_ACTIONS = ["punches", "kicks", "pushes", "pats the back of", "points a finger at", "hugs", "gives an object to",
+            "touches the pocket of", "shakes hands with", "walks towards", "walks away from", "hits", "threatens",
+            "knocks over", "grabs something from", "aims at", "steps on the foot of", "high-fives", "drinks a toast with",
+            "carries something with", "takes a photo of", "follows", "whispers to", "exchanges things with", "supports",
+            "plays rock-paper-scissors with"]
+TRAIN_CAPTIONS = [(f"a person {a} the other person", f"the other person {a} a person") for a in _ACTIONS]
+
+
+def train_with_captions(device, rank, world, iters, B, T):
+    import torch.distributed as dist
+    from hig_b200.datasets import DevicePrefetcher
+    from hig_b200.interaction_transformer import MotionInteractionTransformer
+    from hig_b200.mul_ddpm_trainer import DDPMMulTrainer
+    from hig_b200.optim import FusedAdam
+    os.environ.setdefault("HIG_CLIP_STUB", "1")
+    torch.manual_seed(0)
+    m = MotionInteractionTransformer(CFG["feats"], num_frames=CFG["frames"], num_layers=CFG["layers"], latent_dim=CFG["latent"])
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if not name.startswith("clip.") and p.abs().max() == 0 and "norm.bias" not in name:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    m = m.to(device)
+    enc = m
+    if world > 1:
+        from hig_b200.ddp import DataParallel
+        enc = DataParallel(m)
+    opt = argparse.Namespace(device=device, multi=True, label_path="labels", cap_id=False, diffusion_steps=1000, is_train=True)
+    tr = DDPMMulTrainer(opt, enc)
+    tr.opt_encoder = FusedAdam(m, lr=2e-4)
+    tr.train_mode()
+    gen = torch.Generator().manual_seed(200 + rank)
+    rs = __import__("numpy").random.RandomState(200 + rank)
+    pick = rs.randint(0, len(TRAIN_CAPTIONS), B)
+    batch = ([TRAIN_CAPTIONS[i][0] for i in pick], [TRAIN_CAPTIONS[i][1] for i in pick],
+             torch.randn(B, T, CFG["feats"], generator=gen).pin_memory(), torch.randn(B, T, CFG["feats"], generator=gen).pin_memory(),
+             torch.from_numpy(rs.randint(20, 200, B)), None)
+
+    class _Repeat:
+        def __iter__(self):
+            while True:
+                yield batch
+    feed = iter(DevicePrefetcher(_Repeat(), device))
+    for _ in range(4):
+        tr.forward(next(feed))
+        tr.update_async()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        tr.forward(next(feed))
+        loss = tr.update_async()["loss_mot_rec"]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    if world > 1:
+        tt = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+    return {"workload": f"{B} pairs/GPU x {T} frames, labelled, captions as text ({len(set(batch[0] + batch[1]))} distinct among "
+                        f"{2 * B}; text encoder: {m.text_encoder_kind})", "iters": iters, "ms_per_iter": ms,
+            "pairs_per_s": world * B / ms * 1e3, "loss": float(loss)}
 
 
 def main():

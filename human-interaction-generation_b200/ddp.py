@@ -306,8 +306,8 @@ def generate_bucketed(trainer, caption1, caption2, m_lens, dim_pose, batch_size=
     local, indices = [], []
     for T_b, idx in plan[rank]:
         ml = lens[idx]
-        out = trainer.generate_batch([caption1[i] for i in idx], [caption2[i] for i in idx], ml, dim_pose,
-                                     pair_noise=None if pair_noise is None else pair_noise[idx])
+        extra = {} if pair_noise is None else {"pair_noise": pair_noise[idx]}
+        out = trainer.generate_batch([caption1[i] for i in idx], [caption2[i] for i in idx], ml, dim_pose, **extra)
         B = len(idx)
         for k, i in enumerate(idx):
             n = max(1, min(int(ml[k]), out.shape[1]))

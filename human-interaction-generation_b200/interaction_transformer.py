@@ -61,6 +61,19 @@ def _decoder_layer(latent_dim, text_latent_dim, time_embed_dim, ffn_dim, dropout
     return layer
 
 
+class _TextStack(nn.Module):
+    """text_pre_proj -> textTransEncoder -> text_ln; xf_proj = text_proj(EOT token) (:551-559).  feats [77, U, 512] LND."""
+
+    def __init__(self, net):
+        super().__init__()
+        self.pre, self.enc, self.ln, self.proj = net.text_pre_proj, net.textTransEncoder, net.text_ln, net.text_proj
+
+    def forward(self, feats, eot):
+        out = self.ln(self.enc(self.pre(feats)))
+        proj = self.proj(out[eot, torch.arange(out.shape[1], device=out.device)])
+        return proj, out.permute(1, 0, 2)
+
+
 class MotionInteractionTransformer(nn.Module):
     def __init__(self, input_feats, num_frames=240, latent_dim=512, ff_size=1024, num_layers=8, num_heads=8,
                  dropout=0, activation="gelu", num_text_layers=4, text_latent_dim=256, text_ff_size=2048,
@@ -139,6 +152,14 @@ class MotionInteractionTransformer(nn.Module):
         Same values as the reference, less work: every distinct caption is encoded once per call and
         the result is indexed back to the batch (NTU RGB+D has 43 distinct captions, a training batch 256-512), and
         the FROZEN CLIP features of a caption are cached across calls (invalidated when a CLIP parameter changes)."""
+        xf_proj, xf_out, idx = self._encode_unique(text, device)
+        if idx is not None:
+            xf_proj, xf_out = xf_proj.index_select(0, idx), xf_out.index_select(0, idx)
+        return xf_proj, xf_out
+
+    def _encode_unique(self, text, device):
+        """(xf_proj [U, E], xf_out [U, 77, Dt], idx) for the U distinct captions of `text`; idx (LongTensor [len(text)], or None
+        when every caption is distinct) maps each entry of `text` to its row."""
         text = list(text)
         uniq = list(dict.fromkeys(text))
         if self._text_on_kernels(device):
@@ -146,18 +167,62 @@ class MotionInteractionTransformer(nn.Module):
             feats = self._clip_features(uniq, device)           # [77, U, 512], frozen CLIP cached per caption
             eot = self._eot_index(uniq, device)
             xf_proj, xf_out = self.text_engine().encode(feats.permute(1, 0, 2).contiguous(), eot)
+        elif self._text_graphed(device):
+            # training: the trainable half of the text stack (pre-projection, 4-layer encoder, LayerNorm, EOT projection)
+            # runs through torch.autograd, forward and backward each replayed as ONE CUDA graph per caption-count bucket
+            # (about 350 launch-bound kernels otherwise); captions are independent rows, so padding rows change nothing.
+            bucket = -(-len(uniq) // 16) * 16
+            padded = uniq + [uniq[0]] * (bucket - len(uniq))
+            feats = self._clip_features(padded, device)
+            eot = self._eot_index(padded, device)
+            xf_proj, xf_out = self._text_stack_graphed(bucket, feats, eot)
+            xf_proj, xf_out = xf_proj[:len(uniq)], xf_out[:len(uniq)]
         else:
             feats = self._clip_features(uniq, device)           # [77, U, 512]
-            x = self.text_pre_proj(feats)
-            xf_out = self.text_ln(self.textTransEncoder(x))
             eot = self._eot_index(uniq, device)
-            xf_proj = self.text_proj(xf_out[eot, torch.arange(xf_out.shape[1], device=device)])
-            xf_out = xf_out.permute(1, 0, 2)
+            xf_proj, xf_out = self._text_stack()(feats, eot)
+        idx = None
         if len(uniq) != len(text):
             where = {c: i for i, c in enumerate(uniq)}
             idx = torch.tensor([where[c] for c in text], device=device, dtype=torch.long)
-            xf_proj, xf_out = xf_proj.index_select(0, idx), xf_out.index_select(0, idx)
-        return xf_proj, xf_out
+        return xf_proj, xf_out, idx
+
+    def _text_stack(self):
+        st = self.__dict__.get("_text_stack_mod")
+        if st is None:
+            st = _TextStack(self)
+            object.__setattr__(self, "_text_stack_mod", st)     # not a registered submodule: no duplicate state_dict keys
+        return st
+
+    def _text_graphed(self, device):
+        import os
+        return torch.is_grad_enabled() and torch.device(device).type == "cuda" and not self.no_clip and \
+            self.training and os.environ.get("HIG_TEXT_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing()
+
+    def _text_stack_graphed(self, bucket, feats, eot):
+        st = self._text_stack()
+        # the graphs read the parameters in place: only their addresses (FusedAdam re-flattens) and grad flags key the capture
+        import os
+        key = (bucket, tuple(p.data_ptr() for p in st.parameters()), tuple(p.requires_grad for p in st.parameters()),
+               os.environ.get("HIG_TEXT_TF32", "1"))
+        cache = self.__dict__.setdefault("_text_graphs", {})
+        fn = cache.get(key)
+        if fn is None:
+            for k in [k for k in cache if k[0] == bucket]:
+                del cache[k]
+            # make_graphed_callables rebinds .forward of the module it is given: hand it its own wrapper (same submodules).
+            # bf16 mode: the encoder's fp32 GEMMs may use TF32 tensor cores (cuBLAS picks its kernels at capture time, so the
+            # switch only needs to hold here) — as fp32 SIMT GEMMs, which is what torch runs by default, they cost 4.5 ms of a
+            # 21 ms iteration; TF32's 10-bit mantissa is inside the mode's 1e-2 tolerance.  HIG_TEXT_TF32=0 keeps fp32.
+            tf32 = self.precision == "bf16" and os.environ.get("HIG_TEXT_TF32", "1") != "0"
+            before = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32 or before
+            try:
+                fn = torch.cuda.make_graphed_callables(_TextStack(self), (feats.detach().clone(), eot.clone()))
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = before
+            cache[key] = fn
+        return fn(feats, eot)
 
     def text_engine(self):
         eng = getattr(self, "_text_engine", None)
@@ -172,7 +237,16 @@ class MotionInteractionTransformer(nn.Module):
             os.environ.get("HIG_TEXT_ENGINE", "1") != "0" and self.text_latent_dim in (256, 512)
 
     def _eot_index(self, captions, device):
-        return self._tokenize(captions, truncate=True).to(device).argmax(dim=-1)
+        """Position of the end-of-text token of every caption (the argmax of the token ids, :556) — remembered per caption: the
+        BPE tokeniser is host Python, 0.1 ms per caption, and a training batch repeats a few dozen captions every iteration."""
+        cache = self.__dict__.setdefault("_eot_cache", {})
+        missing = [c for c in dict.fromkeys(captions) if c not in cache]
+        if missing:
+            pos = self._tokenize(missing, truncate=True).argmax(dim=-1).tolist()
+            if len(cache) > 65536:
+                cache.clear()
+            cache.update(zip(missing, pos))
+        return torch.tensor([cache[c] for c in captions], device=device, dtype=torch.long)
 
     def _clip_features(self, captions, device):
         """clip.ln_final(clip.transformer(token_embedding + positional_embedding)) per caption, LND layout (:536-550)."""
@@ -248,10 +322,15 @@ class MotionInteractionTransformer(nn.Module):
         """x [2B, T, input_feats] with persons stacked on dim 0 -> predicted noise, same shape (:577-616)."""
         if not x.is_cuda:
             raise RuntimeError("hig_b200.MotionInteractionTransformer runs on CUDA only: there is no CPU fallback")
+        text_index = None
         if self.cap_id:
             xf_proj, xf_out = self.get_class_embedding(text)
         elif xf_proj is None or xf_out is None:
-            xf_proj, xf_out = self.encode_text(text, x.device)
+            # (xf_out stays one row per DISTINCT caption here; the training engine shares a caption's K/V side between the
+            #  sequences that carry it, every other path expands it below)
+            xf_proj, xf_out, text_index = self._encode_unique(text, x.device)
+            if text_index is not None:
+                xf_proj = xf_proj.index_select(0, text_index)
         if length is None:
             length = [x.shape[1]] * x.shape[0]
         needs_grad = torch.is_grad_enabled() and (
@@ -261,8 +340,12 @@ class MotionInteractionTransformer(nn.Module):
             if self.precision == "bf16" and os.environ.get("HIG_TRAIN_ENGINE", "1") != "0":
                 # product training path: captured graphs over static buffers (train_engine.py)
                 from .train_engine import denoiser_forward_graph
-                return denoiser_forward_graph(self, x, timesteps, length, xf_proj, xf_out)
+                return denoiser_forward_graph(self, x, timesteps, length, xf_proj, xf_out, text_index=text_index)
+            if text_index is not None:
+                xf_out = xf_out.index_select(0, text_index)
             from .autograd import denoiser_forward_with_grad     # fp32 validation mode: eager kernel schedule
             return denoiser_forward_with_grad(self, x, timesteps, length, xf_proj, xf_out)
+        if text_index is not None:
+            xf_out = xf_out.index_select(0, text_index)
         out = self.engine().forward(x, timesteps, length, xf_proj, xf_out)
         return out.to(x.dtype)

@@ -213,14 +213,17 @@ def refresh_special(module, W, C):
 class _Plan:
     """Static buffers + captured graphs of one (S, T, N) training shape."""
 
-    def __init__(self, te, S, T, N):
-        self.te, self.S, self.T, self.N = te, S, T, N
+    def __init__(self, te, S, T, N, U=None):
+        # U: rows of the text side when the batch's captions were deduplicated (xf_out holds U distinct captions, text_idx maps
+        # every sequence to its caption) — None: one text row per sequence
+        self.te, self.S, self.T, self.N, self.U = te, S, T, N, U
         eng, dev = te.eng, te.fp.param.device
         self.x = torch.zeros(S, T, eng.C, device=dev)
         self.t = torch.zeros(S, device=dev, dtype=torch.int64)
         self.len = torch.zeros(S, device=dev, dtype=torch.int32)
         self.xf_proj = torch.zeros(S, eng.E, device=dev)
-        self.xf_out = torch.zeros(S, N, te.module.text_latent_dim, device=dev)
+        self.xf_out = torch.zeros(U or S, N, te.module.text_latent_dim, device=dev)
+        self.text_idx = torch.zeros(S, device=dev, dtype=torch.int64) if U else None
         self.d_eps = torch.zeros(S, T, eng.C, device=dev)
         self.saved = None
         self.fwd_graph = None
@@ -251,16 +254,21 @@ class _Plan:
         st.ss = new(S, W["n_styl"] * 2 * D, dtype=f32)
         G(st.semb, W["emb.w"], bias=W["emb.b"], out_f32=st.ss)
         # ---- text K/V side of every layer's cross attention (:155-161)
+        # (a caption's K/V side does not depend on the motion: with deduplicated captions it is computed once per distinct
+        #  caption — SU rows instead of S — and its A matrices are handed to the sequences by index)
         Dt = self.xf_out.shape[2]
-        st.xf = self.xf_out.view(S * N, Dt)
+        SU = self.U or S
+        st.xf = self.xf_out.view(SU * N, Dt)
         st.tn, st.kv, st.a_text = [], [], []
         for i in range(L):
             p = f"l{i}.ca."
-            tn = ops.ln_film_silu(st.xf, W[p + "tln.w"], W[p + "tln.b"], new(S * N, Dt))
-            kv = new(S * N, 2 * D)
+            tn = ops.ln_film_silu(st.xf, W[p + "tln.w"], W[p + "tln.b"], new(SU * N, Dt))
+            kv = new(SU * N, 2 * D)
             G(tn, W[p + "kv.w"], bias=W[p + "kv.b"], out_bf16=kv)
-            a = new(S, H, HEAD_DIM, HEAD_DIM)
-            ops.eff_attn(ops.ATTN_KV_ONLY, S, N, H, k=kv[:, :D], v=kv[:, D:], a_out=a)
+            a = new(SU, H, HEAD_DIM, HEAD_DIM)
+            ops.eff_attn(ops.ATTN_KV_ONLY, SU, N, H, k=kv[:, :D], v=kv[:, D:], a_out=a)
+            if self.U:
+                a = torch.index_select(a, 0, self.text_idx)
             st.tn.append(tn); st.kv.append(kv); st.a_text.append(a)
         # ---- motion embedding (:593-602)
         st.xa = torch.zeros(tok, eng.CP, device=dev, dtype=bf)
@@ -379,7 +387,7 @@ class _Plan:
 
         pending_gb = []
 
-        def bcast(region2w):
+        def bcast(region2w, S=S):
             """[2W] parameter-gradient region as a stride-0 [S, 2W] view: ln_film_silu_bwd accumulates every sequence's
             (dgamma | dbeta) partials straight into the parameter gradient.  Deterministic mode: per-sequence partials,
             column-summed in a fixed order by flush_gb()."""
@@ -396,7 +404,8 @@ class _Plan:
 
         fp.grad[:fp.n_den].zero_()
         d_ss = torch.zeros_like(st.ss)
-        d_xf = torch.zeros(S * N, st.xf.shape[1], device=dev, dtype=f32)
+        SU = self.U or S
+        d_xf = torch.zeros(SU * N, st.xf.shape[1], device=dev, dtype=f32)
 
         # ---------------- output heads: eps = out(h[:,1:]) / out2(h[:,0])  (:613-616)
         d_eps = self.d_eps.view(tok, C)
@@ -471,14 +480,16 @@ class _Plan:
                 ops.eff_attn_bwd(ops.ATTN_Q_ONLY, S, T, H, q=blk["q"], a_in=st.a_text[li], dy=d_y, dq=d_q, dA=dA)
                 d_n = linear_bwd(d_q, blk["n"], W[f"l{li}.ca.q.w"], gv[mp + "query.weight"], gv[mp + "query.bias"])
                 pre_ln_bwd(blk, d_n, pfx, mp)
+                if self.U:       # sequences that share a caption: their dA add up
+                    dA = torch.zeros(SU, H, HEAD_DIM, HEAD_DIM, device=dev, dtype=f32).index_add_(0, self.text_idx, dA)
                 kv = st.kv[li]
-                d_kv = new(S * N, 2 * D)
-                ops.eff_attn_bwd(ops.ATTN_KV_ONLY, S, N, H, k=kv[:, :D], v=kv[:, D:], dk=d_kv[:, :D], dv=d_kv[:, D:], dA=dA)
+                d_kv = new(SU * N, 2 * D)
+                ops.eff_attn_bwd(ops.ATTN_KV_ONLY, SU, N, H, k=kv[:, :D], v=kv[:, D:], dk=d_kv[:, :D], dv=d_kv[:, D:], dA=dA)
                 Dt = st.xf.shape[1]
                 d_tn = linear_bwd(d_kv, st.tn[li], W[f"l{li}.ca.kv.w"], greg(mp + "key.weight", 2 * D * Dt, (2 * D, Dt)),
                                   greg(mp + "key.bias", 2 * D, (2 * D,)))
                 ops.ln_film_silu_bwd(st.xf, W[pfx + ".tln.w"], W[pfx + ".tln.b"], d_tn, d_xf, N, dx_accumulate=True,
-                                     d_gb=bcast(greg(mp + "text_norm.weight", 2 * Dt, (2 * Dt,))))
+                                     d_gb=bcast(greg(mp + "text_norm.weight", 2 * Dt, (2 * Dt,)), SU))
             else:
                 qkv = blk["qkv"]
                 d_qkv = new(tok, 3 * D)
@@ -527,7 +538,7 @@ class _Plan:
         d_h0 = ops.act_bwd(st.h0, d_te_h, ops.ACT_SILU, new(S, E))
         ops.colsum(d_h0, gv["time_embed.0.bias"])
         wgrad(d_h0, st.temb, gv["time_embed.0.weight"])
-        self.results = (d_emb, d_xf.view(S, N, -1))
+        self.results = (d_emb, d_xf.view(SU, N, -1))
         yield seg
 
     # ------------------------------------------------------------------------------------------ execution
@@ -590,14 +601,14 @@ class TrainEngine:
         self.pool = torch.cuda.graph_pool_handle()
         self.last = None
 
-    def plan(self, S, T, N):
+    def plan(self, S, T, N, U=None):
         # the kernel-selection knobs are baked into the captured graphs
-        key = (S, T, N) + tuple(os.environ.get(k, "") for k in ("HIG_DETERMINISTIC", "HIG_TRAIN_FUSED_ATTN", "HIG_TRAIN_GRAPH"))
+        key = (S, T, N, U) + tuple(os.environ.get(k, "") for k in ("HIG_DETERMINISTIC", "HIG_TRAIN_FUSED_ATTN", "HIG_TRAIN_GRAPH"))
         p = self.plans.get(key)
         if p is None:
             if len(self.plans) >= 3:      # each plan pins its saved activations: keep a few shapes only
                 self.plans.pop(next(iter(self.plans)))
-            p = self.plans[key] = _Plan(self, S, T, N)
+            p = self.plans[key] = _Plan(self, S, T, N, U)
         return p
 
     def refresh(self):
@@ -620,7 +631,7 @@ class DenoiserGraphFn(torch.autograd.Function):
     denoiser parameter (views of the flat gradient buffer, or — FlatParams.direct — written in place and not returned)."""
 
     @staticmethod
-    def forward(ctx, module, x, timesteps, length, xf_proj, xf_out, *params):
+    def forward(ctx, module, x, timesteps, length, xf_proj, xf_out, text_index, *params):
         te = train_engine(module)
         S, T, C = x.shape
         if S % 2:
@@ -628,12 +639,23 @@ class DenoiserGraphFn(torch.autograd.Function):
         if T > module.num_frames:
             raise ValueError(f"T={T} exceeds num_frames={module.num_frames}")
         te.refresh()
-        plan = te.plan(S, T, xf_out.shape[1])
+        U = None
+        if text_index is not None:           # xf_out holds distinct captions; pad their count to a bucket of 16 (graph shapes)
+            U = -(-xf_out.shape[0] // 16) * 16
+        elif xf_out.shape[0] != S:
+            raise ValueError("xf_out must have one row per sequence unless text_index maps the sequences to its rows")
+        plan = te.plan(S, T, xf_out.shape[1], U)
         plan.x.copy_(x.detach())
         plan.t.copy_(timesteps.detach().to(torch.int64))
         plan.len.copy_(length.to(device=x.device, dtype=torch.int32).clamp(min=0, max=T))
         plan.xf_proj.copy_(xf_proj.detach())
-        plan.xf_out.copy_(xf_out.detach())
+        if U:
+            plan.xf_out[:xf_out.shape[0]].copy_(xf_out.detach())
+            plan.text_idx.copy_(text_index)
+            ctx.n_text = xf_out.shape[0]
+        else:
+            plan.xf_out.copy_(xf_out.detach())
+            ctx.n_text = S
         eps = plan.forward()
         ctx.plan, ctx.te = plan, te
         te.last = plan
@@ -671,13 +693,23 @@ class DenoiserGraphFn(torch.autograd.Function):
             grads = [None] * n_den
         else:
             grads = [fp._view(fp.grad, n) for n in fp.names[:n_den]]
-        return (None, None, None, None, d_xf_proj.clone(), d_xf_out.clone(), *grads)
+        return (None, None, None, None, d_xf_proj.clone(), d_xf_out[:ctx.n_text].clone(), None, *grads)
 
 
-def denoiser_forward_graph(module, x, timesteps, length, xf_proj, xf_out):
+def denoiser_forward_graph(module, x, timesteps, length, xf_proj, xf_out, text_index=None):
+    """text_index (LongTensor [S], optional): xf_out holds the batch's DISTINCT captions, sequence s uses row text_index[s]."""
     if not x.is_cuda:
         raise RuntimeError("hig_b200: the denoiser runs on CUDA only (no CPU fallback)")
     fp = flat_params(module)
     params = fp.params[:fp.n_den_params]
     ln = torch.as_tensor(length).reshape(-1)
-    return DenoiserGraphFn.apply(module, x.float(), timesteps, ln, xf_proj.float(), xf_out.float(), *params).to(x.dtype)
+    if text_index is not None:
+        text_index = torch.as_tensor(text_index, device=x.device, dtype=torch.int64).reshape(-1)
+        deterministic = os.environ.get("HIG_DETERMINISTIC", "0") not in ("", "0")
+        if text_index.numel() != x.shape[0]:
+            raise ValueError("text_index needs one entry per sequence")
+        if deterministic or os.environ.get("HIG_TRAIN_TEXT_DEDUP", "1") == "0" or -(-xf_out.shape[0] // 16) * 16 >= x.shape[0]:
+            # nothing to share (or bit-reproducible mode: the shared dA would be summed with atomics): one row per sequence
+            xf_out, text_index = xf_out.index_select(0, text_index), None
+    return DenoiserGraphFn.apply(module, x.float(), timesteps, ln, xf_proj.float(), xf_out.float(), text_index,
+                                 *params).to(x.dtype)

@@ -290,3 +290,76 @@ def test_reference_train_py_control_flow(cuda, tmp_path):
     assert tr2.opt_encoder.step_count == it2
     ck = torch.load(tmp_path / "latest.tar", map_location="cpu")
     assert ck["total_it"] == it2 and set(ck) == {"opt_encoder", "ep", "total_it", "encoder"}
+
+
+@pytest.mark.parametrize("tf32", [False, True])
+def test_graphed_text_stack_matches_eager_autograd(cuda, monkeypatch, tf32):
+    """Training with captions: the trainable half of the text stack replayed as CUDA graphs (forward + backward per
+    caption-count bucket) gives the outputs and parameter gradients of the eager torch.autograd path, on repeated calls with
+    different caption sets in the same bucket, and padding rows leave no gradient behind."""
+    monkeypatch.setenv("HIG_CLIP_STUB", "1")
+    monkeypatch.setenv("HIG_TEXT_TF32", "1" if tf32 else "0")     # bf16 mode's default: TF32 GEMMs in the captured encoder
+    tol = (5e-3, 3e-2) if tf32 else (1e-5, 1e-4)
+    m = _model(cuda, layers=1, cap_id=False)
+    m.train()
+    caps_a = ["a person shakes hands with another person", "a person waves", "a person hugs another person",
+              "a person waves", "a person kicks"]
+    caps_b = ["two people walk towards each other", "a person points at another person", "a person waves"]
+    text_params = [p for n, p in m.named_parameters() if n.startswith(("text_pre_proj", "textTransEncoder", "text_ln", "text_proj"))]
+    assert text_params
+
+    def run(caps, graphed):
+        monkeypatch.setenv("HIG_TEXT_GRAPH", "1" if graphed else "0")
+        for p in text_params:
+            p.grad = None
+        xf_proj, xf_out = m.encode_text(caps, cuda)
+        g = torch.Generator(device="cpu").manual_seed(3)
+        w1 = torch.randn(xf_proj.shape, generator=g).to(cuda)
+        w2 = torch.randn(xf_out.shape, generator=g).to(cuda)
+        ((xf_proj * w1).sum() + (xf_out * w2).sum()).backward()
+        return xf_proj.detach().clone(), xf_out.detach().clone(), [p.grad.clone() for p in text_params]
+
+    for caps in (caps_a, caps_b, caps_a):
+        pe, oe, ge = run(caps, False)
+        pg, og, gg = run(caps, True)
+        assert pg.shape == pe.shape and og.shape == oe.shape
+        assert rel(pg, pe) < tol[0] and rel(og, oe) < tol[0]
+        for a, b in zip(gg, ge):
+            assert rel(a, b) < tol[1]
+    assert len(m.__dict__["_text_graphs"]) == 1          # one capture served all three calls (same bucket of 16)
+
+
+def test_shared_caption_text_side_matches_one_row_per_sequence(cuda):
+    """Training with captions: xf_out handed over as DISTINCT captions + an index per sequence (a caption's K/V side is
+    computed once and its dA summed over the sequences that carry it) against the same call with one text row per sequence."""
+    import weights
+    from hig_b200.train_engine import denoiser_forward_graph
+    L, S, T, U = 2, 24, 24, 3
+    m = _model(cuda, layers=L, cap_id=True)
+    m.cap_id = False
+    m.train()
+    inp = weights.make_inputs(21, S, T, n_text=77, lengths=[24, 20, 7] * 8)
+    g = lambda k: inp[k].to(cuda)
+    tgt = weights.make_noise(21, 0, S, T)[0].to(cuda)
+    idx = torch.tensor([(3 * i + i // 5) % U for i in range(S)], device=cuda)
+    res = {}
+    for shared in (True, False):
+        m.zero_grad(set_to_none=True)
+        xfo_u = g("xf_out")[:U].clone().requires_grad_(True)
+        xfp = g("xf_proj").requires_grad_(True)
+        if shared:
+            pred = denoiser_forward_graph(m, g("x"), g("t"), g("length"), xfp, xfo_u, text_index=idx)
+        else:
+            pred = denoiser_forward_graph(m, g("x"), g("t"), g("length"), xfp, xfo_u.index_select(0, idx))
+        ((pred - tgt) ** 2).mean().backward()
+        res[shared] = (pred.detach().clone(), xfp.grad.clone(), xfo_u.grad.clone(),
+                       {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    a, b = res[True], res[False]
+    assert a[2].shape == (U, 77, m.text_latent_dim)
+    assert torch.equal(a[0], b[0])                    # the forward values are the same numbers, computed once instead of 8 times
+    assert rel(a[1], b[1]) < 1e-3 and rel(a[2], b[2]) < 2e-2
+    # (key.bias: its K half is analytically zero — a constant added along time leaves the time softmax unchanged)
+    worst = max((rel(a[3][n], b[3][n]), n) for n in b[3] if b[3][n].norm() > 1e-7 and not n.endswith("key.bias"))
+    assert worst[0] < 2e-2, worst
+    te = m._hig_train_engine
+    assert any(p.U == 16 for p in te.plans.values()) and any(p.U is None for p in te.plans.values())
