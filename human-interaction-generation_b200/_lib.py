@@ -58,6 +58,8 @@ SIGNATURES = {
     "hig_gemm_bf16_splitk": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
     "hig_gemm_bf16_t": [c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                         c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
+    "hig_gemm_bf16_fused": [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                            c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
     "hig_transpose": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
                       c_void_p],
     "hig_colsum": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
@@ -67,6 +69,9 @@ SIGNATURES = {
                              c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
     "hig_eff_attn_bwd": [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                          c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "hig_eff_attn_bwd_sums": [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                              c_void_p, c_void_p, c_void_p],
     "hig_mha_attention": [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "hig_masked_mse": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                        c_void_p],

@@ -287,26 +287,6 @@ int colsum(const void* in, int dtype, int M, int N, int ld, float* out, cudaStre
 // elementwise activation forward / backward (exact erf GELU :257, SiLU :476/:77); also a plain cast when act == 0.
 //   fwd: out = act(x)            bwd: dx = dy * act'(x)   (x = the saved pre-activation)
 // ------------------------------------------------------------------------------------------------
-HIG_DEVICE float act_fwd_f(float v, int act) {
-  if (act == 1) return gelu_as_f(v);                     // erf to 1.5e-7 absolute (Abramowitz & Stegun 7.1.26): exact-GELU semantics
-  if (act == 2) return __fdividef(v, 1.0f + __expf(-v));
-  if (act == 3) return v / (1.0f + expf(-1.702f * v));   // QuickGELU of CLIP's text transformer MLP: x sigmoid(1.702 x)
-  return v;
-}
-HIG_DEVICE float act_grad_f(float v, int act) {
-  if (act == 1) {
-    // the kernel was instruction-bound on erff + expf (84 % issue-active, 40 us for 143 MB): A&S erf + fast exp
-    const float cdf = 0.5f * (1.0f + erf_as_f(v * 0.70710678118654752440f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
-    return fmaf(v, pdf, cdf);
-  }
-  if (act == 2) {
-    const float s = __fdividef(1.0f, 1.0f + __expf(-v));
-    return s * fmaf(v, 1.0f - s, 1.0f);
-  }
-  return 1.0f;
-}
-
 // 8 elements per thread and iteration (16 / 32-byte accesses); `n8` full groups, the < 8-element tail goes scalar
 template <typename TIn, typename TOut>
 __global__ void act_fwd_kernel(const TIn* __restrict__ x, long long n, int act, TOut* __restrict__ out, int vec) {

@@ -209,6 +209,13 @@ int hig_gemm_bf16_t(int trans_a, int trans_b, const void* A, int lda, const void
                           ldo_bf16, split_k, static_cast<cudaStream_t>(stream));
 }
 
+int hig_gemm_bf16_fused(int trans_b, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                        int act, void* out_bf16, int ldo_bf16, void* out_pre_bf16, int ldo_pre, const void* gate_bf16,
+                        int ld_gate, int gate_act, void* stream) {
+  return hig::gemm_bf16_fused(trans_b, A, lda, W, ldw, M, N, K, bias, act, out_bf16, ldo_bf16, out_pre_bf16, ldo_pre,
+                              gate_bf16, ld_gate, gate_act, static_cast<cudaStream_t>(stream));
+}
+
 int hig_transpose(const void* in, int in_dtype, int M, int N, int ld_in, void* outT, int ld_t, void* copy, int ld_c,
                   int out_dtype, float* colsum, int rows_zero_mod, void* stream) {
   return hig::transpose(in, in_dtype, M, N, ld_in, outT, ld_t, copy, ld_c, out_dtype, colsum, rows_zero_mod,
@@ -241,7 +248,15 @@ int hig_eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void
                      const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
                      const int* length, int S, int T, int H, int pair_shift, int dtype, void* stream) {
   return hig::eff_attn_bwd(mode, q, ldq, k, v, ldkv, a_in, dy, lddy, dq, lddq, dk, dv, lddkv, dA, length, S, T, H,
-                           pair_shift, dtype, static_cast<cudaStream_t>(stream));
+                           pair_shift, dtype, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int hig_eff_attn_bwd_sums(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
+                          const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
+                          const int* length, int S, int T, int H, int pair_shift, int dtype, float* q_sum, float* k_sum,
+                          float* v_sum, void* stream) {
+  return hig::eff_attn_bwd(mode, q, ldq, k, v, ldkv, a_in, dy, lddy, dq, lddq, dk, dv, lddkv, dA, length, S, T, H,
+                           pair_shift, dtype, q_sum, k_sum, v_sum, static_cast<cudaStream_t>(stream));
 }
 
 int hig_mha_attention(const void* q, const void* k, const void* v, int ld, void* out, int ldo, int B, int N, int H,

@@ -23,7 +23,8 @@ namespace hig {
 
 int eff_attn_bwd_tc(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
                     const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
-                    const int* length, int S, int T, int H, int pair_shift, cudaStream_t stream);
+                    const int* length, int S, int T, int H, int pair_shift, float* q_sum, float* k_sum, float* v_sum,
+                    cudaStream_t stream);
 
 constexpr int BW_HD = 64;
 constexpr int BW_LD = 65;       // padded fp32 row
@@ -208,9 +209,20 @@ eff_attn_bwd_kernel(int mode, const T* __restrict__ q, int ldq, const T* __restr
   }
 }
 
+// bias-gradient column sums of dQ / dK / dV as separate passes (the kernels that do not fuse them)
+static int attn_bwd_sums(bool do_q, bool do_kv, const void* dq, int lddq, const void* dk, const void* dv, int lddkv, int rows,
+                         int width, int dtype, float* q_sum, float* k_sum, float* v_sum, cudaStream_t stream) {
+  int rc = HIG_OK;
+  if (do_q && q_sum) rc = colsum(dq, dtype, rows, width, lddq, q_sum, stream);
+  if (rc == HIG_OK && do_kv && k_sum) rc = colsum(dk, dtype, rows, width, lddkv, k_sum, stream);
+  if (rc == HIG_OK && do_kv && v_sum) rc = colsum(dv, dtype, rows, width, lddkv, v_sum, stream);
+  return rc;
+}
+
 int eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
                  const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
-                 const int* length, int S, int T, int H, int pair_shift, int dtype, cudaStream_t stream) {
+                 const int* length, int S, int T, int H, int pair_shift, int dtype, float* q_sum, float* k_sum,
+                 float* v_sum, cudaStream_t stream) {
   if (mode < 0 || mode > 3) return set_error(HIG_ERR_INVALID, "eff_attn_bwd: bad mode");
   if (S <= 0 || T <= 0 || H <= 0) return set_error(HIG_ERR_INVALID, "eff_attn_bwd: empty shape");
   if (T > 256) return set_error(HIG_ERR_UNSUPPORTED, "eff_attn_bwd: T > 256 not supported");
@@ -226,8 +238,12 @@ int eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void* v,
     // tensor-core kernel (eff_attn_bwd_tc.cu); HIG_ATTN_BWD_TC=0 keeps the CUDA-core kernel below for A/B runs
     static const bool use_tc = []() { const char* ev = getenv("HIG_ATTN_BWD_TC"); return !(ev && ev[0] == '0'); }();
     if (use_tc) {
+      // (bit-reproducible mode: the fused column sums are atomics in CTA order — take them with hig::colsum below instead)
+      const bool fuse = !deterministic();
       const int rc = eff_attn_bwd_tc(mode, q, ldq, k, v, ldkv, a_in, dy, lddy, dq, lddq, dk, dv, lddkv, dA, length, S, T,
-                                     H, pair_shift, stream);
+                                     H, pair_shift, fuse ? q_sum : nullptr, fuse ? k_sum : nullptr, fuse ? v_sum : nullptr,
+                                     stream);
+      if (rc == HIG_OK && !fuse) return attn_bwd_sums(do_q, do_kv, dq, lddq, dk, dv, lddkv, S * T, H * BW_HD, dtype, q_sum, k_sum, v_sum, stream);
       if (rc != HIG_ERR_UNSUPPORTED) return rc;
     }
   }
@@ -258,7 +274,7 @@ int eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void* v,
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("eff_attn_bwd launch: ") + cudaGetErrorString(e));
   count_launch();
-  return HIG_OK;
+  return attn_bwd_sums(do_q, do_kv, dq, lddq, dk, dv, lddkv, S * T, H * BW_HD, dtype, q_sum, k_sum, v_sum, stream);
 }
 
 }  // namespace hig

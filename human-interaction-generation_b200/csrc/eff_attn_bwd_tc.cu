@@ -94,7 +94,8 @@ eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, c
                        const __nv_bfloat16* __restrict__ v, int ldkv, const __nv_bfloat16* __restrict__ a_in,
                        const __nv_bfloat16* __restrict__ dy, int lddy, __nv_bfloat16* __restrict__ dq, int lddq,
                        __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int lddkv,
-                       float* __restrict__ dA_g, const int* __restrict__ length, int S, int T, int pair_shift) {
+                       float* __restrict__ dA_g, const int* __restrict__ length, int S, int T, int pair_shift,
+                       float* __restrict__ q_sum, float* __restrict__ k_sum, float* __restrict__ v_sum) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   const bool do_kv = (mode != 3), do_q = (mode != 2);
   const int TP = (T + 15) & ~15;
@@ -474,21 +475,50 @@ eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, c
       }
     }
   }
+  // column sums of the gradient tiles (the projections' bias gradients), optional: a thread stores the same 16-byte chunk
+  // (8 columns) of every row it handles, so the sums ride on the store loop; partials meet in fred[3][64]
+  const bool sums = (q_sum != nullptr) || (k_sum != nullptr) || (v_sum != nullptr);
+  if (sums && tid < 192) fred[tid] = 0.f;
   __syncthreads();
+
+  auto add8 = [](float (&acc)[8], const uint4& u) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      acc[2 * j] += f.x;
+      acc[2 * j + 1] += f.y;
+    }
+  };
+  auto flush8 = [&](float (&acc)[8], float* dst) {   // lanes with equal (lane & 7) own the same chunk: fold rows, then 8 lanes publish
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dst + lane * 8 + j, acc[j]);
+    }
+  };
 
   // ---------------------------------------------------------------- coalesced stores (16 bytes per lane)
   if (do_q) {
     __nv_bfloat16* og = dq + (size_t)s * T * lddq + h * TC_HD;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int i = tid; i < T * 8; i += TC_THREADS) {
       const int r = i >> 3, c = i & 7;
       uint4 u;
       asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(sQ + swz(r, c)));
       *reinterpret_cast<uint4*>(og + (size_t)r * lddq + c * 8) = u;
+      if (q_sum != nullptr) add8(acc, u);
     }
+    if (q_sum != nullptr) flush8(acc, fred);
   }
   if (do_kv) {
     __nv_bfloat16* okg = dk + (size_t)s_kv * T * lddkv + h * TC_HD;
     __nv_bfloat16* ovg = dv + (size_t)s_kv * T * lddkv + h * TC_HD;
+    float acck[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, accv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int i = tid; i < T * 8; i += TC_THREADS) {
       const int r = i >> 3, c = i & 7;
       uint4 u, w;
@@ -496,6 +526,17 @@ eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, c
       asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(sV + swz(r, c)));
       *reinterpret_cast<uint4*>(okg + (size_t)r * lddkv + c * 8) = u;
       *reinterpret_cast<uint4*>(ovg + (size_t)r * lddkv + c * 8) = w;
+      if (k_sum != nullptr) add8(acck, u);
+      if (v_sum != nullptr) add8(accv, w);
+    }
+    if (k_sum != nullptr) flush8(acck, fred + 64);
+    if (v_sum != nullptr) flush8(accv, fred + 128);
+  }
+  if (sums) {
+    __syncthreads();
+    if (tid < 192) {
+      float* dst = tid < 64 ? q_sum : (tid < 128 ? k_sum : v_sum);
+      if (dst != nullptr) atomicAdd(dst + h * TC_HD + (tid & 63), fred[tid]);
     }
   }
 }
@@ -504,7 +545,8 @@ eff_attn_bwd_tc_kernel(int mode, const __nv_bfloat16* __restrict__ q, int ldq, c
 // CUDA-core kernel of eff_attn_bwd.cu)
 int eff_attn_bwd_tc(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
                     const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
-                    const int* length, int S, int T, int H, int pair_shift, cudaStream_t stream) {
+                    const int* length, int S, int T, int H, int pair_shift, float* q_sum, float* k_sum, float* v_sum,
+                    cudaStream_t stream) {
   const bool do_kv = (mode != 3), do_q = (mode != 2);
   auto mis = [](const void* p, int ld) { return p != nullptr && ((reinterpret_cast<uintptr_t>(p) & 15) || (ld % 8)); };
   if (T > 256 || mis(q, ldq) || mis(k, ldkv) || mis(v, ldkv) || mis(dy, lddy) || mis(dq, lddq) || mis(dk, lddkv) ||
@@ -525,7 +567,8 @@ int eff_attn_bwd_tc(int mode, const void* q, int ldq, const void* k, const void*
   auto kern = (occ >= 3 && smem * 3 <= 227 * 1024) ? eff_attn_bwd_tc_kernel<3> : eff_attn_bwd_tc_kernel<2>;
   kern<<<dim3(H, S), TC_THREADS, smem, stream>>>(
       mode, (const bf*)q, ldq, (const bf*)k, (const bf*)v, ldkv, (const bf*)a_in, (const bf*)dy, lddy, (bf*)dq, lddq,
-      (bf*)dk, (bf*)dv, lddkv, dA, length, S, T, pair_shift);
+      (bf*)dk, (bf*)dv, lddkv, dA, length, S, T, pair_shift, do_q ? q_sum : nullptr, do_kv ? k_sum : nullptr,
+      do_kv ? v_sum : nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("eff_attn_bwd_tc launch: ") + cudaGetErrorString(e));
   count_launch();

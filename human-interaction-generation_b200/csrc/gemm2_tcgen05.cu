@@ -173,7 +173,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int gc0 = n_blk * G2_BN + cbase;
       EpiLane L;
       epi_setup(L, slab, ep, row0, M, lane);
-      if (KIND != EPI_GENERIC) {
+      if (KIND != EPI_GENERIC && KIND != EPI_FUSED) {
         // specialised kinds (N % 32 == 0, 16-byte friendly): bias / residual of chunk k+1 are fetched while chunk k
         // is transposed and stored; chunk 0's are in flight before the accumulator is even ready.
         EpiPre P[2];
@@ -196,7 +196,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           uint32_t r[32];
           tmem_ld_32x32(taddr + c, r);
           tmem_ld_wait();
-          if (gc0 + c < N && ep.act != 100) epilogue_chunk<EPI_GENERIC>(r, L, slab, ep, row0, M, gc0 + c, N, vec_ok, lane);
+          if (gc0 + c < N && ep.act != 100) epilogue_chunk<KIND>(r, L, slab, ep, row0, M, gc0 + c, N, vec_ok, lane);
         }
       }
       tc_fence_before();
@@ -244,6 +244,7 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int 
     case EPI_RES_F32_BF16: return launch_2cta_kind<EPI_RES_F32_BF16>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
     case EPI_RES_H: return launch_2cta_kind<EPI_RES_H>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
     case EPI_RES_H_BF16: return launch_2cta_kind<EPI_RES_H_BF16>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
+    case EPI_FUSED: return launch_2cta_kind<EPI_FUSED>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
     default: return launch_2cta_kind<EPI_GENERIC>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
   }
 }
@@ -252,6 +253,10 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int 
 int launch_gemm_2cta_t(int ta, int tb, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
                        const GemmEpilogue& ep, int vec_ok, int num_sms, int k_splits, cudaStream_t stream) {
   int kind = (ep.act >= 100) ? EPI_GENERIC : classify_epilogue(ep, vec_ok, N);
+  if (kind == EPI_FUSED) {
+    if (ta || !tb) return set_error(HIG_ERR_UNSUPPORTED, "gemm_fused: transposed form is trans_b only");
+    return launch_2cta_kind<EPI_FUSED, 0, 1>(tmA, tmB, M, N, K, ep, vec_ok, num_sms, k_splits, stream);
+  }
   if (kind != EPI_BF16 && kind != EPI_RES_F32) kind = EPI_GENERIC;
 #define HIG_G2T(KD)                                                                                                   \
   do {                                                                                                                \

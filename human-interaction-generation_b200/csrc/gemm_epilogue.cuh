@@ -21,6 +21,15 @@ struct GemmEpilogue {
   int ldr16;
   __half* out16;
   int ldo16;
+  // training fusions (generic kind, vector path only; null = off):
+  //   out_pre: bf16 copy of the PRE-activation value (the activation is then applied to that stored, rounded value — what a
+  //            separate activation kernel reading it back would see);  gate: the result is multiplied by act'(gate[row, col])
+  //            (backward of an activation fused into the GEMM that produces its incoming gradient)
+  __nv_bfloat16* out_pre = nullptr;
+  int ldo_pre = 0;
+  const __nv_bfloat16* gate = nullptr;
+  int ld_gate = 0;
+  int gate_act = 0;
 };
 
 // two fp32 -> packed fp16x2 with saturation to +-65504 (no inf in the fp16 residual stream)
@@ -90,7 +99,9 @@ enum EpiKind : int {
   EPI_RES_F32 = 3,      // bias + fp32 residual -> fp32       (block output projection, in place on the stream)
   EPI_RES_F32_BF16 = 4, // ... and a bf16 copy of the stream  (feeds the FFN / output heads)
   EPI_RES_H = 5,        // bias + fp16 residual -> fp16       (product path: the residual stream is stored in fp16)
-  EPI_RES_H_BF16 = 6    // ... and a bf16 copy of the stream
+  EPI_RES_H_BF16 = 6,   // ... and a bf16 copy of the stream
+  EPI_FUSED = 7         // generic + the training fusions (out_pre / gate / erf-form GELU); kept apart so the generic kind
+                        // — every split-K weight gradient runs it — does not carry their registers and branches
 };
 
 // Epilogue of one 32-row x 32-column fp32 chunk owned by one warp.
@@ -111,6 +122,8 @@ struct EpiLane {
   const float* res;
   __half* oh;
   const __half* resh;
+  __nv_bfloat16* pre;
+  const __nv_bfloat16* gate;
 };
 
 HIG_DEVICE void epi_setup(EpiLane& L, uint32_t slab, const GemmEpilogue& ep, int row0, int M, int lane) {
@@ -130,26 +143,37 @@ HIG_DEVICE void epi_setup(EpiLane& L, uint32_t slab, const GemmEpilogue& ep, int
   L.res = ep.residual ? ep.residual + r * ep.ldr + L.cg * 4 : nullptr;
   L.oh = ep.out16 ? ep.out16 + r * ep.ldo16 + L.cg * 4 : nullptr;
   L.resh = ep.residual16 ? ep.residual16 + r * ep.ldr16 + L.cg * 4 : nullptr;
+  L.pre = ep.out_pre ? ep.out_pre + r * ep.ldo_pre + L.cg * 4 : nullptr;
+  L.gate = ep.gate ? ep.gate + r * ep.ld_gate + L.cg * 4 : nullptr;
 }
 
 template <int KIND>
 HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const EpiLane& L, uint32_t slab, const GemmEpilogue& ep,
                                int row0, int M, int col0, int N, int vec_ok, int lane) {
+  constexpr bool GEN = (KIND == EPI_GENERIC || KIND == EPI_FUSED);   // runtime-flag kinds
   const int gcol = col0 + L.cg * 4;
   // warp-uniform: the whole chunk takes the vector path or the scalar one
-  const bool vec = (KIND != EPI_GENERIC) || (vec_ok && (col0 + 32 <= N));
-  const bool has_res = (KIND == EPI_GENERIC) ? (ep.residual != nullptr) : (KIND >= EPI_RES_F32);
+  const bool vec = (!GEN) || (vec_ok && (col0 + 32 <= N));
+  const bool has_res = GEN ? (ep.residual != nullptr) : (KIND >= EPI_RES_F32);
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 rs[8];
+  uint2 gt[8];
   if (vec) {
-    if (KIND != EPI_GENERIC || ep.bias) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol));
+    if (!GEN || ep.bias) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol));
+    if (KIND == EPI_FUSED && L.gate) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        gt[i] = make_uint2(0u, 0u);
+        if ((L.row_ok >> i) & 1u) gt[i] = __ldg(reinterpret_cast<const uint2*>(L.gate + (size_t)(4 * i) * ep.ld_gate + col0));
+      }
+    }
     if (has_res) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if ((L.row_ok >> i) & 1u) {
           const float* rp = L.res + (size_t)(4 * i) * ep.ldr + col0;
-          if (KIND == EPI_GENERIC && ep.res_row_mod > 0)
+          if (GEN && ep.res_row_mod > 0)
             rp = ep.residual + (size_t)((L.row_first + 4 * i) % ep.res_row_mod) * ep.ldr + gcol;
           rs[i] = __ldg(reinterpret_cast<const float4*>(rp));
         }
@@ -172,7 +196,7 @@ HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const EpiLane& L, uint32
 #pragma unroll
       for (int i = 0; i < 8; ++i) { v[i].x += rs[i].x; v[i].y += rs[i].y; v[i].z += rs[i].z; v[i].w += rs[i].w; }
     }
-    if (KIND == EPI_GENERIC && L.resh) {
+    if (GEN && L.resh) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if ((L.row_ok >> i) & 1u) {
@@ -182,7 +206,30 @@ HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const EpiLane& L, uint32
         }
       }
     }
-    const int act = (KIND == EPI_GENERIC) ? ep.act : (KIND == EPI_BF16_GELU ? 1 : 0);
+    if (KIND == EPI_FUSED && L.pre) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint2 h = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+        if ((L.row_ok >> i) & 1u) *reinterpret_cast<uint2*>(L.pre + (size_t)(4 * i) * ep.ldo_pre + col0) = h;
+        const float2 a = unpack_bf16x2(h.x), b = unpack_bf16x2(h.y);
+        v[i] = make_float4(a.x, a.y, b.x, b.y);
+      }
+    }
+    const int act = GEN ? ep.act : (KIND == EPI_BF16_GELU ? 1 : 0);
+    if (KIND == EPI_FUSED && act == 3) {        // erf-form GELU (Abramowitz & Stegun), as hig_act_fwd computes it
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i].x = gelu_as_f(v[i].x); v[i].y = gelu_as_f(v[i].y); v[i].z = gelu_as_f(v[i].z); v[i].w = gelu_as_f(v[i].w);
+      }
+    }
+    if (KIND == EPI_FUSED && L.gate) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 a = unpack_bf16x2(gt[i].x), b = unpack_bf16x2(gt[i].y);
+        v[i].x *= act_grad_f(a.x, ep.gate_act); v[i].y *= act_grad_f(a.y, ep.gate_act);
+        v[i].z *= act_grad_f(b.x, ep.gate_act); v[i].w *= act_grad_f(b.y, ep.gate_act);
+      }
+    }
     if (act == 1) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -194,17 +241,17 @@ HIG_DEVICE void epilogue_chunk(const uint32_t (&r)[32], const EpiLane& L, uint32
         v[i].x = silu_f(v[i].x); v[i].y = silu_f(v[i].y); v[i].z = silu_f(v[i].z); v[i].w = silu_f(v[i].w);
       }
     }
-    const bool w32 = (KIND == EPI_GENERIC) ? (L.o32 != nullptr) : (KIND >= EPI_RES_F32);
-    const bool w16 = (KIND == EPI_GENERIC) ? (L.o16 != nullptr) : (KIND != EPI_RES_F32);
+    const bool w32 = GEN ? (L.o32 != nullptr) : (KIND >= EPI_RES_F32);
+    const bool w16 = GEN ? (L.o16 != nullptr) : (KIND != EPI_RES_F32);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if ((L.row_ok >> i) & 1u) {
-        if (KIND == EPI_GENERIC && L.oh)
+        if (GEN && L.oh)
           *reinterpret_cast<uint2*>(L.oh + (size_t)(4 * i) * ep.ldo16 + col0) =
               make_uint2(pack_f16x2_sat(v[i].x, v[i].y), pack_f16x2_sat(v[i].z, v[i].w));
         if (w32) {
           float* o = L.o32 + (size_t)(4 * i) * ep.ldo_f32 + col0;
-          if (KIND == EPI_GENERIC && ep.atomic) {
+          if (GEN && ep.atomic) {
             // one 16-byte vector reduction instead of four scalar atomics (split-K weight gradients)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[i].x), "f"(v[i].y), "f"(v[i].z),
                          "f"(v[i].w) : "memory");
@@ -293,6 +340,7 @@ HIG_DEVICE void epi_finish(const uint32_t (&r)[32], const EpiPre& P, const EpiLa
 
 // classify a runtime epilogue into the specialised kinds (host side)
 inline int classify_epilogue(const GemmEpilogue& ep, int vec_ok, int N) {
+  if (ep.out_pre || ep.gate || ep.act == 3) return EPI_FUSED;
   if (!vec_ok || (N % 32) != 0 || !ep.bias || ep.res_row_mod > 0 || ep.atomic) return EPI_GENERIC;
   if (ep.residual16 || ep.out16) {
     if (ep.residual16 && ep.out16 && !ep.residual && !ep.out_f32 && ep.act == 0)

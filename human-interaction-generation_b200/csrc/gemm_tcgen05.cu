@@ -306,13 +306,24 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   return HIG_OK;
 }
 
+// out_pre / gate extras of the training fusions: vector path only (the scalar edge path does not implement them)
+static int apply_fused(GemmEpilogue& ep, const GemmEpilogue& f, int vec_ok, int N) {
+  if (!f.out_pre && !f.gate) return HIG_OK;
+  auto bad = [](const void* p, int ld) { return p && ((reinterpret_cast<uintptr_t>(p) & 7) || (ld % 4)); };
+  if (!vec_ok || (N % 32) != 0 || bad(f.out_pre, f.ldo_pre) || bad(f.gate, f.ld_gate) || ep.atomic)
+    return set_error(HIG_ERR_UNSUPPORTED, "gemm_fused: needs N % 32 == 0, 8-byte aligned rows and no split-K");
+  if (f.gate && (f.gate_act < 1 || f.gate_act > 2)) return set_error(HIG_ERR_INVALID, "gemm_fused: gate_act must be 1 (GELU) or 2 (SiLU)");
+  ep.out_pre = f.out_pre; ep.ldo_pre = f.ldo_pre; ep.gate = f.gate; ep.ld_gate = f.ld_gate; ep.gate_act = f.gate_act;
+  return HIG_OK;
+}
+
 // split_k != 0: the K range is cut into slices that run as independent tiles and are combined with fp32 atomics into
 // out_f32 (which the caller has initialised: zeros, or a gradient to accumulate into).  Used by the weight-gradient
 // GEMMs, whose output is a handful of tiles while K = tokens is long.  split_k > 0 forces that many slices.
 static int gemm_bf16_impl(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                           const float* residual, int ldr, int res_row_mod, float* out_f32, int ldo_f32, void* out_bf16,
                           int ldo_bf16, int act, int split_k, cudaStream_t stream, const void* residual16 = nullptr,
-                          int ldr16 = 0, void* out16 = nullptr, int ldo16 = 0) {
+                          int ldr16 = 0, void* out16 = nullptr, int ldo16 = 0, const GemmEpilogue* fused = nullptr) {
   if (!A || !W || M <= 0 || N <= 0 || K <= 0) return set_error(HIG_ERR_INVALID, "gemm: null operand or empty shape");
   if (!out_f32 && !out_bf16 && !out16) return set_error(HIG_ERR_INVALID, "gemm: no output");
   if ((lda % 8) || (ldw % 8)) return set_error(HIG_ERR_INVALID, "gemm: lda/ldw must be multiples of 8 (TMA 16B rule)");
@@ -320,7 +331,7 @@ static int gemm_bf16_impl(const void* A, int lda, const void* W, int ldw, int M,
     return set_error(HIG_ERR_INVALID, "gemm: split-K accumulates raw products into out_f32 only");
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
     return set_error(HIG_ERR_INVALID, "gemm: operands must be 16-byte aligned");
-  if ((act < 0 || act > 2) && act != 100 && act != 101) return set_error(HIG_ERR_INVALID, "gemm: bad activation");
+  if ((act < 0 || act > 3) && act != 100 && act != 101) return set_error(HIG_ERR_INVALID, "gemm: bad activation");
 
   GemmEpilogue ep;
   ep.bias = bias; ep.residual = residual; ep.ldr = ldr; ep.res_row_mod = res_row_mod;
@@ -336,6 +347,10 @@ static int gemm_bf16_impl(const void* A, int lda, const void* W, int ldw, int M,
   if (residual && ((reinterpret_cast<uintptr_t>(residual) & 15) || (ldr % 4))) vec_ok = 0;
   if (out_f32 && ((reinterpret_cast<uintptr_t>(out_f32) & 15) || (ldo_f32 % 4))) vec_ok = 0;
   if (out_bf16 && ((reinterpret_cast<uintptr_t>(out_bf16) & 7) || (ldo_bf16 % 4))) vec_ok = 0;
+  if (fused) {
+    const int rc_f = apply_fused(ep, *fused, vec_ok, N);
+    if (rc_f) return rc_f;
+  }
   if (residual16 && ((reinterpret_cast<uintptr_t>(residual16) & 7) || (ldr16 % 4))) vec_ok = 0;
   if (out16 && ((reinterpret_cast<uintptr_t>(out16) & 7) || (ldo16 % 4))) vec_ok = 0;
 
@@ -361,6 +376,8 @@ static int gemm_bf16_impl(const void* A, int lda, const void* W, int ldw, int M,
     const int mn = ((M + 255) / 256) * ((N + 255) / 256);
     return launch_gemm_2cta(tmA, tmB, M, N, K, ep, vec_ok, num_sms(), pick_splits(mn, num_sms() / 2), stream);
   }
+  if (ep.out_pre || ep.gate || ep.act == 3)
+    return set_error(HIG_ERR_UNSUPPORTED, "gemm_fused: implemented on the CTA-pair kernel only (M >= 512, N >= 256)");
   const bool big_n = N > 128;
   int rc = get_tmap(A, M, K, lda, GEMM_BM, &tmA);
   if (rc) return rc;
@@ -400,12 +417,12 @@ int launch_gemm_2cta_t(int ta, int tb, const CUtensorMap& tmA, const CUtensorMap
 // Training path:  dW[n,k] = sum_m dY[m,n] X[m,k]  -> trans_a = trans_b = 1 (A = dY, W = X, contraction = tokens, split-K);
 //                 dX[m,k] = sum_n dY[m,n] W[n,k]  -> trans_b = 1 (A = dY K-major as stored, W = the weight as stored).
 // split_k != 0: fp32 atomic accumulation into out_f32 (caller initialises it); no bias / residual / bf16 output then.
-int gemm_bf16_t(int trans_a, int trans_b, const void* A, int lda, const void* W, int ldw, int M, int N, int K,
-                const float* bias, const float* residual, int ldr, float* out_f32, int ldo_f32, void* out_bf16,
-                int ldo_bf16, int split_k, cudaStream_t stream) {
+static int gemm_bf16_t_impl(int trans_a, int trans_b, const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                            const float* bias, const float* residual, int ldr, float* out_f32, int ldo_f32, void* out_bf16,
+                            int ldo_bf16, int act, int split_k, cudaStream_t stream, const GemmEpilogue* fused) {
   if (!trans_a && !trans_b)
-    return gemm_bf16_impl(A, lda, W, ldw, M, N, K, bias, residual, ldr, 0, out_f32, ldo_f32, out_bf16, ldo_bf16, 0,
-                          split_k, stream);
+    return gemm_bf16_impl(A, lda, W, ldw, M, N, K, bias, residual, ldr, 0, out_f32, ldo_f32, out_bf16, ldo_bf16, act,
+                          split_k, stream, nullptr, 0, nullptr, 0, fused);
   if (!A || !W || M <= 0 || N <= 0 || K <= 0) return set_error(HIG_ERR_INVALID, "gemm_t: null operand or empty shape");
   if (!out_f32 && !out_bf16) return set_error(HIG_ERR_INVALID, "gemm_t: no output");
   if ((lda % 8) || (ldw % 8)) return set_error(HIG_ERR_INVALID, "gemm_t: lda/ldw must be multiples of 8 (TMA 16B rule)");
@@ -417,13 +434,17 @@ int gemm_bf16_t(int trans_a, int trans_b, const void* A, int lda, const void* W,
   ep.bias = bias; ep.residual = residual; ep.ldr = ldr; ep.res_row_mod = 0;
   ep.out_f32 = out_f32; ep.ldo_f32 = ldo_f32;
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); ep.ldo_bf16 = ldo_bf16;
-  ep.act = 0; ep.atomic = split_k ? 1 : 0;
+  ep.act = act; ep.atomic = split_k ? 1 : 0;
   ep.residual16 = nullptr; ep.ldr16 = 0; ep.out16 = nullptr; ep.ldo16 = 0;
   int vec_ok = 1;
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) vec_ok = 0;
   if (residual && ((reinterpret_cast<uintptr_t>(residual) & 15) || (ldr % 4))) vec_ok = 0;
   if (out_f32 && ((reinterpret_cast<uintptr_t>(out_f32) & 15) || (ldo_f32 % 4))) vec_ok = 0;
   if (out_bf16 && ((reinterpret_cast<uintptr_t>(out_bf16) & 7) || (ldo_bf16 % 4))) vec_ok = 0;
+  if (fused) {
+    const int rc_f = apply_fused(ep, *fused, vec_ok, N);
+    if (rc_f) return rc_f;
+  }
   CUtensorMap tmA, tmB;
   int rc = trans_a ? get_tmap(A, K, M, lda, 64, &tmA) : get_tmap(A, M, K, lda, 128, &tmA);
   if (rc) return rc;
@@ -441,6 +462,29 @@ int gemm_bf16_t(int trans_a, int trans_b, const void* A, int lda, const void* W,
     ks = (k_blocks + per - 1) / per;
   }
   return launch_gemm_2cta_t(trans_a, trans_b, tmA, tmB, M, N, K, ep, vec_ok, num_sms(), ks, stream);
+}
+
+int gemm_bf16_t(int trans_a, int trans_b, const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                const float* bias, const float* residual, int ldr, float* out_f32, int ldo_f32, void* out_bf16,
+                int ldo_bf16, int split_k, cudaStream_t stream) {
+  return gemm_bf16_t_impl(trans_a, trans_b, A, lda, W, ldw, M, N, K, bias, residual, ldr, out_f32, ldo_f32, out_bf16,
+                          ldo_bf16, 0, split_k, stream, nullptr);
+}
+
+// Training fusions around an activation (models/interaction_transformer.py:261-264, the FFN's linear1 -> GELU -> linear2):
+//   forward :  pre = A W^T + bias -> out_pre (bf16);  out = act(pre as stored)                     (act 3: erf-form GELU)
+//   backward:  out = (A W) * act'(gate)   with W as stored (trans_b = 1), gate = the saved pre-activation
+int gemm_bf16_fused(int trans_b, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                    int act, void* out_bf16, int ldo_bf16, void* out_pre_bf16, int ldo_pre, const void* gate_bf16,
+                    int ld_gate, int gate_act, cudaStream_t stream) {
+  if (!out_bf16) return set_error(HIG_ERR_INVALID, "gemm_fused: out_bf16 required");
+  if (act != 0 && act != 1 && act != 2) return set_error(HIG_ERR_INVALID, "gemm_fused: act must be 0, 1 (GELU) or 2 (SiLU)");
+  if (!bias) return set_error(HIG_ERR_INVALID, "gemm_fused: bias required (pass zeros)");
+  GemmEpilogue f;
+  f.out_pre = reinterpret_cast<__nv_bfloat16*>(out_pre_bf16); f.ldo_pre = ldo_pre;
+  f.gate = reinterpret_cast<const __nv_bfloat16*>(gate_bf16); f.ld_gate = ld_gate; f.gate_act = gate_act;
+  return gemm_bf16_t_impl(0, trans_b, A, lda, W, ldw, M, N, K, bias, nullptr, 0, nullptr, 0, out_bf16, ldo_bf16,
+                          act == 1 ? 3 : act, 0, stream, &f);
 }
 
 int gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32, int ldo_f32,

@@ -70,6 +70,27 @@ HIG_DEVICE float gelu_fast_f(float v) {
 // exact (erf) GELU, as torch.nn.GELU() default
 HIG_DEVICE float gelu_erf_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
+// activations of the training kernels and their derivatives (act: 1 GELU erf-form, 2 SiLU, 3 QuickGELU)
+HIG_DEVICE float act_fwd_f(float v, int act) {
+  if (act == 1) return gelu_as_f(v);                     // erf to 1.5e-7 absolute (Abramowitz & Stegun 7.1.26): exact-GELU semantics
+  if (act == 2) return __fdividef(v, 1.0f + __expf(-v));
+  if (act == 3) return v / (1.0f + expf(-1.702f * v));   // QuickGELU of CLIP's text transformer MLP: x sigmoid(1.702 x)
+  return v;
+}
+HIG_DEVICE float act_grad_f(float v, int act) {
+  if (act == 1) {
+    // the kernel was instruction-bound on erff + expf (84 % issue-active, 40 us for 143 MB): A&S erf + fast exp
+    const float cdf = 0.5f * (1.0f + erf_as_f(v * 0.70710678118654752440f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
+    return fmaf(v, pdf, cdf);
+  }
+  if (act == 2) {
+    const float s = __fdividef(1.0f, 1.0f + __expf(-v));
+    return s * fmaf(v, 1.0f - s, 1.0f);
+  }
+  return 1.0f;
+}
+
 HIG_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

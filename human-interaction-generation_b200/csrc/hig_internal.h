@@ -110,6 +110,10 @@ int gemm_bf16_t(int trans_a, int trans_b, const void* A, int lda, const void* W,
                 const float* bias, const float* residual, int ldr, float* out_f32, int ldo_f32, void* out_bf16,
                 int ldo_bf16, int split_k, cudaStream_t stream);
 
+int gemm_bf16_fused(int trans_b, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                    int act, void* out_bf16, int ldo_bf16, void* out_pre_bf16, int ldo_pre, const void* gate_bf16,
+                    int ld_gate, int gate_act, cudaStream_t stream);
+
 int transpose(const void* in, int in_dtype, int M, int N, int ld_in, void* outT, int ld_t, void* copy, int ld_c,
               int out_dtype, float* colsum, int rows_zero_mod, cudaStream_t stream);
 
@@ -126,7 +130,8 @@ int ln_film_silu_bwd(const void* x, int x_dtype, int rows, int width, int rows_p
 
 int eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
                  const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
-                 const int* length, int S, int T, int H, int pair_shift, int dtype, cudaStream_t stream);
+                 const int* length, int S, int T, int H, int pair_shift, int dtype, float* q_sum, float* k_sum,
+                 float* v_sum, cudaStream_t stream);
 
 // ---- text conditioning path (text_ops.cu) ----
 int mha_attention(const void* q, const void* k, const void* v, int ld, void* out, int ldo, int B, int N, int H, int causal,

@@ -64,8 +64,9 @@ class UniformSampler:
         w = self.weights()
         p = w / np.sum(w)
         idx = np.random.choice(len(p), size=(batch_size,), p=p)
-        indices = th.from_numpy(idx).long().to(device)
-        weights = th.from_numpy(1 / (len(p) * p[idx])).float().to(device)
+        from .staging import stage            # pinned, asynchronous: a blocking .to(device) here stalls the training pipeline
+        indices = stage(th.from_numpy(idx), device, th.long)
+        weights = stage(th.from_numpy(1 / (len(p) * p[idx])), device, th.float32)
         return indices, weights
 
 
@@ -73,6 +74,47 @@ def create_named_schedule_sampler(name, diffusion):
     if name != "uniform":
         raise NotImplementedError("only the 'uniform' sampler is reachable in the reference (mul_ddpm_trainer.py:60)")
     return UniformSampler(diffusion)
+
+
+class _Terms(dict):
+    """{'mse', 'target', 'pred'} of training_losses; 'mse' (per-sample mean squared error, :1050) is computed when it is first
+    read — the reference's trainer never reads it (mul_ddpm_trainer.py:130-131 takes 'target' and 'pred'), and three
+    elementwise passes over the batch per iteration are not free."""
+
+    def _mse(self):
+        if not dict.__contains__(self, "mse"):
+            noise, pred = dict.__getitem__(self, "target"), dict.__getitem__(self, "pred")
+            dict.__setitem__(self, "mse", ((noise - pred) ** 2).mean(dim=list(range(1, pred.dim()))))
+
+    def __getitem__(self, k):
+        if k == "mse":
+            self._mse()
+        return dict.__getitem__(self, k)
+
+    def __contains__(self, k):
+        return k == "mse" or dict.__contains__(self, k)
+
+    def keys(self):
+        self._mse()
+        return dict.keys(self)
+
+    def items(self):
+        self._mse()
+        return dict.items(self)
+
+    def values(self):
+        self._mse()
+        return dict.values(self)
+
+    def __iter__(self):
+        self._mse()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        return 3
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
 
 
 def _unwrap(model):
@@ -377,5 +419,4 @@ class GaussianDiffusion:
         pred = model(x_t, self._scale_timesteps(t), **model_kwargs)
         if pred.shape != noise.shape:
             raise RuntimeError("model output shape mismatch")
-        mse = ((noise - pred) ** 2).mean(dim=list(range(1, pred.dim())))
-        return {"mse": mse, "target": noise, "pred": pred}
+        return _Terms(target=noise, pred=pred)

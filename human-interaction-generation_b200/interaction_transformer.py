@@ -184,7 +184,8 @@ class MotionInteractionTransformer(nn.Module):
         idx = None
         if len(uniq) != len(text):
             where = {c: i for i, c in enumerate(uniq)}
-            idx = torch.tensor([where[c] for c in text], device=device, dtype=torch.long)
+            from .staging import stage
+            idx = stage(torch.tensor([where[c] for c in text], dtype=torch.long), device)
         return xf_proj, xf_out, idx
 
     def _text_stack(self):
@@ -246,7 +247,8 @@ class MotionInteractionTransformer(nn.Module):
             if len(cache) > 65536:
                 cache.clear()
             cache.update(zip(missing, pos))
-        return torch.tensor([cache[c] for c in captions], device=device, dtype=torch.long)
+        from .staging import stage
+        return stage(torch.tensor([cache[c] for c in captions], dtype=torch.long), device)
 
     def _clip_features(self, captions, device):
         """clip.ln_final(clip.transformer(token_embedding + positional_embedding)) per caption, LND layout (:536-550)."""
@@ -282,7 +284,9 @@ class MotionInteractionTransformer(nn.Module):
 
     def get_class_embedding(self, text):
         """:561-566 — text = [LongTensor of person-1 caption ids, LongTensor of person-2 caption ids]."""
-        ids = torch.cat([torch.as_tensor(t).reshape(-1) for t in text]).to(self.cap_embedding.device)
+        from .staging import stage
+        ids = torch.cat([torch.as_tensor(t).reshape(-1) for t in text])
+        ids = stage(ids, self.cap_embedding.device, torch.long)
         e = self.cap_embedding[ids]
         return self.text_proj(e), e.unsqueeze(1)
 

@@ -139,7 +139,8 @@ class DDPMMulTrainer(object):
                             motion2.detach().to(dev, non_blocking=True).float()], dim=0)
         caption = list(caption1) + list(caption2)
         B, T = motion1.shape[0], motion.shape[1]
-        cur_len = torch.as_tensor(m_lens).reshape(-1).to(torch.long).clamp(max=T).to(dev, non_blocking=True)
+        from .staging import stage
+        cur_len = stage(torch.as_tensor(m_lens).reshape(-1), dev, torch.long).clamp(max=T)
         t, _ = self.sampler.sample(B, motion.device)
         t = torch.cat([t, t], dim=0)
         if not self.with_label:

@@ -382,6 +382,26 @@ def gemm_t(a, w, trans_a=False, trans_b=False, bias=None, residual=None, out_f32
     return out_f32 if out_bf16 is None else out_bf16
 
 
+def gemm_fused(a, w, bias, out, trans_b=False, act=0, out_pre=None, gate=None, gate_act=0):
+    """nn.Linear next to an activation in one tcgen05 GEMM (training path):
+    forward  — pre = a @ w.T + bias; out_pre = pre (bf16); out = act(pre as stored)        (act: ACT_GELU / ACT_SILU / 0)
+    backward — trans_b=True, w = the next layer's weight [K, N] as stored: out = (a @ w + bias) * act'(gate)."""
+    lib = _lib.load()
+    for t in (a, w, out, out_pre, gate):
+        if t is not None and t.dtype != torch.bfloat16:
+            raise TypeError("hig_b200.gemm_fused: bf16 operands / outputs required")
+    M, K = a.shape
+    Kw, N = (w.shape if trans_b else w.shape[::-1])
+    if K != Kw or bias is None or bias.dtype != torch.float32 or bias.numel() < N:
+        raise ValueError("hig_b200.gemm_fused: shape mismatch or missing fp32 bias")
+    rc = lib.hig_gemm_bf16_fused(1 if trans_b else 0, _ptr(a), _rowmajor(a, "A"), _ptr(w), _rowmajor(w, "W"), M, N, K,
+                                 _ptr(bias), int(act), _ptr(out), _rowmajor(out, "out"), _ptr(out_pre),
+                                 _rowmajor(out_pre, "out_pre") if out_pre is not None else 0, _ptr(gate),
+                                 _rowmajor(gate, "gate") if gate is not None else 0, int(gate_act), _stream())
+    _lib.check(rc, "hig_gemm_bf16_fused")
+    return out
+
+
 def transpose(x, out_t=None, copy=None, colsum=None, rows_zero_mod=0):
     """x [M,N] -> out_t [N,>=M] (transposed), copy [M,N] (cast), colsum[N] += column sums; any subset."""
     lib = _lib.load()
@@ -446,19 +466,23 @@ def ln_film_silu_bwd(x, gamma, beta, dout, dx, rows_per_seq, scale_shift=None, s
 
 
 def eff_attn_bwd(mode, S, T, H, q=None, k=None, v=None, a_in=None, dy=None, dq=None, dk=None, dv=None, dA=None,
-                 length=None, pair_shift=0):
+                 length=None, pair_shift=0, q_sum=None, k_sum=None, v_sum=None):
+    """q_sum / k_sum / v_sum (fp32 [H*64], optional): += column sums of dq / dk / dv — the bias gradients of the projections."""
     lib = _lib.load()
+    for t in (q_sum, k_sum, v_sum):
+        if t is not None and (t.dtype != torch.float32 or t.numel() < H * 64 or not t.is_contiguous()):
+            raise ValueError("hig_b200.eff_attn_bwd: column-sum outputs must be contiguous fp32 [H*64]")
     ref = q if q is not None else k
     if dA is not None and dA.dtype != torch.float32:
         raise TypeError("hig_b200.eff_attn_bwd: dA must be fp32")
     if dk is not None and dv.stride(0) != dk.stride(0):
         raise ValueError("hig_b200.eff_attn_bwd: dK and dV must share a leading dimension")
-    rc = lib.hig_eff_attn_bwd(mode, _ptr(q), q.stride(0) if q is not None else 0, _ptr(k), _ptr(v),
-                              k.stride(0) if k is not None else 0, _ptr(a_in), _ptr(dy),
-                              dy.stride(0) if dy is not None else 0, _ptr(dq), dq.stride(0) if dq is not None else 0,
-                              _ptr(dk), _ptr(dv), dk.stride(0) if dk is not None else 0, _ptr(dA), _ptr(length), S, T,
-                              H, pair_shift, _dt(ref), _stream())
-    _lib.check(rc, "hig_eff_attn_bwd")
+    rc = lib.hig_eff_attn_bwd_sums(mode, _ptr(q), q.stride(0) if q is not None else 0, _ptr(k), _ptr(v),
+                                   k.stride(0) if k is not None else 0, _ptr(a_in), _ptr(dy),
+                                   dy.stride(0) if dy is not None else 0, _ptr(dq), dq.stride(0) if dq is not None else 0,
+                                   _ptr(dk), _ptr(dv), dk.stride(0) if dk is not None else 0, _ptr(dA), _ptr(length), S, T,
+                                   H, pair_shift, _dt(ref), _ptr(q_sum), _ptr(k_sum), _ptr(v_sum), _stream())
+    _lib.check(rc, "hig_eff_attn_bwd_sums")
 
 
 def mha_attention(qkv, out, B, N, H, causal=False):

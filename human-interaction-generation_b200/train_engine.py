@@ -289,6 +289,11 @@ class _Plan:
             return i, st.ss[:, i * 2 * D:(i + 1) * 2 * D]
 
         fused_attn = os.environ.get("HIG_TRAIN_FUSED_ATTN", "1") != "0"
+        # HIG_TRAIN_FUSED_FFN=1: linear1's epilogue writes h1 and GELU(h1), linear2's input-gradient GEMM applies GELU'(h1).
+        # Correct (bit-identical forward) and SLOWER: 16.5 vs 16.0 ms per iteration on the same box — the K = 512 GEMMs are
+        # paced by their 8 epilogue warps, and an erf / exp per element there costs more than the 143 MB round trip of the
+        # 64-warps-per-SM elementwise kernels it removes.  Off by default.
+        fused_ffn = os.environ.get("HIG_TRAIN_FUSED_FFN", "0") == "1" and tok >= 512     # CTA-pair GEMM shapes only
         xb = None
         kinds = ["sa", "ca"] + (["ic"] if eng.has_ic else [])
         for li in range(L):
@@ -332,9 +337,12 @@ class _Plan:
                 st.blocks.append(blk)
             # FFN (:261-264)
             blk = {"kind": "ffn", "xres_in": xres, "li": li, "xb_in": xb}
-            h1 = new(tok, F_)
-            G(xb, W[p + "ffn.w1"], bias=W[p + "ffn.b1"], out_bf16=h1)
-            g = ops.act_fwd(h1, ops.ACT_GELU, new(tok, F_))
+            h1, g = new(tok, F_), new(tok, F_)
+            if fused_ffn:      # linear1 with both h1 (saved for GELU') and GELU(h1) written by its epilogue
+                ops.gemm_fused(xb, W[p + "ffn.w1"], W[p + "ffn.b1"], g, act=ops.ACT_GELU, out_pre=h1)
+            else:
+                G(xb, W[p + "ffn.w1"], bias=W[p + "ffn.b1"], out_bf16=h1)
+                ops.act_fwd(h1, ops.ACT_GELU, g)
             y = new(tok, D)
             G(g, W[p + "ffn.w2"], bias=W[p + "ffn.b2"], out_bf16=y)
             i_ss, ss = ss_of(p + "ffn")
@@ -367,6 +375,7 @@ class _Plan:
         # output tile instead of K-slices combined with fp32 atomics, column sums and the gradient norm with one contributor
         # per address (the C side reads the same variable), LayerNorm parameter gradients through per-sequence partials.
         det = os.environ.get("HIG_DETERMINISTIC", "0") not in ("", "0")
+        fused_ffn = os.environ.get("HIG_TRAIN_FUSED_FFN", "0") == "1" and tok >= 512
 
         def zero_bias(n):
             zb = W["zero.b"].get(n)
@@ -442,7 +451,9 @@ class _Plan:
             return d_y
 
         def linear_bwd(dy, x_saved, w, w_grad, b_grad, dx_into=None):
-            ops.colsum(dy, b_grad)
+            """b_grad None: the kernel that produced dy already left its column sums in the bias gradient."""
+            if b_grad is not None:
+                ops.colsum(dy, b_grad)
             dx = None
             if dx_into is not None:
                 dgrad(dy, w, out_f32=dx_into, accumulate=True)
@@ -469,36 +480,48 @@ class _Plan:
             mp = f"temporal_decoder_blocks.{li}.{modname[kind]}"
             d_y = stylize_project_bwd(blk, pfx, mp)
             if kind == "ffn":
-                d_g = linear_bwd(d_y, blk["g"], W[f"l{li}.ffn.w2"], gv[mp + "linear2.weight"], gv[mp + "linear2.bias"])
-                d_h1 = ops.act_bwd(blk["h1"], d_g, ops.ACT_GELU, new(tok, F_))
+                if fused_ffn:
+                    # d_h1 = (d_y . W2) * GELU'(h1) straight from the input-gradient GEMM's epilogue: d_g never reaches HBM
+                    w2 = W[f"l{li}.ffn.w2"]
+                    ops.colsum(d_y, gv[mp + "linear2.bias"])
+                    d_h1 = ops.gemm_fused(d_y, w2, zero_bias(w2.shape[1]), new(tok, F_), trans_b=True, gate=blk["h1"],
+                                          gate_act=ops.ACT_GELU)
+                    wgrad(d_y, blk["g"], gv[mp + "linear2.weight"])
+                else:
+                    d_g = linear_bwd(d_y, blk["g"], W[f"l{li}.ffn.w2"], gv[mp + "linear2.weight"], gv[mp + "linear2.bias"])
+                    d_h1 = ops.act_bwd(blk["h1"], d_g, ops.ACT_GELU, new(tok, F_))
                 # no pre-norm in the FFN: d(xres_in) = dres (skip path) + d_h1 . W1, accumulated by the GEMM epilogue
                 linear_bwd(d_h1, blk["xb_in"], W[f"l{li}.ffn.w1"], gv[mp + "linear1.weight"], gv[mp + "linear1.bias"],
                            dx_into=dres)
             elif kind == "ca":
                 d_q = new(tok, D)
                 dA = new(S, H, HEAD_DIM, HEAD_DIM, dtype=f32)
-                ops.eff_attn_bwd(ops.ATTN_Q_ONLY, S, T, H, q=blk["q"], a_in=st.a_text[li], dy=d_y, dq=d_q, dA=dA)
-                d_n = linear_bwd(d_q, blk["n"], W[f"l{li}.ca.q.w"], gv[mp + "query.weight"], gv[mp + "query.bias"])
+                ops.eff_attn_bwd(ops.ATTN_Q_ONLY, S, T, H, q=blk["q"], a_in=st.a_text[li], dy=d_y, dq=d_q, dA=dA,
+                                 q_sum=gv[mp + "query.bias"])
+                d_n = linear_bwd(d_q, blk["n"], W[f"l{li}.ca.q.w"], gv[mp + "query.weight"], None)
                 pre_ln_bwd(blk, d_n, pfx, mp)
                 if self.U:       # sequences that share a caption: their dA add up
                     dA = torch.zeros(SU, H, HEAD_DIM, HEAD_DIM, device=dev, dtype=f32).index_add_(0, self.text_idx, dA)
                 kv = st.kv[li]
                 d_kv = new(SU * N, 2 * D)
-                ops.eff_attn_bwd(ops.ATTN_KV_ONLY, SU, N, H, k=kv[:, :D], v=kv[:, D:], dk=d_kv[:, :D], dv=d_kv[:, D:], dA=dA)
+                kv_b = greg(mp + "key.bias", 2 * D, (2 * D,))
+                ops.eff_attn_bwd(ops.ATTN_KV_ONLY, SU, N, H, k=kv[:, :D], v=kv[:, D:], dk=d_kv[:, :D], dv=d_kv[:, D:], dA=dA,
+                                 k_sum=kv_b[:D], v_sum=kv_b[D:])
                 Dt = st.xf.shape[1]
-                d_tn = linear_bwd(d_kv, st.tn[li], W[f"l{li}.ca.kv.w"], greg(mp + "key.weight", 2 * D * Dt, (2 * D, Dt)),
-                                  greg(mp + "key.bias", 2 * D, (2 * D,)))
+                d_tn = linear_bwd(d_kv, st.tn[li], W[f"l{li}.ca.kv.w"], greg(mp + "key.weight", 2 * D * Dt, (2 * D, Dt)), None)
                 ops.ln_film_silu_bwd(st.xf, W[pfx + ".tln.w"], W[pfx + ".tln.b"], d_tn, d_xf, N, dx_accumulate=True,
                                      d_gb=bcast(greg(mp + "text_norm.weight", 2 * Dt, (2 * Dt,)), SU))
             else:
                 qkv = blk["qkv"]
                 d_qkv = new(tok, 3 * D)
                 mode = ops.ATTN_SELF if kind == "sa" else ops.ATTN_INTER
+                qkv_b = greg(mp + "query.bias", 3 * D, (3 * D,))
                 ops.eff_attn_bwd(mode, S, T, H, q=qkv[:, :D], k=qkv[:, D:2 * D], v=qkv[:, 2 * D:], dy=d_y,
                                  dq=d_qkv[:, :D], dk=d_qkv[:, D:2 * D], dv=d_qkv[:, 2 * D:], length=self.len,
-                                 pair_shift=S // 2 if kind == "ic" else 0)
+                                 pair_shift=S // 2 if kind == "ic" else 0, q_sum=qkv_b[:D], k_sum=qkv_b[D:2 * D],
+                                 v_sum=qkv_b[2 * D:])
                 d_n = linear_bwd(d_qkv, blk["n"], W[f"l{li}.{kind}.qkv.w"], greg(mp + "query.weight", 3 * D * D, (3 * D, D)),
-                                 greg(mp + "query.bias", 3 * D, (3 * D,)))
+                                 None)
                 pre_ln_bwd(blk, d_n, pfx, mp)
             if kind == "sa":
                 # every parameter of layer li is final — including its StylizationBlocks' emb-linears: their (scale | shift)
@@ -603,7 +626,7 @@ class TrainEngine:
 
     def plan(self, S, T, N, U=None):
         # the kernel-selection knobs are baked into the captured graphs
-        key = (S, T, N, U) + tuple(os.environ.get(k, "") for k in ("HIG_DETERMINISTIC", "HIG_TRAIN_FUSED_ATTN", "HIG_TRAIN_GRAPH"))
+        key = (S, T, N, U) + tuple(os.environ.get(k, "") for k in ("HIG_DETERMINISTIC", "HIG_TRAIN_FUSED_ATTN", "HIG_TRAIN_FUSED_FFN", "HIG_TRAIN_GRAPH"))
         p = self.plans.get(key)
         if p is None:
             if len(self.plans) >= 3:      # each plan pins its saved activations: keep a few shapes only

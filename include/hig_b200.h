@@ -235,6 +235,16 @@ int hig_gemm_bf16_t(int trans_a, int trans_b, const void* A, int lda, const void
                     const float* bias, const float* residual, int ldr, float* out_f32, int ldo_f32, void* out_bf16,
                     int ldo_bf16, int split_k, void* stream);
 
+/* An nn.Linear next to an activation, fused for the training path (the FFN of models/interaction_transformer.py:261-264,
+ * linear1 -> GELU -> linear2, and what torch.autograd does on the way back):
+ *   forward  (trans_b = 0, W [N,K]):  pre = A W^T + bias;  out_pre_bf16 (nullable) = pre;  out_bf16 = act(pre as stored)
+ *   backward (trans_b = 1, W [K,N] = the next layer's weight as stored):  out_bf16 = (A W + bias) * act'(gate_bf16[M,N]),
+ *            gate = the saved pre-activation (nullable: no gating), gate_act 1 GELU / 2 SiLU
+ * act: 0 none, 1 GELU (erf form, as hig_act_fwd), 2 SiLU.  bias fp32 [N] is required (pass zeros).  N % 32 == 0. */
+int hig_gemm_bf16_fused(int trans_b, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                        int act, void* out_bf16, int ldo_bf16, void* out_pre_bf16, int ldo_pre, const void* gate_bf16,
+                        int ld_gate, int gate_act, void* stream);
+
 /* in [M,N] -> outT [N,M] (nullable), copy [M,N] in the output dtype (nullable), colsum[n] += sum_m in[m,n] (nullable,
  * fp32 atomics: bias gradients).  rows_zero_mod > 0 treats rows with m % rows_zero_mod == 0 as zero (frame 0 of a
  * sequence belongs to the out2 head, models/interaction_transformer.py:613-616). */
@@ -261,6 +271,15 @@ int hig_ln_film_silu_bwd(const void* x, int x_dtype, int rows, int width, int ro
 int hig_eff_attn_bwd(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
                      const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
                      const int* length, int S, int T, int H, int pair_shift, int dtype, void* stream);
+
+/* The same, plus the bias gradients of the projections that produced Q / K / V (torch.autograd's sum over the token rows of
+ * the nn.Linear outputs' gradients, models/interaction_transformer.py:108-110): q_sum / k_sum / v_sum [H*64] fp32 (each
+ * nullable) += column sums of dq / dk / dv as stored.  The bf16 tensor-core kernel takes them from the tiles it is about to
+ * store; the other kernels (and HIG_DETERMINISTIC=1) run hig_colsum afterwards. */
+int hig_eff_attn_bwd_sums(int mode, const void* q, int ldq, const void* k, const void* v, int ldkv, const void* a_in,
+                          const void* dy, int lddy, void* dq, int lddq, void* dk, void* dv, int lddkv, float* dA,
+                          const int* length, int S, int T, int H, int pair_shift, int dtype, float* q_sum, float* k_sum,
+                          float* v_sum, void* stream);
 
 /* Softmax multi-head attention of the text transformers in MotionInteractionTransformer.encode_text
  * (models/interaction_transformer.py:533-559: CLIP's causal 8-head text transformer, and the 4-head nn.TransformerEncoder of

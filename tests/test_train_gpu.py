@@ -219,8 +219,13 @@ def test_eff_attn_bwd_self_and_inter(cuda, dtype, S, T, H):
         y.backward(dy.float().view(S, T, H, 64))
         want = r.grad.view(S * T, 3 * D)
         d = torch.empty_like(qkv)
+        base = torch.randn(3 * D, device=cuda)                 # bias-gradient column sums are ACCUMULATED
+        sums = base.clone()
         ops.eff_attn_bwd(mode, S, T, H, q=qkv[:, :D], k=qkv[:, D:2 * D], v=qkv[:, 2 * D:], dy=dy, dq=d[:, :D],
-                         dk=d[:, D:2 * D], dv=d[:, 2 * D:], length=lens, pair_shift=S // 2 if mode == ops.ATTN_INTER else 0)
+                         dk=d[:, D:2 * D], dv=d[:, 2 * D:], length=lens, pair_shift=S // 2 if mode == ops.ATTN_INTER else 0,
+                         q_sum=sums[:D], k_sum=sums[D:2 * D], v_sum=sums[2 * D:])
+        want_sums = d.double().sum(0)
+        assert ((sums - base).double() - want_sums).abs().max().item() < 1e-4 * max(1.0, want_sums.abs().max().item())
         for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
             if T == 1 and name != "dv":
                 # one key row: Ks == 1, A has identical rows, so dQ and dK are exactly zero analytically
@@ -248,9 +253,13 @@ def test_eff_attn_bwd_text(cuda, dtype, N):
     ops.eff_attn(ops.ATTN_KV_ONLY, S, N, H, k=kv[:, :D], v=kv[:, D:], a_out=a)
     dq = torch.empty_like(q)
     dA = torch.empty(S, H, 64, 64, device=cuda)
-    ops.eff_attn_bwd(ops.ATTN_Q_ONLY, S, T, H, q=q, a_in=a, dy=dy, dq=dq, dA=dA)
+    sums = torch.zeros(3 * D, device=cuda)
+    ops.eff_attn_bwd(ops.ATTN_Q_ONLY, S, T, H, q=q, a_in=a, dy=dy, dq=dq, dA=dA, q_sum=sums[:D])
     dkv = torch.empty_like(kv)
-    ops.eff_attn_bwd(ops.ATTN_KV_ONLY, S, N, H, k=kv[:, :D], v=kv[:, D:], dk=dkv[:, :D], dv=dkv[:, D:], dA=dA)
+    ops.eff_attn_bwd(ops.ATTN_KV_ONLY, S, N, H, k=kv[:, :D], v=kv[:, D:], dk=dkv[:, :D], dv=dkv[:, D:], dA=dA,
+                     k_sum=sums[D:2 * D], v_sum=sums[2 * D:])
+    want_sums = torch.cat([dq.double().sum(0), dkv.double().sum(0)])
+    assert (sums.double() - want_sums).abs().max().item() < 1e-4 * max(1.0, want_sums.abs().max().item())
     tol = 3e-5 if dtype == torch.float32 else 2e-2
     if N > 1:
         assert rel(dq, qr.grad.view(S * T, D)) < tol
@@ -402,3 +411,38 @@ def test_nccl_data_parallel_two_gpus(cuda):
                         "--master-addr", "127.0.0.1", "--master-port", "29631", os.path.join(ROOT, "tools", "ddp_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ddp_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("M,N,K", [(23296, 1024, 512), (1000, 256, 512), (2048, 512, 1024)])
+def test_gemm_fused_forward_and_gated_backward(cuda, M, N, K):
+    """linear -> GELU with both the pre-activation and the activation written by the GEMM epilogue, and the input-gradient
+    GEMM of the next linear gated by GELU'(saved pre-activation): against the unfused kernels they replace (same arithmetic:
+    bit-identical) and against fp64."""
+    ops = _ops()
+    g = torch.Generator(device=cuda).manual_seed(M + N)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=cuda, generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device=cuda, generator=g)
+    pre, act = torch.empty(M, N, device=cuda, dtype=torch.bfloat16), torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm_fused(a, w, b, act, act=ops.ACT_GELU, out_pre=pre)
+    pre_ref = torch.empty_like(pre)
+    ops.gemm(a, w, bias=b, out_bf16=pre_ref)
+    act_ref = ops.act_fwd(pre_ref, ops.ACT_GELU, torch.empty_like(pre_ref))
+    assert torch.equal(pre, pre_ref) and torch.equal(act, act_ref)
+    want = torch.nn.functional.gelu(a.double() @ w.double().t() + b.double())
+    assert rel(act, want) < 6e-3
+    # backward: d_pre = (dy @ w2) * GELU'(pre), w2 [K2, N] as nn.Linear stores it
+    K2 = 512
+    dy = torch.randn(M, K2, device=cuda, generator=g).bfloat16()
+    w2 = (torch.randn(K2, N, device=cuda, generator=g) / K2 ** 0.5).bfloat16()
+    zb = torch.zeros(N, device=cuda)
+    d_pre = ops.gemm_fused(dy, w2, zb, torch.empty(M, N, device=cuda, dtype=torch.bfloat16), trans_b=True, gate=pre,
+                           gate_act=ops.ACT_GELU)
+    d_act = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm_t(dy, w2, trans_b=True, bias=zb, out_bf16=d_act)
+    d_ref = ops.act_bwd(pre, d_act, ops.ACT_GELU, torch.empty_like(d_act))
+    # the unfused path rounds d_act to bf16 before the multiplication: one extra rounding, not a different formula
+    assert rel(d_pre, d_ref) < 6e-3
+    p64 = pre.double().requires_grad_(True)
+    torch.nn.functional.gelu(p64).backward(dy.double() @ w2.double())
+    assert rel(d_pre, p64.grad) < 6e-3

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--frames", type=int, default=91)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--sync-debug", action="store_true", help="warn (with a stack) on every host-synchronising CUDA call in the timed loop")
     ap.add_argument("--denoiser-only", action="store_true", help="cap_id model: no CLIP / text-encoder forward")
     ap.add_argument("--pit", action="store_true", help="unlabelled (PIT) mode: 4B sequences per iteration")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
@@ -103,11 +104,19 @@ def main():
     if args.profile:
         torch.cuda.cudart().cudaProfilerStart()
     import time
+    if args.sync_debug:
+        import traceback
+        import warnings
+        warnings.simplefilter("always")
+        warnings.showwarning = lambda m, c, f, l, *a, **k: (print(f"SYNC: {m}"), traceback.print_stack(limit=12))
+        torch.cuda.set_sync_debug_mode(1)
     e0.record()
     h0 = time.perf_counter()
     evs = [it() for _ in range(args.iters)]
     host_ms = (time.perf_counter() - h0) * 1e3 / args.iters      # time the host needs to ISSUE an iteration (no sync inside)
     e1.record()
+    if args.sync_debug:
+        torch.cuda.set_sync_debug_mode(0)
     torch.cuda.synchronize()
     if args.profile:
         torch.cuda.cudart().cudaProfilerStop()
