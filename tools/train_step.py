@@ -99,6 +99,16 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    # host time to ISSUE one iteration while the launch queue is empty (later iterations block on the queue depth: the host
+    # runs ~80 ms ahead of the GPU and then moves in lock-step with it)
+    import time as _t
+    h_ = _t.perf_counter()
+    for _ in range(3):
+        it()
+    host_free_ms = (_t.perf_counter() - h_) * 1e3 / 3
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if args.profile:
@@ -133,7 +143,7 @@ def main():
         print(json.dumps({"workload": f"training step, {B} pairs/GPU x {T} frames, {'PIT' if args.pit else 'labelled'}, "
                                       f"{'denoiser only (cap_id)' if args.denoiser_only else 'with CLIP + text encoder'}",
                           "n_gpus": world, "ms_per_iter": ms, "pairs_per_s": world * B / ms * 1e3,
-                          "host_issue_ms_per_iter": host_ms, "forward_ms": fwd, "backward_plus_adam_ms": bwd, "loss": float(evs[-1][1]["loss_mot_rec"]), "optimizer": args.optimizer,
+                          "host_issue_ms_per_iter": host_ms, "host_issue_ms_queue_empty": host_free_ms, "forward_ms": fwd, "backward_plus_adam_ms": bwd, "loss": float(evs[-1][1]["loss_mot_rec"]), "optimizer": args.optimizer,
                           "hig_launches_per_iter": (_lib.launch_count() - l0) / args.iters,
                           "denoiser_fwd_bwd_tflops": fl / (ms * 1e-3) / 1e12,
                           "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
