@@ -76,6 +76,7 @@ SIGNATURES = {
     "hig_masked_mse": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                        c_void_p],
     "hig_sumsq": [c_void_p, ctypes.c_longlong, c_void_p, c_void_p],
+    "hig_mean_slices": [c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_longlong, c_int, ctypes.c_float, c_void_p],
     "hig_adam_flat": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_float, ctypes.c_float,
                       ctypes.c_float, ctypes.c_float, c_int, c_void_p, ctypes.c_float, c_void_p],
 }

@@ -273,6 +273,10 @@ int hig_sumsq(const float* x, long long n, double* out, void* stream) {
   return hig::sumsq(x, n, out, static_cast<cudaStream_t>(stream));
 }
 
+int hig_mean_slices(float* own, const float* staged, long long n, long long stride, int count, float scale, void* stream) {
+  return hig::mean_slices(own, staged, n, stride, count, scale, static_cast<cudaStream_t>(stream));
+}
+
 int hig_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
                   float beta2, float eps, int step, const double* gnorm2, float max_norm, void* stream) {
   return hig::adam_flat(p, g, m, v, p_bf16, n, lr, beta1, beta2, eps, step, gnorm2, max_norm,

@@ -141,6 +141,7 @@ int mha_attention(const void* q, const void* k, const void* v, int ld, void* out
 int masked_mse(const float* pred, const float* tgt, const int* length, int S, int T, int C, int pit, float* rows, float* w,
                float* loss, float* d_pred, cudaStream_t stream);
 int sumsq(const float* x, long long n, double* out, cudaStream_t stream);
+int mean_slices(float* own, const float* staged, long long n, long long stride, int count, float scale, cudaStream_t stream);
 int adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1, float beta2,
               float eps, int step, const double* gnorm2, float max_norm, cudaStream_t stream);
 

@@ -168,6 +168,52 @@ int sumsq(const float* x, long long n, double* out, cudaStream_t stream) {
   return HIG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- slice mean
+// own[i] = (own[i] + sum_j staged[j * stride + i]) * scale — the reduction step of the peer-memory gradient exchange
+// (ddp.PeerGradExchange): `count` contributions pulled from the other ranks by the copy engines.  A few blocks only: it runs
+// beside the backward kernels and must not take the machine from them.
+__global__ void __launch_bounds__(256)
+mean_slices_kernel(float* __restrict__ own, const float* __restrict__ staged, long long n, long long stride, int count,
+                   float scale, int vec) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long i = tid; i < n4; i += nth) {
+      float4 a = reinterpret_cast<float4*>(own)[i];
+      for (int j = 0; j < count; ++j) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(staged + (long long)j * stride) + i);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+      reinterpret_cast<float4*>(own)[i] = a;
+    }
+    for (long long i = (n4 << 2) + tid; i < n; i += nth) {
+      float a = own[i];
+      for (int j = 0; j < count; ++j) a += staged[(long long)j * stride + i];
+      own[i] = a * scale;
+    }
+    return;
+  }
+  for (long long i = tid; i < n; i += nth) {
+    float a = own[i];
+    for (int j = 0; j < count; ++j) a += staged[(long long)j * stride + i];
+    own[i] = a * scale;
+  }
+}
+
+int mean_slices(float* own, const float* staged, long long n, long long stride, int count, float scale, cudaStream_t stream) {
+  if (!own || !staged || n <= 0 || count < 0) return set_error(HIG_ERR_INVALID, "mean_slices: bad arguments");
+  const int vec = ((reinterpret_cast<uintptr_t>(own) | reinterpret_cast<uintptr_t>(staged)) & 15) == 0 && (stride % 4) == 0;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 32) blocks = 32;
+  if (blocks < 1) blocks = 1;
+  mean_slices_kernel<<<(unsigned)blocks, 256, 0, stream>>>(own, staged, n, stride, count, scale, vec);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HIG_ERR_CUDA, std::string("mean_slices launch: ") + cudaGetErrorString(e));
+  count_launch();
+  return HIG_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- Adam
 // torch.optim.Adam (no weight decay, no amsgrad):  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
 //   p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)          bc_i = 1 - b_i^step

@@ -16,6 +16,8 @@ rank 0 (the reference samples on a single GPU, codes/trainers/mul_ddpm_trainer.p
 
 The host logic is backend-agnostic: tests/test_ddp_cpu.py runs it with world_size 2 on `gloo`.
 """
+import os
+
 import torch
 import torch.distributed as dist
 from torch import nn
@@ -25,6 +27,163 @@ def _avg_supported(group):
     return dist.get_backend(group) == "nccl"
 
 
+class PeerGradExchange:
+    """Mean of the flat gradient buffer over the ranks WITHOUT an SM-resident collective kernel.
+
+    OPT-IN (HIG_DDP_EXCHANGE=peer); the default is the coalesced NCCL all-reduce.  It was written to test a hypothesis and
+    the measurement refuted it.  Hypothesis: every compute kernel of the backward fills the machine (persistent tcgen05 GEMM
+    grids with one CTA per SM, attention and LayerNorm backward at their register / shared-memory occupancy limit), so an
+    NCCL all-reduce kernel launched beside them either waits for SMs or takes them from a statically partitioned GEMM grid —
+    hence 0.6-0.7 of a 0.83 ms all-reduce exposed at N = 2 and 0.9-1.2 of 1.18 ms at N = 8, whatever the number of NCCL
+    channels or of SMs set aside for them (profiles/r02_n2_nccl_channels_sm_reservation_sweep.txt).  Result: this exchange
+    uses no SMs for the transfers and exposes the SAME time (N = 2: 14.5-14.9 ms per iteration against 14.8-15.0 with NCCL
+    and 14.2 without any exchange; N = 8: 15.24 against 15.27 and 14.33).  Its timeline (HIG_DDP_TRACE=1,
+    profiles/r02_n2_peer_exchange_timeline.txt) shows why: every segment's exchange ends 0.3-0.5 ms after the segment is
+    ready, long before the next one, so the transfers ARE overlapped; what remains is the tail after the last backward kernel
+    (layer 0's and the embeddings' segments, 0.26-0.35 ms) and a ~0.4 ms slowdown of the backward kernels themselves while
+    850 MB cross NVLink and HBM under the board's power cap.  Neither is a scheduling problem.
+
+    How: the gradient buffer is symmetric memory (train_engine._alloc_flat_grad), every rank maps its peers' buffers over
+    NVLink / NVSwitch, and a segment that became final is averaged as reduce-scatter + all-gather made of COPY-ENGINE
+    transfers on a side stream:
+        barrier                      every rank's segment is final
+        pull                         rank r copies slice r of the segment from each peer into a local staging area
+        reduce (one small kernel)    slice r = (own + staged) / world, written in place
+        barrier                      every slice is reduced
+        pull                         rank r copies the reduced slices of the others from their owners
+    The copy engines move the bytes while the SMs run the next layer's backward; the only kernels are the signal-pad
+    barriers (one block) and the slice reduction.  Every slice is reduced by exactly one rank, so all ranks end up with
+    bit-identical gradients.  finish() adds a last barrier (no rank may zero its buffer for the next iteration while a peer
+    still reads it) and makes the compute stream wait for the side stream."""
+
+    def __init__(self, fp, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.grad = fp.grad
+        self.group = group if group is not None else dist.group.WORLD
+        self.hdl = symm.rendezvous(self.grad, self.group)
+        if self.hdl is None:
+            raise RuntimeError("flat gradient buffer is not symmetric memory")
+        self.rank, self.world = self.hdl.rank, self.hdl.world_size
+        n = self.grad.numel()
+        self.peers = [self.grad if p == self.rank else self.hdl.get_buffer(p, (n,), torch.float32, 0)
+                      for p in range(self.world)]
+        # (alternating two exchange streams so that the small last segment does not queue behind the layer before it was
+        #  measured SLOWER: 15.04 vs 14.87 ms per iteration at N = 2)
+        self.stream = torch.cuda.Stream(device=self.grad.device, priority=-1)
+        self.pull_streams = [torch.cuda.Stream(device=self.grad.device, priority=-1)
+                             for _ in range(max(self.world - 1, int(os.environ.get("HIG_DDP_COPY_STREAMS", "6"))))]
+        # staging for the slices this rank owns: (world - 1) contributions of at most ceil(n / world) + slack elements
+        self.stage = torch.empty((self.world - 1) * (n // self.world + 64 * 8), device=self.grad.device, dtype=torch.float32)
+        self.bytes_moved = 0
+        self.calls = 0
+        self._dirty = False
+        # HIG_DDP_TRACE=1: timing events per segment (ready on the compute stream, done on the exchange stream) and at the
+        # join; tools/train_step.py prints the last iteration's timeline
+        self.trace = [] if os.environ.get("HIG_DDP_TRACE", "0") == "1" else None
+
+    @staticmethod
+    def _cuts(lo, hi, world):
+        """Slice boundaries of [lo, hi) — multiples of 4 elements (16-byte copies) except the end."""
+        n = hi - lo
+        per = -(-n // world)
+        per = -(-per // 4) * 4
+        return [min(hi, lo + k * per) for k in range(world + 1)]
+
+    def _fan_out(self, jobs):
+        """jobs[i]: list of (dst, src) copies from peer step i + 1.  The copies are spread over several streams — one copy
+        engine moves ~130 GB/s over NVLink, far below the link — forked from and joined back into the exchange stream; with
+        few peers a large copy is cut into pieces so that every stream has work."""
+        flat = [c for todo in jobs for c in todo]
+        if not flat:
+            return
+        ns = len(self.pull_streams)
+        pieces = max(1, ns // max(1, len(flat)))
+        work = []
+        for dst, src in flat:
+            n = dst.numel()
+            k = pieces if n >= pieces * (1 << 18) else 1           # pieces of at least 1 MB
+            step = -(-(-(-n // k)) // 4) * 4
+            for a in range(0, n, step):
+                work.append((dst[a:a + step], src[a:a + step]))
+        fork = torch.cuda.Event()
+        fork.record(self.stream)
+        for q, st in enumerate(self.pull_streams):
+            mine = work[q::ns]
+            if not mine:
+                continue
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                for dst, src in mine:
+                    dst.copy_(src)
+            done = torch.cuda.Event()
+            done.record(st)
+            self.stream.wait_event(done)
+
+    def segment_ready(self, ranges):
+        """`ranges`: [(lo, hi)] element ranges of the flat buffer that are final on this rank."""
+        from . import ops
+        r, W = self.rank, self.world
+        cur = torch.cuda.current_stream(self.grad.device)
+        ev = torch.cuda.Event(enable_timing=self.trace is not None)
+        ev.record(cur)
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            self.hdl.barrier(channel=0, timeout_ms=60000)
+            if self.trace is not None:
+                b1 = torch.cuda.Event(enable_timing=True)
+                b1.record(self.stream)
+            off, owned = 0, []
+            pulls = [[] for _ in range(W - 1)]
+            for lo, hi in ranges:
+                cuts = self._cuts(lo, hi, W)
+                a, b = cuts[r], cuts[r + 1]
+                n = b - a
+                if n <= 0:
+                    continue
+                st = self.stage[off:off + (W - 1) * n].view(W - 1, n)
+                off += (W - 1) * n
+                for i in range(1, W):
+                    pulls[i - 1].append((st[i - 1], self.peers[(r - i) % W][a:b]))
+                owned.append((a, b, st))
+                self.bytes_moved += (W - 1) * n * 4
+            self._fan_out(pulls)
+            for a, b, st in owned:
+                ops.mean_slices(self.grad[a:b], st, 1.0 / W)
+            self.hdl.barrier(channel=0, timeout_ms=60000)
+            pulls = [[] for _ in range(W - 1)]
+            for lo, hi in ranges:
+                cuts = self._cuts(lo, hi, W)
+                for i in range(1, W):
+                    p = (r - i) % W
+                    a, b = cuts[p], cuts[p + 1]
+                    if b > a:
+                        pulls[i - 1].append((self.grad[a:b], self.peers[p][a:b]))
+                        self.bytes_moved += (b - a) * 4
+            self._fan_out(pulls)
+            if self.trace is not None:
+                done = torch.cuda.Event(enable_timing=True)
+                done.record(self.stream)
+                self.trace.append(("segment", ev, b1, done))
+        self.calls += 1
+        self._dirty = True
+
+    def finish(self):
+        if not self._dirty:
+            return
+        cur = torch.cuda.current_stream(self.grad.device)
+        if self.trace is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record(cur)                       # the last backward kernel is done
+        with torch.cuda.stream(self.stream):
+            self.hdl.barrier(channel=0, timeout_ms=60000)
+        cur.wait_stream(self.stream)
+        if self.trace is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(cur)                       # the exchange has joined: the optimizer may start
+            self.trace.append(("join", e0, e0, e1))
+        self._dirty = False
+
+
 class GradReducer:
     """Asynchronous mean all-reduce of gradient segments + one trailing bucket of 'other' parameters."""
 
@@ -32,6 +191,8 @@ class GradReducer:
         self.group = group
         self.world = dist.get_world_size(group)
         self._pending = []          # (work, tensor, needs_div)
+        self._peer = {}             # id(FlatParams) -> PeerGradExchange (or False: unavailable)
+        self._px_active = None
         self.bytes_reduced = 0
         self.calls = 0
 
@@ -48,6 +209,47 @@ class GradReducer:
         self.bytes_reduced += flat.numel() * flat.element_size()
         self.calls += 1
 
+    def _peer_exchange(self, fp):
+        """The copy-engine exchange for this FlatParams (created on first use: a collective rendezvous), or None."""
+        if fp is None or not getattr(fp, "grad_symmetric", False) or not _avg_supported(self.group):
+            return None
+        px = self._peer.get(id(fp))
+        if px is None:
+            try:
+                px = PeerGradExchange(fp, self.group)
+            except Exception as e:  # noqa: BLE001 — every rank fails alike (same software, same topology): NCCL path
+                import warnings
+                warnings.warn(f"hig_b200: peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL")
+                px = False
+            self._peer[id(fp)] = px
+        return px or None
+
+    def segments_ready(self, index, flats, fp=None):
+        """Several disjoint ranges became final together (a layer's own parameters + its share of the stylization
+        emb-linears).  Symmetric gradient buffer: the copy-engine exchange (PeerGradExchange); otherwise ONE coalesced NCCL
+        launch (ncclGroupStart/End) instead of one per range."""
+        flats = [f for f in flats if f.numel()]
+        if self.world == 1 or not flats:
+            return
+        px = self._peer_exchange(fp)
+        if px is not None:
+            base = fp.grad.storage_offset()
+            px.segment_ready([(f.storage_offset() - base, f.storage_offset() - base + f.numel()) for f in flats])
+            self.bytes_reduced += sum(f.numel() * f.element_size() for f in flats)
+            self.calls += 1
+            self._px_active = px
+            return
+        if len(flats) == 1 or not _avg_supported(self.group) or os.environ.get("HIG_DDP_COALESCE", "1") == "0":
+            for f in flats:
+                self.segment_ready(index, f)
+            return
+        with dist._coalescing_manager(self.group, async_ops=True) as cm:
+            for f in flats:
+                dist.all_reduce(f, op=dist.ReduceOp.AVG, group=self.group)
+        self._pending.append((cm, None, False))
+        self.bytes_reduced += sum(f.numel() * f.element_size() for f in flats)
+        self.calls += 1
+
     def finish(self):
         """Make the current stream wait for every outstanding all-reduce (no host synchronisation on NCCL)."""
         for work, flat, needs_div in self._pending:
@@ -55,6 +257,9 @@ class GradReducer:
             if needs_div:
                 flat.div_(self.world)
         self._pending = []
+        if self._px_active is not None:
+            self._px_active.finish()
+            self._px_active = None
 
     def reduce_params(self, params):
         """Mean all-reduce of p.grad for `params` as ONE flat bucket (blocking on the stream, not the host)."""
@@ -87,6 +292,7 @@ class DataParallel(nn.Module):
                     dist.broadcast(p.data, src=0, group=process_group)
         # the denoiser's flat gradient segments (autograd.py / train_engine.py)
         module._grad_segment_hook = self.reducer.segment_ready
+        module._grad_segments_hook = self.reducer.segments_ready
         module._grad_finish_hook = self.reducer.finish
         # Persistent GEMM grids own every SM, so an NCCL kernel launched beside them only runs in the gaps between kernels
         # (measured at N = 2: 0.70 ms of a 0.82 ms all-reduce exposed).  Reserve a few SMs for NCCL while training in parallel:

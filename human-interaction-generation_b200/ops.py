@@ -523,6 +523,18 @@ def sumsq(x, out):
     return out
 
 
+def mean_slices(own, staged, scale):
+    """own[n] = (own + staged[count, n].sum(0)) * scale in one pass (fp32; the peer-memory gradient exchange's reduction)."""
+    lib = _lib.load()
+    if own.dtype != torch.float32 or staged.dtype != torch.float32 or staged.dim() != 2 or staged.shape[1] != own.numel():
+        raise ValueError("hig_b200.mean_slices: own fp32 [n], staged fp32 [count, n]")
+    if not own.is_contiguous() or staged.stride(1) != 1:
+        raise ValueError("hig_b200.mean_slices: contiguous rows required")
+    rc = lib.hig_mean_slices(_ptr(own), _ptr(staged), own.numel(), staged.stride(0), staged.shape[0], float(scale), _stream())
+    _lib.check(rc, "hig_mean_slices")
+    return own
+
+
 def adam_flat(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, p_bf16=None, gnorm2=None, max_norm=0.0):
     """One fused clip + Adam step over flat fp32 buffers (+ bf16 mirror of the new parameters)."""
     lib = _lib.load()

@@ -32,6 +32,25 @@ def _rup(n, m):
 
 
 # ====================================================================================================== flat parameters
+def _alloc_flat_grad(n, dev):
+    """The flat gradient buffer.  HIG_DDP_EXCHANGE=peer (opt-in, see ddp.PeerGradExchange for why it is not the default):
+    under NCCL data parallelism it is allocated as SYMMETRIC memory (same allocation on every rank, mappable by the peers over
+    NVLink / NVSwitch) so that the ranks can average it with copy-engine transfers between the backward graphs; anything
+    that goes wrong here simply leaves an ordinary tensor (NCCL all-reduce)."""
+    import torch.distributed as dist
+    if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl"
+            and os.environ.get("HIG_DDP_EXCHANGE", "nccl") == "peer"):
+        try:
+            import torch.distributed._symmetric_memory as symm
+            g = symm.empty(n, dtype=torch.float32, device=dev)
+            g.zero_()
+            return g, True
+        except Exception as e:  # noqa: BLE001
+            import warnings
+            warnings.warn(f"hig_b200: symmetric memory unavailable ({type(e).__name__}: {e}); gradients go through NCCL")
+    return torch.zeros(n, device=dev, dtype=torch.float32), False
+
+
 class FlatParams:
     """fp32 parameters / gradients of a module as flat buffers (+ bf16 mirror); p.data become views (names unchanged)."""
 
@@ -77,7 +96,7 @@ class FlatParams:
                                     (b0 + li * npl * per_b, b0 + (li + 1) * npl * per_b)])
         self.seg_ranges.append([(rest0, self.seg_bounds[-1][1])])
         self.param = torch.zeros(self.n_total, device=dev, dtype=torch.float32)
-        self.grad = torch.zeros(self.n_total, device=dev, dtype=torch.float32)
+        self.grad, self.grad_symmetric = _alloc_flat_grad(self.n_total, dev)
         self.mirror = torch.zeros(self.n_den, device=dev, dtype=torch.bfloat16)
         self.names = den + self.other_names
         self.shapes = {n: tuple(named[n].shape) for n in self.names}
@@ -698,9 +717,12 @@ class DenoiserGraphFn(torch.autograd.Function):
                 p.grad = None
         plan.d_eps.copy_(d_eps.detach())
         hook = getattr(module, "_grad_segment_hook", None)
+        hook_many = getattr(module, "_grad_segments_hook", None) if hook is not None else None
 
         def seg_done(k):
-            if hook is not None:
+            if hook_many is not None:
+                hook_many(k, [fp.grad[lo:hi] for lo, hi in fp.seg_ranges[k]], fp)
+            elif hook is not None:
                 for lo, hi in fp.seg_ranges[k]:
                     hook(k, fp.grad[lo:hi])
 

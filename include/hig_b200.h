@@ -300,6 +300,11 @@ int hig_masked_mse(const float* pred, const float* tgt, const int* length, int S
 /* *out (double, caller-zeroed) += sum_i x[i]^2 — the global gradient norm of clip_grad_norm_ (mul_ddpm_trainer.py:253) */
 int hig_sumsq(const float* x, long long n, double* out, void* stream);
 
+/* own[i] = (own[i] + sum_{j < count} staged[j * stride + i]) * scale, fp32, n elements: the reduction step of the data-parallel
+ * gradient mean (the reference's DDP all-reduce, tools/train.py:78-82) when the ranks exchange their gradient slices through
+ * NVLink peer memory with the copy engines (hig_b200.ddp.PeerGradExchange) instead of an SM-resident NCCL kernel. */
+int hig_mean_slices(float* own, const float* staged, long long n, long long stride, int count, float scale, void* stream);
+
 /* clip-by-global-norm + torch.optim.Adam step (mul_ddpm_trainer.py:253-255, :291) over flat fp32 buffers in one pass;
  * p_bf16 (nullable) receives the bf16 mirror of the updated parameters (the tcgen05 GEMM operands).  gnorm2 (nullable):
  * device double holding the squared global gradient norm; the gradient is scaled by min(1, max_norm / (norm + 1e-6)). */

@@ -363,3 +363,16 @@ def test_shared_caption_text_side_matches_one_row_per_sequence(cuda):
     assert worst[0] < 2e-2, worst
     te = m._hig_train_engine
     assert any(p.U == 16 for p in te.plans.values()) and any(p.U is None for p in te.plans.values())
+
+
+@pytest.mark.parametrize("n,count", [(1 << 20, 7), (4099, 1), (33, 3), (5_000_001, 1)])
+def test_mean_slices_matches_torch(cuda, n, count):
+    """Reduction step of the peer-memory gradient exchange: own = (own + sum of the staged contributions) / world."""
+    ops = _ops()
+    g = torch.Generator(device=cuda).manual_seed(n)
+    base = torch.randn(n + 4, device=cuda, generator=g)
+    own = base[4:].clone() if n % 2 else base[:n].clone()
+    staged = torch.randn(count, n + 12, device=cuda, generator=g)[:, :n]         # row pitch != n
+    want = (own.double() + staged.double().sum(0)) / (count + 1)
+    ops.mean_slices(own, staged, 1.0 / (count + 1))
+    assert (own.double() - want).abs().max().item() < 1e-6

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--frames", type=int, default=91)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cprofile", action="store_true", help="cProfile the timed loop on rank 0 (host-side cost per call site)")
     ap.add_argument("--sync-debug", action="store_true", help="warn (with a stack) on every host-synchronising CUDA call in the timed loop")
     ap.add_argument("--denoiser-only", action="store_true", help="cap_id model: no CLIP / text-encoder forward")
     ap.add_argument("--pit", action="store_true", help="unlabelled (PIT) mode: 4B sequences per iteration")
@@ -122,7 +123,19 @@ def main():
         torch.cuda.set_sync_debug_mode(1)
     e0.record()
     h0 = time.perf_counter()
+    prof = None
+    if args.cprofile and rank == 0:
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     evs = [it() for _ in range(args.iters)]
+    if prof is not None:
+        prof.disable()
+        import io
+        import pstats
+        buf = io.StringIO()
+        pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(45)
+        print(buf.getvalue()[:9000], file=sys.stderr)
     host_ms = (time.perf_counter() - h0) * 1e3 / args.iters      # time the host needs to ISSUE an iteration (no sync inside)
     e1.record()
     if args.sync_debug:
@@ -147,6 +160,18 @@ def main():
                           "hig_launches_per_iter": (_lib.launch_count() - l0) / args.iters,
                           "denoiser_fwd_bwd_tflops": fl / (ms * 1e-3) / 1e12,
                           "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+    if world > 1 and os.environ.get("HIG_DDP_TRACE") == "1" and rank == 0:
+        for px in getattr(enc.reducer, "_peer", {}).values():
+            tr_ = px.trace if px else None
+            if not tr_:
+                continue
+            n_last = next(i for i in range(len(tr_) - 1, -1, -1) if tr_[i][0] == "join")
+            start = max(i for i in range(n_last) if tr_[i][0] == "join") + 1 if any(t[0] == "join" for t in tr_[:n_last]) else 0
+            t0 = tr_[start][1]
+            print("peer exchange timeline of the last iteration (ms after the first segment was ready):", file=sys.stderr)
+            for kind, a, b, c in tr_[start:n_last + 1]:
+                print(f"  {kind:8s} ready {t0.elapsed_time(a):8.3f}  barrier passed {t0.elapsed_time(b):8.3f}  done {t0.elapsed_time(c):8.3f}",
+                      file=sys.stderr)
     if world > 1:
         dist.destroy_process_group()
 
