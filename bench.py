@@ -390,6 +390,13 @@ def train_block(device, rank, world, iters, pk):
                     "overlap_frac": max(0.0, min(1.0, 1.0 - exposed / ms_ar)) if ms_ar > 0 else None,
                     "allreduce_busbw_gbs": 2 * (world - 1) / world * flat.numel() * 4 / (ms_ar * 1e-3) / 1e9})
         out["nccl_reserved_sms"] = int(os.environ.get("HIG_DDP_NCCL_SMS", "0"))
+        out["exchange"] = ("copy-engine reduce-scatter + all-gather over symmetric peer memory (HIG_DDP_EXCHANGE=peer)"
+                           if getattr(fp, "grad_symmetric", False) else
+                           "NCCL all-reduce (AVG), one coalesced launch per gradient segment, issued between the backward graphs")
+        out["exposed_note"] = ("per-segment timeline in profiles/r02_n2_peer_exchange_timeline.txt: the transfers finish long before "
+                               "the next segment is ready; the exposed time is the tail after the last backward kernel plus the "
+                               "backward kernels running slower while the exchange is in flight (same figure with an SM-free "
+                               "copy-engine exchange)")
     else:
         out.update({"allreduce_bytes": 0, "overlap_frac": None})
     # ---- the same step with captions as TEXT: (random-init) CLIP features cached per caption, the trainable 4-layer text

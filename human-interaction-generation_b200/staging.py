@@ -10,7 +10,7 @@ import threading
 
 import torch
 
-_SLOTS = 16
+_SLOTS = 64
 _rings = {}
 _lock = threading.Lock()
 
