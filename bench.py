@@ -306,19 +306,25 @@ def train_block(device, rank, world, iters, pk):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        evs[0].record()
+        for i in range(n):
             tr.forward(next(feed))
             loss = tr.update_async()["loss_mot_rec"]
-        e1.record()
+            evs[i + 1].record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / n
+        ms = evs[0].elapsed_time(evs[n]) / n
+        # the median iteration: what the comparisons between two runs use (a single allocator or clock hiccup of ~100 ms in
+        # one of the runs otherwise decides the sign of their difference)
+        med = float(np.median([evs[i].elapsed_time(evs[i + 1]) for i in range(n)]))
         if world > 1:
-            tt = torch.tensor([ms], device=device, dtype=torch.float64)
+            tt = torch.tensor([ms, med], device=device, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = tt.item()
+            ms, med = tt.tolist()
+        medians.append(med)
         return ms, float(loss)
+
+    medians = []
 
     out = {"workload": f"configs[3]: DDP training step, {B} pairs/GPU x {T} frames, labelled, caption ids (denoiser + loss + "
                        f"clip + Adam; text encoder not on this path)", "iters": iters, "optimizer": "hig_b200.optim.FusedAdam"}
@@ -355,9 +361,10 @@ def train_block(device, rank, world, iters, pk):
     else:
         out["ddp_check"] = None
     ms, loss = run(iters)
+    med_on = medians[-1]
     fl = flops_per_denoiser_step(2 * B, T) * 3
     tf = fl / (ms * 1e-3) / 1e12
-    out.update({"ms_per_iter": ms, "pairs_per_s": world * B / ms * 1e3, "loss": loss, "denoiser_fwd_bwd_tflops": tf,
+    out.update({"ms_per_iter": ms, "ms_per_iter_median": med_on, "pairs_per_s": world * B / ms * 1e3, "loss": loss, "denoiser_fwd_bwd_tflops": tf,
                 "roofline_frac": tf / pk["bf16_tflops_sustained"],
                 "roofline_basis": f"3 x {fl / 3e9:.1f} algorithmic GFLOP (forward + 2x backward, SURVEY §8d) per iteration and GPU "
                                   f"over the CUDA-event time, against the {pk['source']} sustained bf16 peak",
@@ -371,6 +378,7 @@ def train_block(device, rank, world, iters, pk):
         out["allreduce_calls_per_iter"] = (red.calls - c0) / n_it
         set_hooks(False)
         ms_off, _ = run(iters)
+        med_off = medians[-1]
         set_hooks(True)
         # the all-reduce alone, same buffer, same collective
         flat = fp.grad[:fp.n_den]
@@ -385,8 +393,9 @@ def train_block(device, rank, world, iters, pk):
         e1.record()
         torch.cuda.synchronize()
         ms_ar = e0.elapsed_time(e1) / 5
-        exposed = max(ms - ms_off, 0.0)
-        out.update({"ms_per_iter_allreduce_off": ms_off, "exposed_allreduce_ms": exposed, "allreduce_alone_ms": ms_ar,
+        exposed = max(med_on - med_off, 0.0)         # medians, see run()
+        out.update({"ms_per_iter_allreduce_off": ms_off, "ms_per_iter_allreduce_off_median": med_off,
+                    "exposed_allreduce_ms": exposed, "allreduce_alone_ms": ms_ar,
                     "overlap_frac": max(0.0, min(1.0, 1.0 - exposed / ms_ar)) if ms_ar > 0 else None,
                     "allreduce_busbw_gbs": 2 * (world - 1) / world * flat.numel() * 4 / (ms_ar * 1e-3) / 1e9})
         out["nccl_reserved_sms"] = int(os.environ.get("HIG_DDP_NCCL_SMS", "0"))
@@ -461,21 +470,22 @@ def train_with_captions(device, rank, world, iters, B, T):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    evs[0].record()
+    for i in range(iters):
         tr.forward(next(feed))
         loss = tr.update_async()["loss_mot_rec"]
-    e1.record()
+        evs[i + 1].record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    ms = evs[0].elapsed_time(evs[iters]) / iters
+    med = float(__import__("numpy").median([evs[i].elapsed_time(evs[i + 1]) for i in range(iters)]))
     if world > 1:
-        tt = torch.tensor([ms], device=device, dtype=torch.float64)
+        tt = torch.tensor([ms, med], device=device, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = tt.item()
+        ms, med = tt.tolist()
     return {"workload": f"{B} pairs/GPU x {T} frames, labelled, captions as text ({len(set(batch[0] + batch[1]))} distinct among "
                         f"{2 * B}; text encoder: {m.text_encoder_kind})", "iters": iters, "ms_per_iter": ms,
-            "pairs_per_s": world * B / ms * 1e3, "loss": float(loss)}
+            "ms_per_iter_median": med, "pairs_per_s": world * B / ms * 1e3, "loss": float(loss)}
 
 
 def main():
