@@ -304,6 +304,9 @@ def train_block(device, rank, world, iters, pk):
             tr.forward(next(feed))
             tr.update_async()
         torch.cuda.synchronize()
+        import gc
+        gc.collect()
+        gc.freeze()          # as DDPMMulTrainer.train does after its first iterations: no full collections inside the loop
         if world > 1:
             dist.barrier()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
@@ -468,6 +471,9 @@ def train_with_captions(device, rank, world, iters, B, T):
         tr.forward(next(feed))
         tr.update_async()
     torch.cuda.synchronize()
+    import gc
+    gc.collect()
+    gc.freeze()
     if world > 1:
         dist.barrier()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]

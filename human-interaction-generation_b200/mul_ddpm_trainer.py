@@ -232,6 +232,7 @@ class DDPMMulTrainer(object):
         log_path = getattr(opt, "log_file", None) or os.path.join(getattr(opt, "model_dir", "."), "train_log.jsonl")
         max_iters = getattr(opt, "max_iters", None)
         acc, n_acc = None, 0
+        frozen, it0 = False, it
         self.mean_losses = []
         for epoch in range(cur_epoch, opt.num_epochs):
             self.train_mode()
@@ -243,6 +244,14 @@ class DDPMMulTrainer(object):
                 acc = loss.clone() if acc is None else acc + loss
                 n_acc += 1
                 it += 1
+                if not frozen and it - it0 >= 3:
+                    # everything the loop keeps alive exists now (graphs, plans, optimizer state: ~10^5 Python objects): take
+                    # it out of the cyclic collector's reach, or a full collection stalls the host for ~100 ms every few
+                    # hundred iterations — longer than the work queued on the GPU, which then idles
+                    import gc
+                    gc.collect()
+                    gc.freeze()
+                    frozen = True
                 if it % opt.log_every == 0:
                     mean = float(acc) / n_acc            # the only host synchronisation of the loop
                     acc, n_acc = None, 0

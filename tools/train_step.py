@@ -98,6 +98,9 @@ def main():
     for _ in range(args.warmup):
         it()
     torch.cuda.synchronize()
+    import gc
+    gc.collect()
+    gc.freeze()
     if world > 1:
         dist.barrier()
     # host time to ISSUE one iteration while the launch queue is empty (later iterations block on the queue depth: the host
