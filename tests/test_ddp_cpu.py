@@ -58,6 +58,16 @@ def _w_segments(rank, world):
     want = torch.arange(100, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
     assert torch.allclose(flat, want)
     assert red.calls == 3 and red.bytes_reduced == 400
+    # several ranges that became final together (a layer's parameters + its share of the emb-linears): on gloo every range
+    # is reduced on its own (NCCL coalesces them into one launch); a FlatParams without a symmetric gradient buffer — or
+    # none at all — takes this path too
+    flat2 = torch.arange(60, dtype=torch.float32) * (rank + 2)
+    red.segments_ready(7, [flat2[0:16], flat2[40:60], flat2[20:20]], None)
+    red.finish()
+    mean_scale = sum(r + 2 for r in range(world)) / world
+    assert torch.allclose(flat2[0:16], torch.arange(0, 16, dtype=torch.float32) * mean_scale)
+    assert torch.allclose(flat2[40:60], torch.arange(40, 60, dtype=torch.float32) * mean_scale)
+    assert torch.equal(flat2[16:40], torch.arange(16, 40, dtype=torch.float32) * (rank + 2))      # untouched
 
 
 def _w_other_bucket_and_broadcast(rank, world):
@@ -231,3 +241,18 @@ def test_flat_gradient_layout_covers_every_denoiser_parameter():
     r = gr.region(first, n_styl * 1024 * 2048, (n_styl * 1024, 2048))
     r[1024 * 5:1024 * 6].fill_(5.0)
     assert float(gr.views["temporal_decoder_blocks.1.ca_block.proj_out.emb_layers.1.weight"].min()) == 5.0
+
+
+def test_peer_exchange_slices_partition_every_range():
+    """PeerGradExchange._cuts: every element of a gradient range belongs to exactly one rank, slices start on 16-byte
+    boundaries relative to the range start (copy-engine transfers), empty slices are allowed for tiny ranges."""
+    import hig_b200  # noqa: F401
+    from hig_b200.ddp import PeerGradExchange
+    for lo, hi in ((0, 1), (8, 8 + 13), (1000, 1000 + 4096), (64, 64 + 9_437_187), (5, 5 + 7)):
+        for world in (2, 3, 8):
+            cuts = PeerGradExchange._cuts(lo, hi, world)
+            assert len(cuts) == world + 1 and cuts[0] == lo and cuts[-1] == hi
+            assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+            assert all((c - lo) % 4 == 0 or c == hi for c in cuts)
+            sizes = [b - a for a, b in zip(cuts, cuts[1:])]
+            assert sum(sizes) == hi - lo and max(sizes) <= -(-(hi - lo) // world) + 3

@@ -177,3 +177,45 @@ def test_clip_stub_is_explicit(monkeypatch):
         assert any("RANDOM-INIT" in str(x.message) for x in w)
         m = _model(cap_id=False)
         assert m.text_encoder_kind == "stub" and m._clip_dtype == torch.float32
+
+
+def test_encode_unique_returns_distinct_captions_and_an_index():
+    """forward() hands the training engine one text row per DISTINCT caption + an index per sequence; expanding it must give
+    encode_text's output, and the EOT positions come from a per-caption cache that agrees with the tokeniser."""
+    m = _model(cap_id=False).eval()
+    caps = ["a person pushes the other person", "two people shake hands", "a person pushes the other person",
+            "a person pushes the other person", "two people shake hands", "a person hugs the other person"]
+    with torch.no_grad():
+        pu, ou, idx = m._encode_unique(caps, "cpu")
+        p, o = m.encode_text(caps, "cpu")
+    assert pu.shape[0] == ou.shape[0] == 3 and idx.tolist() == [0, 1, 0, 0, 1, 2]
+    assert torch.equal(pu.index_select(0, idx), p) and torch.equal(ou.index_select(0, idx), o)
+    want = m._tokenize(caps, truncate=True).argmax(dim=-1)
+    assert torch.equal(m._eot_index(caps, "cpu"), want) and torch.equal(m._eot_index(caps, "cpu"), want)     # cold, then cached
+    assert set(m._eot_cache) == set(caps)
+    # all captions distinct: no index
+    with torch.no_grad():
+        assert m._encode_unique(caps[:2], "cpu")[2] is None
+
+
+def test_training_losses_terms_compute_mse_lazily():
+    from hig_b200.gaussian_diffusion import _Terms
+    noise, pred = torch.randn(4, 5, 6), torch.randn(4, 5, 6)
+    t = _Terms(target=noise, pred=pred)
+    assert "mse" in t and len(t) == 3 and not dict.__contains__(t, "mse")        # advertised, not computed yet
+    assert t["pred"] is pred and t["target"] is noise and not dict.__contains__(t, "mse")
+    want = ((noise - pred) ** 2).mean(dim=[1, 2])
+    assert torch.equal(t["mse"], want) and dict.__contains__(t, "mse")
+    assert sorted(t.keys()) == ["mse", "pred", "target"] and torch.equal(dict(t.items())["mse"], want)
+    assert torch.equal(_Terms(target=noise, pred=pred).get("mse"), want)
+
+
+def test_stage_falls_back_to_plain_copies_off_gpu():
+    """staging.stage: pinned asynchronous copies on CUDA; for a CPU target (and for tensors that are not on the host) it is
+    an ordinary .to() with the optional cast."""
+    from hig_b200.staging import stage
+    a = torch.arange(6, dtype=torch.int32)
+    b = stage(a, "cpu", torch.long)
+    assert b.dtype == torch.long and b.tolist() == list(range(6))
+    assert stage([1.5, 2.5], torch.device("cpu"), torch.float32).tolist() == [1.5, 2.5]
+    assert stage(torch.empty(0), "cpu").numel() == 0
