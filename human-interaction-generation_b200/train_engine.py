@@ -522,10 +522,18 @@ class _Plan:
                 if self.U:       # sequences that share a caption: their dA add up
                     dA = torch.zeros(SU, H, HEAD_DIM, HEAD_DIM, device=dev, dtype=f32).index_add_(0, self.text_idx, dA)
                 kv = st.kv[li]
-                d_kv = new(SU * N, 2 * D)
                 kv_b = greg(mp + "key.bias", 2 * D, (2 * D,))
-                ops.eff_attn_bwd(ops.ATTN_KV_ONLY, SU, N, H, k=kv[:, :D], v=kv[:, D:], dk=d_kv[:, :D], dv=d_kv[:, D:], dA=dA,
-                                 k_sum=kv_b[:D], v_sum=kv_b[D:])
+                if N == 1 and not det:
+                    # one text token (caption ids, :561-566): its time softmax is exactly 1, so dK == 0 and
+                    # dV[l] = sum_d dA[d, l] — a reduction of dA instead of a launch of the attention backward that spends
+                    # 58 us (ncu) loading 64 x 64 fp32 matrices to multiply them with a column of ones
+                    d_kv = torch.zeros(SU, 2 * D, device=dev, dtype=bf)
+                    d_kv[:, D:].copy_(dA.view(SU, H, HEAD_DIM, HEAD_DIM).sum(dim=2).view(SU, D))
+                    ops.colsum(d_kv[:, D:], kv_b[D:])
+                else:
+                    d_kv = new(SU * N, 2 * D)
+                    ops.eff_attn_bwd(ops.ATTN_KV_ONLY, SU, N, H, k=kv[:, :D], v=kv[:, D:], dk=d_kv[:, :D], dv=d_kv[:, D:],
+                                     dA=dA, k_sum=kv_b[:D], v_sum=kv_b[D:])
                 Dt = st.xf.shape[1]
                 d_tn = linear_bwd(d_kv, st.tn[li], W[f"l{li}.ca.kv.w"], greg(mp + "key.weight", 2 * D * Dt, (2 * D, Dt)), None)
                 ops.ln_film_silu_bwd(st.xf, W[pfx + ".tln.w"], W[pfx + ".tln.b"], d_tn, d_xf, N, dx_accumulate=True,
