@@ -376,3 +376,36 @@ def test_mean_slices_matches_torch(cuda, n, count):
     want = (own.double() + staged.double().sum(0)) / (count + 1)
     ops.mean_slices(own, staged, 1.0 / (count + 1))
     assert (own.double() - want).abs().max().item() < 1e-6
+
+
+def test_single_token_text_backward_shortcut_matches_the_kernel(cuda, monkeypatch):
+    """Caption ids give ONE text token per sequence: the engine then takes dV = sum_d dA[d, :] and dK = 0 instead of launching
+    the K/V attention backward.  HIG_DETERMINISTIC=1 keeps the kernel: gradients of the text-side parameters (key / value
+    projections, text_norm) and of xf_out must agree."""
+    import weights
+    L, S, T = 2, 8, 40
+    m = _model(cuda, layers=L)
+    m.cap_id = False
+    m.train()
+    inp = weights.make_inputs(9, S, T, n_text=1, lengths=[40, 33, 12, 40, 40, 33, 12, 40])
+    tgt = weights.make_noise(9, 0, S, T)[0].to(cuda)
+    g = lambda k: inp[k].to(cuda)
+    res = {}
+    for det in ("1", "0"):
+        monkeypatch.setenv("HIG_DETERMINISTIC", det)
+        m.zero_grad(set_to_none=True)
+        xfo = g("xf_out").requires_grad_(True)
+        pred = m(g("x"), g("t"), length=g("length"), xf_proj=g("xf_proj"), xf_out=xfo)
+        ((pred - tgt) ** 2).mean().backward()
+        res[det] = (xfo.grad.clone(), {n: p.grad.clone() for n, p in m.named_parameters()
+                                       if p.grad is not None and (".ca_block.key" in n or ".ca_block.value" in n or "text_norm" in n)})
+    (xa, pa), (xb, pb) = res["1"], res["0"]
+    assert pa and set(pa) == set(pb)
+    assert rel(xb, xa) < 2e-2
+    for n in pa:
+        if n.endswith("key.weight") or n.endswith("key.bias"):
+            # K half: analytically zero (a constant along a one-token time axis); the kernel leaves rounding noise, the shortcut 0
+            scale = max(pa[n.replace("key", "value")].abs().max().item(), 1e-12)
+            assert pa[n].abs().max().item() < 1e-3 * scale and pb[n].abs().max().item() < 1e-3 * scale, n
+        elif pa[n].norm() > 1e-9:
+            assert rel(pb[n], pa[n]) < 2e-2, (n, rel(pb[n], pa[n]))
