@@ -737,3 +737,43 @@ def test_encode_text_on_kernels_matches_torch_path(cuda, precision, monkeypatch)
 def _lib_count():
     from hig_b200 import _lib
     return _lib.launch_count()
+
+
+def test_forward_with_caption_strings_equals_forward_with_encoded_text(cuda, monkeypatch):
+    """The reference's call `model(x, t, length=..., text=[captions])` (interaction_transformer.py:577-590): forward() encodes
+    the distinct captions once and expands them by index; the result must be the call with encode_text's tensors passed in,
+    without autograd (sampling / evaluation) and with it (training engine, shared-caption text side)."""
+    import hig_b200  # noqa: F401
+    from hig_b200.interaction_transformer import MotionInteractionTransformer
+    monkeypatch.setenv("HIG_CLIP_STUB", "1")
+    torch.manual_seed(0)
+    m = MotionInteractionTransformer(263, num_frames=196, num_layers=1, cap_id=False).to(cuda)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if not n.startswith("clip.") and p.abs().max() == 0 and "norm.bias" not in n:
+                p.copy_(torch.randn_like(p) * 0.02)
+    S, T = 36, 24
+    caps = ["two people shake hands", "a person pushes the other person", "a person hugs the other person"]
+    text = [caps[(i * 7) % 3] for i in range(S)]
+    g = torch.Generator(device=cuda).manual_seed(1)
+    x = torch.randn(S, T, 263, device=cuda, generator=g)
+    t = torch.randint(0, 1000, (S,), device=cuda, generator=g)
+    length = torch.randint(5, T + 1, (S,), device=cuda, generator=g)
+    m.eval()
+    with torch.no_grad():
+        a = m(x, t, length=length, text=text)
+        xp, xo = m.encode_text(text, cuda)
+        b = m(x, t, length=length, xf_proj=xp, xf_out=xo)
+    assert torch.equal(a, b)
+    # training: 3 distinct captions in a bucket of 16 < 36 sequences -> the shared-caption plan; against one text row per sequence
+    m.train()
+    monkeypatch.setenv("HIG_TEXT_GRAPH", "0")
+    out = {}
+    for dedup in ("1", "0"):
+        monkeypatch.setenv("HIG_TRAIN_TEXT_DEDUP", dedup)
+        m.zero_grad(set_to_none=True)
+        y = m(x, t, length=length, text=text)
+        y.square().mean().backward()
+        out[dedup] = (y.detach().clone(), m.text_ln.weight.grad.clone(), m.temporal_decoder_blocks[0].ca_block.value.weight.grad.clone())
+    assert torch.equal(out["1"][0], out["0"][0])
+    assert _rel(out["1"][1], out["0"][1]) < 2e-2 and _rel(out["1"][2], out["0"][2]) < 2e-2
