@@ -14,7 +14,6 @@ operand packing) replayed for the remaining steps; the timestep lives in device 
 generated in-kernel (Philox4x32-10) unless a noise sequence is injected for parity runs.
 """
 import enum
-import math
 
 import numpy as np
 import torch as th

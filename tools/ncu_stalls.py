@@ -1,6 +1,5 @@
 """Top warp-stall reasons + instruction mix per kernel of ncu --set full reports (first launch of each kernel name).
 usage: python tools/ncu_stalls.py <reports...>"""
-import collections
 import csv
 import io
 import subprocess

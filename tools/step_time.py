@@ -1,7 +1,6 @@
 """ms per denoiser+posterior step at the C2 shape via CUDA-graph replay (the production path), 200 steps."""
 import os
 import sys
-import time
 
 import torch
 
